@@ -1,0 +1,104 @@
+"""ctypes binding of libmvm_b200.so (C ABI declared in include/mvm_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call returns a non-zero
+status this module raises.  Build it with ``python -m e2e_multi_view_matching_b200.build``
+(nvcc, sm_100a) -- __graft_entry__.build() does that.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmvm_b200.so')
+
+MVM_MAX_LAYERS = 64
+MVM_MAX_VIEWS = 8
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [('w_qkv', _fp), ('b_qkv', _fp), ('w_merge', _fp), ('b_merge', _fp),
+                ('w_mlp0', _fp), ('b_mlp0', _fp), ('w_mlp1', _fp), ('b_mlp1', _fp),
+                ('is_cross', C.c_int)]
+
+
+class MatcherWeights(C.Structure):
+    _fields_ = [('n_layers', C.c_int),
+                ('kenc_w', _fp * 5), ('kenc_b', _fp * 5),
+                ('layers', LayerWeights * MVM_MAX_LAYERS),
+                ('w_final', _fp), ('b_final', _fp),
+                ('bin_score', C.c_float),
+                ('has_conf', C.c_int),
+                ('conf_wf0', _fp), ('conf_bf0', _fp),
+                ('conf_wf1', _fp), ('conf_bf1', _fp),
+                ('conf_wc0', _fp), ('conf_bc0', _fp),
+                ('conf_wc1', _fp), ('conf_bc1', _fp),
+                ('conf_wl', _fp), ('conf_bl', C.c_float)]
+
+
+class PairIO(C.Structure):
+    _fields_ = [('view_a', C.c_int), ('view_b', C.c_int),
+                ('matches_a', _fp), ('matches_b', _fp),
+                ('mscores_a', _fp), ('mscores_b', _fp),
+                ('scores', _fp), ('conf', _fp)]
+
+
+class MvmError(RuntimeError):
+    pass
+
+
+_STATUS = {1: 'invalid argument', 2: 'kernel launch failure', 3: 'workspace too small'}
+_lib = None
+
+
+def lib():
+    """Load the shared library once; fail loudly when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MvmError(
+            'libmvm_b200.so not found at %s -- the CUDA extension is required (no CPU fallback). '
+            'Build it with: python -m e2e_multi_view_matching_b200.build' % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.mvm_version.restype = C.c_char_p
+    L.mvm_matcher_workspace_bytes.restype = C.c_size_t
+    L.mvm_matcher_workspace_bytes.argtypes = [C.c_int] * 5
+    L.mvm_matcher_forward.restype = C.c_int
+    L.mvm_matcher_forward.argtypes = [
+        C.POINTER(MatcherWeights), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _fp, _fp, _fp,
+        C.c_float, C.c_float, C.c_int, C.c_float, C.POINTER(PairIO), C.c_int, _fp, C.c_size_t, _fp]
+    L.mvm_linear.restype = C.c_int
+    L.mvm_linear.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int,
+                             _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp]
+    L.mvm_attention.restype = C.c_int
+    L.mvm_attention.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, _fp]
+    L.mvm_sinkhorn_workspace_floats.restype = C.c_size_t
+    L.mvm_sinkhorn_workspace_floats.argtypes = [C.c_int, C.c_int, C.c_int]
+    for name in ('mvm_log_optimal_transport', 'mvm_log_optimal_transport_ref'):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp]
+    L.mvm_extract_matches.restype = C.c_int
+    L.mvm_extract_matches.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp,
+                                      _fp, _fp, _fp]
+    _lib = L
+    return L
+
+
+def check(status, what):
+    if status != 0:
+        raise MvmError('%s failed: %s (status %d)' % (what, _STATUS.get(status, 'unknown'), status))
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (or NULL for None)."""
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), 'libmvm_b200 needs contiguous CUDA tensors'
+    return C.c_void_p(t.data_ptr())

@@ -1,0 +1,66 @@
+// Shared device/host helpers for the sm_100a kernels of the matcher + pose hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MVM_OK 0
+#define MVM_ERR_INVALID 1
+#define MVM_ERR_LAUNCH 2
+#define MVM_ERR_WORKSPACE 3
+
+#define MVM_CHECK_LAUNCH()                                                        \
+  do {                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess) {                                                     \
+      fprintf(stderr, "[mvm_b200] launch failed at %s:%d: %s\n", __FILE__,        \
+              __LINE__, cudaGetErrorString(e__));                                 \
+      return MVM_ERR_LAUNCH;                                                      \
+    }                                                                             \
+  } while (0)
+
+#define MVM_REQUIRE(cond)                                                         \
+  do {                                                                            \
+    if (!(cond)) {                                                                \
+      fprintf(stderr, "[mvm_b200] invalid argument at %s:%d: %s\n", __FILE__,     \
+              __LINE__, #cond);                                                   \
+      return MVM_ERR_INVALID;                                                     \
+    }                                                                             \
+  } while (0)
+
+static inline int mvm_div_up(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- GEMM descriptor shared by the SIMT and tcgen05 paths ------------------------------
+// C[M,N] = act(alpha * [A | A2][M,K] * W[N,K]^T + bias[N]) + R[M,N]
+// A covers k in [0,K1), A2 covers k in [K1,K) (concat-by-K-split; A2 == nullptr -> K1 == K).
+struct GemmDesc {
+  const float* A;  int lda;
+  const float* A2; int lda2; int K1;
+  const float* W;  int ldw;
+  const float* bias;
+  const float* R;  int ldr;
+  float* C;        int ldc;
+  int M, N, K;
+  float alpha;
+  int relu;
+  int batch;                                   // gridDim.z
+  long long sA, sA2, sW, sR, sC;               // per-batch element strides
+};
+
+int launch_gemm_simt(const GemmDesc& g, cudaStream_t stream);

@@ -1,0 +1,58 @@
+// Internal launch prototypes (host side) of the matcher kernels.
+#pragma once
+#include "common.cuh"
+
+constexpr int MVM_MAX_PAIRS = 28;  // C(8,2)
+
+// Per-pair table passed BY VALUE to the pair-stage kernels (score GEMM, Sinkhorn, match
+// extraction, confidence head): one launch covers every (pair, batch) problem and the
+// whole forward stays CUDA-graph capturable (no host->device table copies).
+struct PairTable {
+  int n_pairs;
+  int n_views;                 // views per tuple (slot of view t in tuple b = b*n_views + t)
+  int a[MVM_MAX_PAIRS], b[MVM_MAX_PAIRS];   // view ids, a < b
+  int m[MVM_MAX_PAIRS], n[MVM_MAX_PAIRS];   // true keypoint counts of a and b
+  float* scores[MVM_MAX_PAIRS];             // [batch, m+1, n+1]
+  int64_t* matches_a[MVM_MAX_PAIRS];        // [batch, m]
+  int64_t* matches_b[MVM_MAX_PAIRS];        // [batch, n]
+  float* ms_a[MVM_MAX_PAIRS];
+  float* ms_b[MVM_MAX_PAIRS];
+  float* conf[MVM_MAX_PAIRS];               // [batch, m] (or nullptr)
+  long long ws_off[MVM_MAX_PAIRS];          // float offset of this pair's (u,v) scratch
+};
+typedef PairTable SinkhornTable;
+
+int launch_kenc_front(const float* kpts, const float* kscores, const float* const* w,
+                      const float* const* b, float* h3, int n_points, float img_w, float img_h,
+                      cudaStream_t stream);
+int launch_transpose_cn(const float* in, float* out, int n_views_total, int C, int n_pad,
+                        cudaStream_t stream);
+
+struct AttnSegs {
+  int n_views;
+  int counts[8];
+};
+int launch_attention_simt(const float* qkv, float* out, int batch, int n_pad, AttnSegs segs,
+                          int is_cross, cudaStream_t stream);
+
+// scores[p][bi] inner block = mdesc[a] . mdesc[b]^T * alpha   (mdesc: [views, n_pad, 256])
+int launch_score_gemm_simt(const float* mdesc, int n_pad, const PairTable& tab, int batch,
+                           float alpha, cudaStream_t stream);
+
+int launch_sinkhorn_ref(const SinkhornTable& tab, int batch, float bin_score, int iters,
+                        float* ws, cudaStream_t stream);
+int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
+                    cudaStream_t stream);
+size_t sinkhorn_ws_floats(int n_pairs, int batch, int n_pad);
+
+// idx_ws: ints [n_pairs*batch*2*n_pad] + floats; see match.cu
+int launch_extract_matches(const PairTable& tab, int batch, int n_pad, float thresh, int* idx_ws,
+                           cudaStream_t stream);
+
+// feat [n_pairs*batch*n_pad, 512] = cat(mdesc_a[i], mdesc_b[match(i)]); sc [rows] = Z[i, match(i)]
+int launch_conf_gather(const float* mdesc, const PairTable& tab, int batch, int n_pad, float* feat,
+                       float* sc, cudaStream_t stream);
+int launch_conf_c0(const float* sc, const float* w, const float* b, float* out, long long rows,
+                   cudaStream_t stream);
+int launch_conf_final(const float* h, const float* wl, float bl, const PairTable& tab, int batch,
+                      int n_pad, cudaStream_t stream);

@@ -1,0 +1,231 @@
+// Host-side sequencing of the matcher forward + the C ABI (include/mvm_b200.h).
+// Mirrors MultiViewMatcher.multi_match in eval mode (multi_view_matcher.py:217-320) on
+// point-major activations: kenc -> L x {qkv, attention, merge, mlp} -> final_proj ->
+// per pair {score GEMM, Sinkhorn, mutual NN, confidence head}.  Every launch is
+// stream-ordered; no host sync, no allocation: the whole call is CUDA-graph capturable.
+#include "../../include/mvm_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+struct Workspace {
+  float *DT, *H3, *H4, *X, *QKV, *MSG, *MRG, *H, *MD;
+  float* sink_ws;
+  int* match_ws;
+  float *FEAT, *SC, *CF1, *CF2, *CC0, *CC1;
+  size_t total;
+};
+
+size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+Workspace carve(char* base, int batch, int n_views, int n_pad, int n_pairs, int has_conf) {
+  Workspace w;
+  size_t off = 0;
+  const size_t rows = (size_t)batch * n_views * n_pad;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes);
+    return p;
+  };
+  w.DT = (float*)take(rows * 256 * 4);
+  w.H3 = (float*)take(rows * 128 * 4);
+  w.H4 = (float*)take(rows * 256 * 4);
+  w.X = (float*)take(rows * 256 * 4);
+  w.QKV = (float*)take(rows * 768 * 4);
+  w.MSG = (float*)take(rows * 256 * 4);
+  w.MRG = (float*)take(rows * 256 * 4);
+  w.H = (float*)take(rows * 512 * 4);
+  w.MD = (float*)take(rows * 256 * 4);
+  const size_t probs = (size_t)n_pairs * batch;
+  w.sink_ws = (float*)take(sinkhorn_ws_floats(n_pairs, batch, n_pad) * 4);
+  w.match_ws = (int*)take(probs * 3 * (size_t)n_pad * 4);
+  const size_t crow = has_conf ? probs * n_pad : 0;
+  w.FEAT = (float*)take(crow * 512 * 4);
+  w.SC = (float*)take(crow * 4);
+  w.CF1 = (float*)take(crow * 512 * 4);
+  w.CF2 = (float*)take(crow * 256 * 4);
+  w.CC0 = (float*)take(crow * 256 * 4);
+  w.CC1 = (float*)take(crow * 256 * 4);
+  w.total = off;
+  return w;
+}
+
+GemmDesc make_gemm(const float* A, int lda, const float* W, int K, const float* bias, float* C,
+                   int ldc, int M, int N, int relu) {
+  GemmDesc g;
+  g.A = A; g.lda = lda; g.A2 = nullptr; g.lda2 = 0; g.K1 = K;
+  g.W = W; g.ldw = K; g.bias = bias; g.R = nullptr; g.ldr = 0;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = 1.f; g.relu = relu;
+  g.batch = 1; g.sA = g.sA2 = g.sW = g.sR = g.sC = 0;
+  return g;
+}
+
+int run_gemm(const GemmDesc& g, cudaStream_t s) { return launch_gemm_simt(g, s); }
+
+#define MVM_TRY(x)            \
+  do {                        \
+    int rc__ = (x);           \
+    if (rc__ != MVM_OK) return rc__; \
+  } while (0)
+
+int fill_pair_table(PairTable& tab, const mvm_pair_io* pairs, int n_pairs, int n_views,
+                    const int* counts, int batch) {
+  MVM_REQUIRE(n_pairs >= 1 && n_pairs <= MVM_MAX_PAIRS);
+  tab.n_pairs = n_pairs;
+  tab.n_views = n_views;
+  long long off = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    const int a = pairs[p].view_a, b = pairs[p].view_b;
+    MVM_REQUIRE(a >= 0 && b >= 0 && a < n_views && b < n_views && a != b);
+    tab.a[p] = a; tab.b[p] = b;
+    tab.m[p] = counts[a]; tab.n[p] = counts[b];
+    tab.scores[p] = pairs[p].scores;
+    tab.matches_a[p] = pairs[p].matches_a; tab.matches_b[p] = pairs[p].matches_b;
+    tab.ms_a[p] = pairs[p].mscores_a; tab.ms_b[p] = pairs[p].mscores_b;
+    tab.conf[p] = pairs[p].conf;
+    tab.ws_off[p] = off;
+    off += (long long)batch * (counts[a] + counts[b] + 2);
+  }
+  return MVM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mvm_version(void) { return "mvm_b200 0.1 sm_100a"; }
+
+size_t mvm_matcher_workspace_bytes(int batch, int n_views, int n_pad, int n_pairs, int has_conf) {
+  return carve(nullptr, batch, n_views, n_pad, n_pairs, has_conf).total;
+}
+
+int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, int n_pad,
+                        const int* counts, const float* kpts, const float* kscores,
+                        const float* desc, float img_w, float img_h, int sinkhorn_iters,
+                        float match_threshold, const mvm_pair_io* pairs, int n_pairs,
+                        void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  MVM_REQUIRE(w && counts && kpts && kscores && desc && pairs && workspace);
+  MVM_REQUIRE(batch >= 1 && n_views >= 2 && n_views <= MVM_MAX_VIEWS);
+  MVM_REQUIRE(n_pad >= 64 && n_pad % 64 == 0);
+  MVM_REQUIRE(w->n_layers >= 0 && w->n_layers <= MVM_MAX_LAYERS);
+  for (int t = 0; t < n_views; ++t) MVM_REQUIRE(counts[t] >= 1 && counts[t] <= n_pad);
+  Workspace ws = carve((char*)workspace, batch, n_views, n_pad, n_pairs, w->has_conf);
+  if (ws.total > workspace_bytes) return MVM_ERR_WORKSPACE;
+
+  const int V = batch * n_views;
+  const int rows = V * n_pad;
+  AttnSegs segs;
+  segs.n_views = n_views;
+  for (int t = 0; t < 8; ++t) segs.counts[t] = t < n_views ? counts[t] : 0;
+
+  // keypoint encoder + descriptor add (multi_view_matcher.py:265-269)
+  MVM_TRY(launch_transpose_cn(desc, ws.DT, V, 256, n_pad, s));
+  MVM_TRY(launch_kenc_front(kpts, kscores, w->kenc_w, w->kenc_b, ws.H3, rows, img_w, img_h, s));
+  MVM_TRY(run_gemm(make_gemm(ws.H3, 128, w->kenc_w[3], 128, w->kenc_b[3], ws.H4, 256, rows, 256, 1), s));
+  {
+    GemmDesc g = make_gemm(ws.H4, 256, w->kenc_w[4], 256, w->kenc_b[4], ws.X, 256, rows, 256, 0);
+    g.R = ws.DT; g.ldr = 256;
+    MVM_TRY(run_gemm(g, s));
+  }
+
+  // attentional GNN (multi_view_matcher.py:87-100 / superglue.py:131-140)
+  for (int l = 0; l < w->n_layers; ++l) {
+    const mvm_layer_weights& L = w->layers[l];
+    MVM_TRY(run_gemm(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), s));
+    MVM_TRY(launch_attention_simt(ws.QKV, ws.MSG, batch, n_pad, segs, L.is_cross, s));
+    MVM_TRY(run_gemm(make_gemm(ws.MSG, 256, L.w_merge, 256, L.b_merge, ws.MRG, 256, rows, 256, 0), s));
+    {
+      GemmDesc g = make_gemm(ws.X, 256, L.w_mlp0, 512, L.b_mlp0, ws.H, 512, rows, 512, 1);
+      g.A2 = ws.MRG; g.lda2 = 256; g.K1 = 256;   // cat([x, message]) by K-split
+      MVM_TRY(run_gemm(g, s));
+    }
+    {
+      GemmDesc g = make_gemm(ws.H, 512, L.w_mlp1, 512, L.b_mlp1, ws.X, 256, rows, 256, 0);
+      g.R = ws.X; g.ldr = 256;                   // desc = desc + delta
+      MVM_TRY(run_gemm(g, s));
+    }
+  }
+
+  // final projection once per view (the reference redoes it per pair, :276)
+  MVM_TRY(run_gemm(make_gemm(ws.X, 256, w->w_final, 256, w->b_final, ws.MD, 256, rows, 256, 0), s));
+
+  PairTable tab;
+  MVM_TRY(fill_pair_table(tab, pairs, n_pairs, n_views, counts, batch));
+  MVM_TRY(launch_score_gemm_simt(ws.MD, n_pad, tab, batch, 1.0f / 16.0f, s));
+  MVM_TRY(launch_sinkhorn(tab, batch, w->bin_score, sinkhorn_iters, ws.sink_ws, s));
+  MVM_TRY(launch_extract_matches(tab, batch, n_pad, match_threshold, ws.match_ws, s));
+
+  if (w->has_conf) {
+    const long long crow = (long long)n_pairs * batch * n_pad;
+    MVM_TRY(launch_conf_gather(ws.MD, tab, batch, n_pad, ws.FEAT, ws.SC, s));
+    MVM_TRY(run_gemm(make_gemm(ws.FEAT, 512, w->conf_wf0, 512, w->conf_bf0, ws.CF1, 512, (int)crow, 512, 1), s));
+    MVM_TRY(run_gemm(make_gemm(ws.CF1, 512, w->conf_wf1, 512, w->conf_bf1, ws.CF2, 256, (int)crow, 256, 1), s));
+    MVM_TRY(launch_conf_c0(ws.SC, w->conf_wc0, w->conf_bc0, ws.CC0, crow, s));
+    {
+      GemmDesc g = make_gemm(ws.CC0, 256, w->conf_wc1, 256, w->conf_bc1, ws.CC1, 256, (int)crow, 256, 1);
+      g.R = ws.CF2; g.ldr = 256;                 // out_f + out_c
+      MVM_TRY(run_gemm(g, s));
+    }
+    MVM_TRY(launch_conf_final(ws.CC1, w->conf_wl, w->conf_bl, tab, batch, n_pad, s));
+  }
+  return MVM_OK;
+}
+
+int mvm_linear(const float* A, int lda, const float* A2, int lda2, int K1, const float* W,
+               int ldw, const float* bias, const float* R, int ldr, float* C, int ldc, int M,
+               int N, int K, float alpha, int relu, void* stream) {
+  MVM_REQUIRE(A && W && C);
+  GemmDesc g = make_gemm(A, lda, W, K, bias, C, ldc, M, N, relu);
+  g.ldw = ldw; g.alpha = alpha;
+  if (A2) { g.A2 = A2; g.lda2 = lda2; g.K1 = K1; }
+  if (R) { g.R = R; g.ldr = ldr; }
+  return launch_gemm_simt(g, (cudaStream_t)stream);
+}
+
+int mvm_attention(const float* qkv, float* out, int batch, int n_views, int n_pad,
+                  const int* counts, int is_cross, void* stream) {
+  MVM_REQUIRE(qkv && out && counts && n_views >= 1 && n_views <= 8);
+  AttnSegs segs;
+  segs.n_views = n_views;
+  for (int t = 0; t < 8; ++t) segs.counts[t] = t < n_views ? counts[t] : 0;
+  return launch_attention_simt(qkv, out, batch, n_pad, segs, is_cross, (cudaStream_t)stream);
+}
+
+size_t mvm_sinkhorn_workspace_floats(int n_pairs, int batch, int n_max) {
+  return sinkhorn_ws_floats(n_pairs, batch, (n_max + 63) / 64 * 64);
+}
+
+int mvm_log_optimal_transport(float* scores, int batch, int m, int n, float bin_score, int iters,
+                              float* ws, void* stream) {
+  MVM_REQUIRE(scores && ws && batch >= 1 && m >= 1 && n >= 1);
+  PairTable tab;
+  tab.n_pairs = 1; tab.n_views = 2; tab.a[0] = 0; tab.b[0] = 1; tab.m[0] = m; tab.n[0] = n;
+  tab.scores[0] = scores; tab.ws_off[0] = 0;
+  return launch_sinkhorn(tab, batch, bin_score, iters, ws, (cudaStream_t)stream);
+}
+
+int mvm_log_optimal_transport_ref(float* scores, int batch, int m, int n, float bin_score,
+                                  int iters, float* ws, void* stream) {
+  MVM_REQUIRE(scores && ws && batch >= 1 && m >= 1 && n >= 1);
+  PairTable tab;
+  tab.n_pairs = 1; tab.n_views = 2; tab.a[0] = 0; tab.b[0] = 1; tab.m[0] = m; tab.n[0] = n;
+  tab.scores[0] = scores; tab.ws_off[0] = 0;
+  return launch_sinkhorn_ref(tab, batch, bin_score, iters, ws, (cudaStream_t)stream);
+}
+
+int mvm_extract_matches(const float* scores, int batch, int m, int n, float match_threshold,
+                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
+                        void* ws, void* stream) {
+  MVM_REQUIRE(scores && matches0 && matches1 && mscores0 && mscores1 && ws);
+  PairTable tab;
+  tab.n_pairs = 1; tab.n_views = 2; tab.a[0] = 0; tab.b[0] = 1; tab.m[0] = m; tab.n[0] = n;
+  tab.scores[0] = const_cast<float*>(scores);
+  tab.matches_a[0] = matches0; tab.matches_b[0] = matches1;
+  tab.ms_a[0] = mscores0; tab.ms_b[0] = mscores1;
+  const int n_pad = ((m > n ? m : n) + 63) / 64 * 64;
+  return launch_extract_matches(tab, batch, n_pad, match_threshold, (int*)ws, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+"""Stage-level entry points (torch tensors in/out) over the C ABI.  Names follow the reference
+functions they replace (superglue.py:87-172, multi_view_matcher.py:288-300)."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def linear(a, w, bias=None, a2=None, residual=None, relu=False, alpha=1.0):
+    """act(alpha * [a|a2] @ w.T + bias) + residual on point-major activations (Conv1d k=1)."""
+    lib = _lib.lib()
+    M, K1 = a.shape
+    K = K1 + (a2.shape[1] if a2 is not None else 0)
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    rc = lib.mvm_linear(_lib.ptr(a), a.stride(0), _lib.ptr(a2), a2.stride(0) if a2 is not None else 0,
+                        K1, _lib.ptr(w), w.stride(0), _lib.ptr(bias), _lib.ptr(residual),
+                        residual.stride(0) if residual is not None else 0, _lib.ptr(out), N, M, N, K,
+                        float(alpha), int(relu), _lib.stream_ptr())
+    _lib.check(rc, 'mvm_linear')
+    return out
+
+
+def attention(qkv, batch, n_views, counts, is_cross):
+    """qkv [batch*n_views, n_pad, 768] (q|k|v, head-contiguous) -> [batch*n_views, n_pad, 256]."""
+    lib = _lib.lib()
+    V, n_pad, _ = qkv.shape
+    out = torch.zeros(V, n_pad, 256, dtype=torch.float32, device=qkv.device)
+    cnt = (C.c_int * n_views)(*counts)
+    rc = lib.mvm_attention(_lib.ptr(qkv), _lib.ptr(out), batch, n_views, n_pad, cnt, int(is_cross),
+                           _lib.stream_ptr())
+    _lib.check(rc, 'mvm_attention')
+    return out
+
+
+def log_optimal_transport(scores, alpha, iters, ref_kernel=False):
+    """superglue.py:152-172: scores [B,m,n] -> couplings [B,m+1,n+1]."""
+    lib = _lib.lib()
+    B, m, n = scores.shape
+    Z = torch.empty(B, m + 1, n + 1, dtype=torch.float32, device=scores.device)
+    Z[:, :m, :n] = scores
+    nws = lib.mvm_sinkhorn_workspace_floats(1, B, max(m, n))
+    ws = torch.empty(nws, dtype=torch.float32, device=scores.device)
+    fn = lib.mvm_log_optimal_transport_ref if ref_kernel else lib.mvm_log_optimal_transport
+    rc = fn(_lib.ptr(Z), B, m, n, float(alpha), int(iters), _lib.ptr(ws), _lib.stream_ptr())
+    _lib.check(rc, 'mvm_log_optimal_transport')
+    return Z
+
+
+def extract_matches(Z, match_threshold=0.0):
+    """multi_view_matcher.py:288-300 on couplings [B,m+1,n+1]."""
+    lib = _lib.lib()
+    B, m1, n1 = Z.shape
+    m, n = m1 - 1, n1 - 1
+    dev = Z.device
+    m0 = torch.empty(B, m, dtype=torch.int64, device=dev)
+    m1_ = torch.empty(B, n, dtype=torch.int64, device=dev)
+    s0 = torch.empty(B, m, dtype=torch.float32, device=dev)
+    s1 = torch.empty(B, n, dtype=torch.float32, device=dev)
+    n_pad = (max(m, n) + 63) // 64 * 64
+    ws = torch.empty(3 * B * n_pad, dtype=torch.int32, device=dev)
+    rc = lib.mvm_extract_matches(_lib.ptr(Z.contiguous()), B, m, n, float(match_threshold), _lib.ptr(m0),
+                                 _lib.ptr(m1_), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(ws), _lib.stream_ptr())
+    _lib.check(rc, 'mvm_extract_matches')
+    return m0, m1_, s0, s1

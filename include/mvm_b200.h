@@ -1,0 +1,134 @@
+/* mvm_b200.h -- C ABI of libmvm_b200.so, the B200 (sm_100a) drop-in for the hot path of
+ * barbararoessle/e2e_multi_view_matching.
+ *
+ * The reference has no FFI layer: the path sits behind Python callables.  Each entry point
+ * below is what a binding for that callable would call (INTEGRATION.md shows the ctypes
+ * stubs).  Conventions: plain device pointers + sizes, an explicit CUDA stream (passed as
+ * void* == cudaStream_t), int status return (0 ok, 1 invalid argument, 2 launch failure,
+ * 3 workspace too small).  Nothing throws across the ABI, every call is stream-ordered and
+ * re-entrant per stream; the only state is the caller-provided workspace.
+ *
+ * Activation layout inside the library is point-major [view, keypoint, channel]; the
+ * reference's channel-first [B, C, N] tensors are accepted at the boundary.
+ */
+#ifndef MVM_B200_H
+#define MVM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVM_DESC_DIM 256
+#define MVM_HEADS 4
+#define MVM_MAX_VIEWS 8
+#define MVM_MAX_LAYERS 64
+
+/* One AttentionalPropagation layer (superglue.py:112-121), repacked:
+ * BatchNorm folded into the preceding 1x1 conv; q/k/v rows and merge columns permuted from
+ * the reference's channel = d*4 + h interleave (superglue.py:106,109) to head-contiguous
+ * h*64 + d; q,k,v stacked into one [768,256] matrix.  All matrices row-major [out, in]. */
+typedef struct mvm_layer_weights {
+  const float* w_qkv;   /* [768,256] */
+  const float* b_qkv;   /* [768]     */
+  const float* w_merge; /* [256,256] */
+  const float* b_merge; /* [256]     */
+  const float* w_mlp0;  /* [512,512]  mlp.0 with mlp.1 (BN) folded */
+  const float* b_mlp0;  /* [512]     */
+  const float* w_mlp1;  /* [256,512]  mlp.3 */
+  const float* b_mlp1;  /* [256]     */
+  int is_cross;         /* 0 = 'self', 1 = 'cross' */
+} mvm_layer_weights;
+
+/* Whole matcher (multi_view_matcher.py:103-148).  Device pointers; BN folded everywhere. */
+typedef struct mvm_matcher_weights {
+  int n_layers;
+  /* KeypointEncoder 3->32->64->128->256->256 (multi_view_matcher.py:24-37) */
+  const float* kenc_w[5];
+  const float* kenc_b[5];
+  mvm_layer_weights layers[MVM_MAX_LAYERS];
+  const float* w_final; /* [256,256] final_proj */
+  const float* b_final;
+  float bin_score;
+  /* ConfidenceMLP (multi_view_matcher.py:39-53); has_conf = 0 skips it */
+  int has_conf;
+  const float* conf_wf0; const float* conf_bf0; /* [512,512] layers_f.0 (+BN) */
+  const float* conf_wf1; const float* conf_bf1; /* [256,512] layers_f.3 (+BN) */
+  const float* conf_wc0; const float* conf_bc0; /* [256] each: layers_c.0 (1->256, +BN) */
+  const float* conf_wc1; const float* conf_bc1; /* [256,256] layers_c.3 (+BN) */
+  const float* conf_wl;  float conf_bl;         /* [256], scalar: layers.0 */
+} mvm_matcher_weights;
+
+/* Outputs of one view pair (a < b), batch-major, exactly the tensors the reference returns
+ * (multi_view_matcher.py:308-315): matches{a}_{a}_{b} [B,n_a] int64 (-1 = none),
+ * matches{b}_{a}_{b} [B,n_b], matching_scores (fp32), scores_{a}_{b} [B,n_a+1,n_b+1],
+ * conf_scores_{a}_{b} [B,n_a,1].  conf may be NULL when has_conf == 0. */
+typedef struct mvm_pair_io {
+  int view_a, view_b;
+  int64_t* matches_a; int64_t* matches_b;
+  float* mscores_a;   float* mscores_b;
+  float* scores;
+  float* conf;
+} mvm_pair_io;
+
+/* Bytes of scratch mvm_matcher_forward needs for this shape. */
+size_t mvm_matcher_workspace_bytes(int batch, int n_views, int n_pad, int n_pairs, int has_conf);
+
+/* MultiViewMatcher.forward in eval mode (multi_view_matcher.py:322-332; multi_match
+ * :217-320; with n_views == 2 it is also SuperGlue/`match`, :150-215, superglue.py:230-285).
+ *   batch     tuples; n_views views per tuple; view v of tuple b is slot b*n_views + v
+ *   n_pad     row stride of the per-view buffers (multiple of 64, >= max count)
+ *   counts    host int[n_views]: true keypoints per view (shared by the batch)
+ *   kpts      [batch*n_views, n_pad, 2]  pixel x,y        (device)
+ *   kscores   [batch*n_views, n_pad]                       (device)
+ *   desc      [batch*n_views, 256, n_pad] channel-first    (device)
+ *   img_w/h   image size used by normalize_keypoints (superglue.py:65-72)
+ *   pairs     host array of n_pairs descriptors with device output pointers
+ *   match_threshold  0 for MultiViewMatcher (:297), 0.2 for SuperGlue (superglue.py:275) */
+int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, int n_pad,
+                        const int* counts, const float* kpts, const float* kscores,
+                        const float* desc, float img_w, float img_h, int sinkhorn_iters,
+                        float match_threshold, const mvm_pair_io* pairs, int n_pairs,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- individual stages (exported for stage-parity tests and for callers that only need
+ * one stage; same semantics as the fused forward) -------------------------------------- */
+
+/* C[M,N] = act(alpha*[A|A2] W^T + bias) + R, fp32 CUDA cores (superglue.py:51-62). */
+int mvm_linear(const float* A, int lda, const float* A2, int lda2, int K1, const float* W,
+               int ldw, const float* bias, const float* R, int ldr, float* C, int ldc, int M,
+               int N, int K, float alpha, int relu, void* stream);
+
+/* Multi-head attention over key/value segments (superglue.py:87-109 with the multi-view
+ * cross source of multi_view_matcher.py:92-95).  qkv [n_views_total, n_pad, 768]
+ * (q|k|v, head-contiguous); view v attends to its own keys (is_cross = 0) or to all other
+ * views of its tuple in ascending order (is_cross = 1).  out [n_views_total, n_pad, 256]. */
+int mvm_attention(const float* qkv, float* out, int batch, int n_views, int n_pad,
+                  const int* counts, int is_cross, void* stream);
+
+/* log_optimal_transport (superglue.py:143-172).  scores: [batch, m+1, n+1] buffers whose
+ * inner [m,n] block holds the raw scores on entry; on exit the full coupling matrix
+ * Z + u + v - norm.  ws: mvm_sinkhorn_workspace_floats(1, batch, max(m,n)) floats.
+ * The shared-memory-resident multi-CTA kernel; _ref is the one-CTA-per-problem kernel that
+ * walks the matrix in L2/HBM like the reference does (kept as the on-device cross-check). */
+size_t mvm_sinkhorn_workspace_floats(int n_pairs, int batch, int n_max);
+int mvm_log_optimal_transport(float* scores, int batch, int m, int n, float bin_score,
+                              int iters, float* ws, void* stream);
+int mvm_log_optimal_transport_ref(float* scores, int batch, int m, int n, float bin_score,
+                                  int iters, float* ws, void* stream);
+
+/* Mutual-nearest-neighbour extraction (multi_view_matcher.py:288-300).
+ * ws: 3 * batch * round_up(max(m,n), 64) 4-byte words. */
+int mvm_extract_matches(const float* scores, int batch, int m, int n, float match_threshold,
+                        int64_t* matches0, int64_t* matches1, float* mscores0,
+                        float* mscores1, void* ws, void* stream);
+
+/* Library/build info: returns "mvm_b200 <version> sm_100a". */
+const char* mvm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVM_B200_H */

@@ -1,0 +1,84 @@
+"""GPU parity: the CUDA matcher (through the reference-shaped MultiViewMatcher -> C ABI) against the
+committed reference outputs, on the same seeded weights/inputs the golden generator used."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import MATCHER_CASES, load_case, case_inputs, compare_matcher_outputs
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ours(meta, sd, data):
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    model = MultiViewMatcher({'multi_frame_matching': meta['multi'], 'GNN_layers': meta['layers'],
+                              'conf_mlp': True}).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    model = model.cuda()
+    tdata = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in data.items()}
+    out = model(tdata)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items() if v is not None}
+
+
+@pytest.mark.parametrize('name', MATCHER_CASES)
+def test_matcher_matches_reference_golden(name):
+    meta, ref = load_case(name)
+    sd, data = case_inputs(meta)
+    got = run_ours(meta, sd, data)
+    assert set(ref.keys()) == set(got.keys())
+    rep = compare_matcher_outputs(ref, got, min_stable=0.5 if 'sharp' not in name else 0.9)
+    print(name, rep)
+
+
+def test_matcher_batched_equals_single():
+    """Batch of tuples (B=3) gives the same result per tuple as B=1 calls."""
+    from oracle.weights import make_state_dict, make_correlated_view_inputs
+    layers = ['self', 'cross', 'cross'] * 2
+    meta = dict(multi=True, layers=layers)
+    sd = make_state_dict(len(layers), seed=21, final_proj_gain=12.0)
+    data = make_correlated_view_inputs(77, 3, 80, batch=3)
+    full = run_ours(meta, sd, data)
+    for b in range(3):
+        one = {k: (v[b:b + 1] if isinstance(v, np.ndarray) else v) for k, v in data.items()}
+        single = run_ours(meta, sd, one)
+        for k in single:
+            if k.startswith('matches'):
+                assert np.array_equal(single[k][0], full[k][b]), k
+            else:
+                np.testing.assert_allclose(single[k][0], full[k][b], atol=1e-5, rtol=1e-5, err_msg=k)
+
+
+def test_superglue_api_and_threshold():
+    """SuperGlue.forward contract (superglue.py:230-285): matches0/1 with the 0.2 threshold."""
+    from e2e_multi_view_matching_b200.models.superglue import SuperGlue
+    from oracle.weights import make_state_dict, make_correlated_view_inputs
+    from oracle.matcher import matcher_forward
+    layers = ['self', 'cross'] * 3
+    sd = make_state_dict(len(layers), seed=5, conf_mlp=False, final_proj_gain=14.0)
+    data = make_correlated_view_inputs(5, 2, 100)
+    model = SuperGlue({'GNN_layers': layers}).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    model = model.cuda()
+    out = model({k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in data.items()})
+    ref = matcher_forward(sd, {'multi_frame_matching': False, 'GNN_layers': layers, 'conf_mlp': False,
+                               'match_threshold': 0.2}, data)
+    m0 = out['matches0'].cpu().numpy()
+    assert m0.dtype == np.int64
+    agree = (m0 == ref['matches0_0_1']).mean()
+    assert agree > 0.97, agree
+    assert (m0 >= 0).sum() > 10
+    ms = out['matching_scores0'].cpu().numpy()
+    assert ((ms > 0.2) | (m0 < 0)).all()
+
+
+def test_empty_view_returns_reference_shapes():
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    model = MultiViewMatcher({'multi_frame_matching': False, 'GNN_layers': ['self', 'cross']}).eval().cuda()
+    data = {'keypoints0': torch.zeros(1, 0, 2).cuda(), 'keypoints1': torch.rand(1, 20, 2).cuda(),
+            'scores0': torch.zeros(1, 0).cuda(), 'scores1': torch.rand(1, 20).cuda(),
+            'descriptors0': torch.zeros(1, 256, 0).cuda(), 'descriptors1': torch.rand(1, 256, 20).cuda(),
+            'image0': torch.zeros(1, 1, 48, 64), 'image1': torch.zeros(1, 1, 48, 64), 'ids': [0, 1]}
+    out = model(data)
+    assert out['matches0_0_1'].shape == (1, 0) and out['matches1_0_1'].shape == (1, 20)
+    assert (out['matches1_0_1'] == -1).all() and out['matches1_0_1'].dtype == torch.int32

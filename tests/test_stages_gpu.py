@@ -1,0 +1,88 @@
+"""GPU stage parity: each CUDA stage against the oracle (or fp64 torch math) on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_linear_epilogues():
+    from e2e_multi_view_matching_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K1, K2) in [(300, 256, 128, 0), (1024, 768, 256, 0), (130, 512, 256, 256), (64, 256, 512, 0)]:
+        a = torch.randn(M, K1, generator=g).cuda()
+        a2 = torch.randn(M, K2, generator=g).cuda() if K2 else None
+        w = torch.randn(N, K1 + K2, generator=g).cuda() / 16
+        b = torch.randn(N, generator=g).cuda()
+        r = torch.randn(M, N, generator=g).cuda()
+        out = ops.linear(a, w, bias=b, a2=a2, residual=r, relu=True)
+        A = torch.cat([a, a2], 1) if a2 is not None else a
+        ref = torch.relu(A.double() @ w.double().T + b.double()) + r.double()
+        assert (out.double() - ref).abs().max().item() < 2e-4
+
+
+def test_attention_self_and_cross_ragged():
+    from e2e_multi_view_matching_b200 import ops
+    from oracle.matcher import attention as oracle_attention
+    rng = np.random.default_rng(1)
+    B, T, n_pad = 2, 3, 128
+    counts = [100, 128, 77]
+    qkv = rng.standard_normal((B * T, n_pad, 768)).astype(np.float32)
+    for is_cross in (0, 1):
+        out = ops.attention(torch.from_numpy(qkv).cuda(), B, T, counts, is_cross).cpu().numpy()
+        for b in range(B):
+            for t in range(T):
+                v = b * T + t
+                segs = [s for s in range(T) if (s != t if is_cross else s == t)]
+                q = qkv[v, :counts[t], 0:256].reshape(counts[t], 4, 64)
+                k = np.concatenate([qkv[b * T + s, :counts[s], 256:512] for s in segs], 0).reshape(-1, 4, 64)
+                vv = np.concatenate([qkv[b * T + s, :counts[s], 512:768] for s in segs], 0).reshape(-1, 4, 64)
+                # oracle layout [B, d, h, N]
+                o = oracle_attention(q.transpose(2, 1, 0)[None], k.transpose(2, 1, 0)[None],
+                                     vv.transpose(2, 1, 0)[None])[0]      # [d, h, n]
+                ref = o.transpose(2, 1, 0).reshape(counts[t], 256)
+                np.testing.assert_allclose(out[v, :counts[t]], ref, atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize('shape', [(1, 60, 50), (3, 128, 128), (2, 33, 200), (1, 300, 257)])
+@pytest.mark.parametrize('spread', [1.0, 12.0])
+def test_sinkhorn_kernels_vs_oracle(shape, spread):
+    from e2e_multi_view_matching_b200 import ops
+    from oracle.matcher import log_optimal_transport
+    B, m, n = shape
+    rng = np.random.default_rng(m * 1000 + n)
+    s = (rng.standard_normal((B, m, n)) * spread).astype(np.float32)
+    ref = log_optimal_transport(s, 1.0, 100)
+    for ref_kernel in (True, False):
+        Z = ops.log_optimal_transport(torch.from_numpy(s).cuda(), 1.0, 100, ref_kernel=ref_kernel).cpu().numpy()
+        err = np.abs(Z - ref)
+        assert (err <= 1e-4 + 1e-5 * np.abs(ref)).all(), (ref_kernel, float(err.max()))
+
+
+def test_sinkhorn_full_size_marginals():
+    """1024 x 1024 (BASELINE size): size-independent property -- row/col marginals of exp(Z)."""
+    from e2e_multi_view_matching_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    m = n = 1024
+    s = (torch.randn(2, m, n, generator=g) * 4).cuda()
+    Z = ops.log_optimal_transport(s, 1.0, 100)
+    P = torch.exp(Z.double()) / (m + n)
+    assert (P[:, :m, :].sum(2) * (m + n) - 1).abs().max().item() < 5e-3
+    assert (P[:, :, :n].sum(1) * (m + n) - 1).abs().max().item() < 5e-3
+    Zr = ops.log_optimal_transport(s, 1.0, 100, ref_kernel=True)
+    assert (Z - Zr).abs().max().item() < 2e-4
+
+
+def test_extract_matches_vs_oracle():
+    from e2e_multi_view_matching_b200 import ops
+    from oracle.matcher import extract_matches
+    rng = np.random.default_rng(5)
+    for (B, m, n) in [(2, 70, 90), (1, 128, 128), (1, 257, 64)]:
+        Z = rng.standard_normal((B, m + 1, n + 1)).astype(np.float32)
+        for thr in (0.0, 0.2):
+            r = extract_matches(Z, thr)
+            g = ops.extract_matches(torch.from_numpy(Z).cuda(), thr)
+            assert np.array_equal(r[0], g[0].cpu().numpy())
+            assert np.array_equal(r[1], g[1].cpu().numpy())
+            np.testing.assert_allclose(g[2].cpu().numpy(), r[2], rtol=1e-5)
+            np.testing.assert_allclose(g[3].cpu().numpy(), r[3], rtol=1e-5)
