@@ -125,6 +125,31 @@ int mvm_extract_matches(const float* scores, int batch, int m, int n, float matc
                         int64_t* matches0, int64_t* matches1, float* mscores0,
                         float* mscores1, void* ws, void* stream);
 
+/* ---- two-view pose (pose_optimization/two_view/) ------------------------------------- */
+
+/* estimate_relative_pose_w8pt (estimate_relative_pose.py:84-128): weighted eight-point on
+ * matched keypoints, one CTA per batch element, fp64 on chip.
+ *   kpts0/1 [B,N,2] pixels (kpts1 already gathered by the matches), intr0/1 [B,4] = fx,fy,cx,cy,
+ *   conf [B,N] (un-normalised), T_gt [B,16] target pose for choose_closest (else NULL).
+ * Outputs: T021 [B,16] row-major 4x4; kpts{0,1}_norm [B,N,2]; conf_norm [B,N] = conf/(sum+1e-6);
+ * pos_depth_mask / inliers [B,N] bytes (inliers only when determine_inliers); F_out [B,9] the
+ * normalised essential matrix (may be NULL).  The caller handles N < 8 -> (None, None). */
+int mvm_w8pt(const float* kpts0, const float* kpts1, const float* intr0, const float* intr1,
+             const float* conf, int batch, int n, const float* T_gt, int choose_closest,
+             int determine_inliers, float* T021, float* kpts0_norm, float* kpts1_norm,
+             float* conf_norm, unsigned char* pos_depth_mask, unsigned char* inliers,
+             float* F_out, void* stream);
+
+/* run_bundle_adjust_2_view -> BundleAdjustGaussNewton2View.run
+ * (estimate_relative_pose.py:138-143, bundle_adjust_gauss_newton_2_view.py:127-201):
+ * LM with the reference's schedule, Schur-complement step, one CTA per batch element.
+ *   conf [B,N]: entries <= 0 are invalid matches; items with <= 6 valid matches get
+ *   valid_batch = 0 and T_out = T_init.  pts_ws: B*N*3 doubles.  trace: [B,n_iterations+1]
+ *   residual norms per evaluation, or NULL. */
+int mvm_ba2view(const float* kpts0_norm, const float* kpts1_norm, const float* conf,
+                const float* T_init, int batch, int n, int n_iterations, float* T_out,
+                unsigned char* valid_batch, double* pts_ws, float* trace, void* stream);
+
 /* Library/build info: returns "mvm_b200 <version> sm_100a". */
 const char* mvm_version(void);
 
