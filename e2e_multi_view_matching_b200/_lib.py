@@ -82,6 +82,11 @@ def lib():
     L.mvm_extract_matches.restype = C.c_int
     L.mvm_extract_matches.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp,
                                       _fp, _fp, _fp]
+    L.mvm_w8pt.restype = C.c_int
+    L.mvm_w8pt.argtypes = [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp,
+                           _fp, _fp, _fp, _fp, _fp, _fp, _fp]
+    L.mvm_ba2view.restype = C.c_int
+    L.mvm_ba2view.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp]
     _lib = L
     return L
 
