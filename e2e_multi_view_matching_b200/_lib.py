@@ -84,9 +84,24 @@ def lib():
                                       _fp, _fp, _fp]
     L.mvm_w8pt.restype = C.c_int
     L.mvm_w8pt.argtypes = [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp,
-                           _fp, _fp, _fp, _fp, _fp, _fp, _fp]
+                           _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]
     L.mvm_ba2view.restype = C.c_int
-    L.mvm_ba2view.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp]
+    L.mvm_ba2view.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp]
+    L.mvm_gather_matches.restype = C.c_int
+    L.mvm_gather_matches.argtypes = [_fp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(PairIO), C.c_int,
+                                     C.c_int, C.c_float, _fp, _fp, _fp, _fp, _fp]
+    L.mvm_spanning_tree_init.restype = C.c_int
+    L.mvm_spanning_tree_init.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
+                                         _fp, _fp, _fp, _fp, _fp, _fp]
+    L.mvm_mvba_workspace_bytes.restype = C.c_size_t
+    L.mvm_mvba_workspace_bytes.argtypes = [C.c_int] * 4
+    L.mvm_multi_view_ba.restype = C.c_int
+    L.mvm_multi_view_ba.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
+                                    _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]
+    L.mvm_launch_count.restype = C.c_ulonglong
+    L.mvm_profile_enable.argtypes = [C.c_int]
+    L.mvm_profile_collect.restype = C.c_int
+    L.mvm_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     _lib = L
     return L
 
@@ -107,3 +122,16 @@ def ptr(t):
         return C.c_void_p(0)
     assert t.is_cuda and t.is_contiguous(), 'libmvm_b200 needs contiguous CUDA tensors'
     return C.c_void_p(t.data_ptr())
+
+
+PROFILE_TAGS = ['gemm', 'attention', 'sinkhorn', 'score_gemm', 'match', 'conf', 'kenc', 'w8pt', 'ba2',
+                'mvba', 'misc']
+
+
+def profile_collect():
+    """-> {tag: (milliseconds, scopes)} since the last collect (needs mvm_profile_enable(1))."""
+    n = len(PROFILE_TAGS)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int * n)()
+    lib().mvm_profile_collect(ms, cnt, n)
+    return {PROFILE_TAGS[i]: (ms[i], cnt[i]) for i in range(n)}

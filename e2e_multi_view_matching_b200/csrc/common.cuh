@@ -9,8 +9,21 @@
 #define MVM_ERR_LAUNCH 2
 #define MVM_ERR_WORKSPACE 3
 
+extern unsigned long long g_mvm_launches;   // kernels launched by this library (profile.cu)
+
+// kernel classes for the optional event profiler (mvm_profile_*)
+enum MvmTag { MVM_TAG_GEMM = 0, MVM_TAG_ATTN, MVM_TAG_SINKHORN, MVM_TAG_SCORE, MVM_TAG_MATCH,
+              MVM_TAG_CONF, MVM_TAG_KENC, MVM_TAG_W8PT, MVM_TAG_BA2, MVM_TAG_MVBA, MVM_TAG_MISC,
+              MVM_N_TAGS };
+struct MvmProfScope {
+  MvmProfScope(int tag, cudaStream_t s);
+  ~MvmProfScope();
+  int tag_; cudaStream_t s_; int idx_;
+};
+
 #define MVM_CHECK_LAUNCH()                                                        \
   do {                                                                            \
+    ++g_mvm_launches;                                                             \
     cudaError_t e__ = cudaGetLastError();                                         \
     if (e__ != cudaSuccess) {                                                     \
       fprintf(stderr, "[mvm_b200] launch failed at %s:%d: %s\n", __FILE__,        \

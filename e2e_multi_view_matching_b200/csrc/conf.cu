@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) conf_final_kernel(const float* __restrict
 
 int launch_conf_gather(const float* mdesc, const PairTable& tab, int batch, int n_pad, float* feat,
                        float* sc, cudaStream_t stream) {
+  MvmProfScope prof__(MVM_TAG_CONF, stream);
   conf_gather_kernel<<<dim3(mvm_div_up(n_pad, 8), tab.n_pairs * batch), 256, 0, stream>>>(
       mdesc, tab, batch, n_pad, feat, sc);
   MVM_CHECK_LAUNCH();
@@ -78,6 +79,7 @@ int launch_conf_gather(const float* mdesc, const PairTable& tab, int batch, int 
 
 int launch_conf_c0(const float* sc, const float* w, const float* b, float* out, long long rows,
                    cudaStream_t stream) {
+  MvmProfScope prof__(MVM_TAG_CONF, stream);
   const long long total = rows * 256;
   conf_c0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(sc, w, b, out, rows);
   MVM_CHECK_LAUNCH();
@@ -86,6 +88,7 @@ int launch_conf_c0(const float* sc, const float* w, const float* b, float* out, 
 
 int launch_conf_final(const float* h, const float* wl, float bl, const PairTable& tab, int batch,
                       int n_pad, cudaStream_t stream) {
+  MvmProfScope prof__(MVM_TAG_CONF, stream);
   conf_final_kernel<<<dim3(mvm_div_up(n_pad, 8), tab.n_pairs * batch), 256, 0, stream>>>(
       h, wl, bl, tab, batch, n_pad);
   MVM_CHECK_LAUNCH();

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256, 2) score_gemm_simt_kernel(const float* __
 
 int launch_score_gemm_simt(const float* mdesc, int n_pad, const PairTable& tab, int batch,
                            float alpha, cudaStream_t stream) {
+  MvmProfScope prof__(MVM_TAG_SCORE, stream);
   int max_m = 0, max_n = 0;
   for (int p = 0; p < tab.n_pairs; ++p) {
     max_m = tab.m[p] > max_m ? tab.m[p] : max_m;
@@ -145,6 +146,7 @@ int launch_score_gemm_simt(const float* mdesc, int n_pad, const PairTable& tab, 
 }
 
 int launch_gemm_simt(const GemmDesc& g, cudaStream_t stream) {
+  MvmProfScope prof__(MVM_TAG_GEMM, stream);
   MVM_REQUIRE(g.K % BK == 0 && g.K1 % BK == 0);
   MVM_REQUIRE(g.lda % 4 == 0 && g.ldw % 4 == 0 && (g.A2 == nullptr || g.lda2 % 4 == 0));
   MVM_REQUIRE(g.M > 0 && g.N > 0 && g.batch > 0);

@@ -82,6 +82,7 @@ __global__ void transpose_cn_kernel(const float* __restrict__ in, float* __restr
 int launch_kenc_front(const float* kpts, const float* kscores, const float* const* w,
                       const float* const* b, float* h3, int n_points, float img_w, float img_h,
                       cudaStream_t stream) {
+  MvmProfScope prof__(MVM_TAG_KENC, stream);
   const float scale = 0.7f * fmaxf(img_w, img_h);
   kenc_front_kernel<<<mvm_div_up(n_points, PTS), 256, 0, stream>>>(
       kpts, kscores, w[0], b[0], w[1], b[1], w[2], b[2], h3, n_points, img_w * 0.5f, img_h * 0.5f,

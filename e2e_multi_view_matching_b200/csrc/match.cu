@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) mutual_kernel(PairTable tab, int batch, i
 
 int launch_extract_matches(const PairTable& tab, int batch, int n_pad, float thresh, int* idx_ws,
                            cudaStream_t stream) {
+  MvmProfScope prof__(MVM_TAG_MATCH, stream);
   int max_m = 0, max_n = 0;
   for (int p = 0; p < tab.n_pairs; ++p) {
     max_m = tab.m[p] > max_m ? tab.m[p] : max_m;

@@ -21,6 +21,8 @@ struct Ba2Args {
   const float* k0n; const float* k1n;   // [B,N,2] normalised image coordinates
   const float* conf;                    // [B,N]; <= 0 marks an invalid match
   const float* T_init;                  // [B,16]
+  const int* n_valid;                   // [B] effective keypoints per item or null
+  const unsigned char* mask;            // [B,N] or null: conf is treated as 0 where mask == 0
   int N, n_iter;
   float* T_out;                         // [B,16]
   unsigned char* valid_batch;           // [B]
@@ -134,18 +136,21 @@ __global__ void __launch_bounds__(NT) ba2_kernel(Ba2Args a) {
   __shared__ double s_lambda, s_best_r;
   __shared__ int s_ok, s_precond;
 
-  const int b = blockIdx.x, N = a.N, tid = threadIdx.x;
-  const float* k0 = a.k0n + (long long)b * N * 2;
-  const float* k1 = a.k1n + (long long)b * N * 2;
-  const float* cf = a.conf + (long long)b * N;
-  double* P = a.pts + (long long)b * N * 3;
+  const int b = blockIdx.x, NS = a.N, tid = threadIdx.x;
+  const int N = a.n_valid ? min(max(a.n_valid[b], 0), NS) : NS;
+  const float* k0 = a.k0n + (long long)b * NS * 2;
+  const float* k1 = a.k1n + (long long)b * NS * 2;
+  const float* cf_raw = a.conf + (long long)b * NS;
+  const unsigned char* mk = a.mask ? a.mask + (long long)b * NS : nullptr;
+  auto CF = [&](int i) -> float { return (mk && !mk[i]) ? 0.f : cf_raw[i]; };
+  double* P = a.pts + (long long)b * NS * 3;
   float* Tout = a.T_out + b * 16;
 
   // valid = conf > 0 (:129-131); weights conf / (0.5 * sum over the 2n observations) (:44-48)
   double v2[NRED];
   v2[0] = 0.0; v2[1] = 0.0;
   for (int i = tid; i < N; i += NT)
-    if (cf[i] > 0.f) { v2[0] += 1.0; v2[1] += (double)cf[i]; }
+    if (CF(i) > 0.f) { v2[0] += 1.0; v2[1] += (double)CF(i); }
   block_reduce(v2, 2, s_red, s_sum);
   const int n_matches = (int)(s_sum[0] + 0.5);
   const double sum_conf = fmax(2.0 * s_sum[1], 1e-6);
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(NT) ba2_kernel(Ba2Args a) {
       t[i] = s_T[i * 4 + 3];
     }
     for (int i = tid; i < N; i += NT) {
-      if (!(cf[i] > 0.f)) continue;
+      if (!(CF(i) > 0.f)) continue;
       double X[3];
       triangulate_dlt(R, t, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1], X);
       P[3 * i] = X[0]; P[3 * i + 1] = X[1]; P[3 * i + 2] = X[2];
@@ -185,10 +190,10 @@ __global__ void __launch_bounds__(NT) ba2_kernel(Ba2Args a) {
     for (int e = 0; e < NRED; ++e) acc[e] = 0.0;
     int diag_ok = 1;
     for (int i = tid; i < N; i += NT) {
-      if (!(cf[i] > 0.f)) continue;
+      if (!(CF(i) > 0.f)) continue;
       PointBlocks pb;
       const double p[3] = {P[3 * i], P[3 * i + 1], P[3 * i + 2]};
-      point_blocks(T, p, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1], (double)cf[i] * w_scale, pb);
+      point_blocks(T, p, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1], (double)CF(i) * w_scale, pb);
       for (int e = 0; e < 21; ++e) acc[e] += pb.Acc[e];
       for (int e = 0; e < 6; ++e) acc[21 + e] += pb.bc[e];
       acc[27] += pb.rho;
@@ -228,10 +233,10 @@ __global__ void __launch_bounds__(NT) ba2_kernel(Ba2Args a) {
     for (int e = 0; e < NRED; ++e) acc[e] = 0.0;
     int sing = 0;
     for (int i = tid; i < N; i += NT) {
-      if (!(cf[i] > 0.f)) continue;
+      if (!(CF(i) > 0.f)) continue;
       PointBlocks pb;
       const double p[3] = {P[3 * i], P[3 * i + 1], P[3 * i + 2]};
-      point_blocks(T, p, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1], (double)cf[i] * w_scale, pb);
+      point_blocks(T, p, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1], (double)CF(i) * w_scale, pb);
       double M[6] = {pb.App[0], pb.App[1], pb.App[2], pb.App[3], pb.App[4], pb.App[5]};
       if (precond) {   // (A + lambda * max(diag A, 1e-12)) (:171-184)
         M[0] += lambda * fmax(pb.App[0], 1e-12); M[3] += lambda * fmax(pb.App[3], 1e-12);
@@ -286,10 +291,10 @@ __global__ void __launch_bounds__(NT) ba2_kernel(Ba2Args a) {
       double dc[6];
       for (int r = 0; r < 6; ++r) dc[r] = s_delta[r];
       for (int i = tid; i < N; i += NT) {
-        if (!(cf[i] > 0.f)) continue;
+        if (!(CF(i) > 0.f)) continue;
         PointBlocks pb;
         const double p[3] = {P[3 * i], P[3 * i + 1], P[3 * i + 2]};
-        point_blocks(T, p, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1], (double)cf[i] * w_scale, pb);
+        point_blocks(T, p, k0[2 * i], k0[2 * i + 1], k1[2 * i], k1[2 * i + 1], (double)CF(i) * w_scale, pb);
         double M[6] = {pb.App[0], pb.App[1], pb.App[2], pb.App[3], pb.App[4], pb.App[5]};
         if (precond) {
           M[0] += lambda * fmax(pb.App[0], 1e-12); M[3] += lambda * fmax(pb.App[3], 1e-12);
@@ -320,11 +325,14 @@ __global__ void __launch_bounds__(NT) ba2_kernel(Ba2Args a) {
 
 extern "C" int mvm_ba2view(const float* kpts0_norm, const float* kpts1_norm, const float* conf,
                            const float* T_init, int batch, int n, int n_iterations, float* T_out,
-                           unsigned char* valid_batch, double* pts_ws, float* trace, void* stream) {
+                           unsigned char* valid_batch, double* pts_ws, float* trace,
+                           const int* n_valid, const unsigned char* mask, void* stream) {
+  MvmProfScope prof__(MVM_TAG_BA2, (cudaStream_t)stream);
   MVM_REQUIRE(kpts0_norm && kpts1_norm && conf && T_init && T_out && valid_batch && pts_ws);
   MVM_REQUIRE(batch >= 1 && n >= 1 && n_iterations >= 0);
   Ba2Args a;
   a.k0n = kpts0_norm; a.k1n = kpts1_norm; a.conf = conf; a.T_init = T_init; a.N = n;
+  a.n_valid = n_valid; a.mask = mask;
   a.n_iter = n_iterations; a.T_out = T_out; a.valid_batch = valid_batch; a.pts = pts_ws;
   a.trace = trace;
   ba2_kernel<<<batch, NT, 0, (cudaStream_t)stream>>>(a);

@@ -37,6 +37,8 @@ struct W8ptArgs {
   const float* intr0; const float* intr1;   // [B,4]: fx, fy, cx, cy
   const float* conf;                        // [B,N]
   const float* T_gt;                        // [B,16] or null (choose_closest)
+  const int* n_valid;                       // [B] effective keypoints per item (<= N) or null
+  unsigned char* success;                   // [B] or null: 0 when an item has < 8 keypoints
   int N;
   int choose_closest, determine_inliers;
   float* T021;                              // [B,16]
@@ -111,15 +113,34 @@ __global__ void __launch_bounds__(NT) w8pt_kernel(W8ptArgs a) {
   __shared__ int s_choice;
   __shared__ double s_Rc[9], s_tc[3];
 
-  const int b = blockIdx.x, N = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* k0 = a.kpts0 + (long long)b * N * 2;
-  const float* k1 = a.kpts1 + (long long)b * N * 2;
-  const float* cf = a.conf + (long long)b * N;
+  const int b = blockIdx.x, NS = a.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.n_valid ? min(max(a.n_valid[b], 0), NS) : NS;   // effective count; NS = row stride
+  const float* k0 = a.kpts0 + (long long)b * NS * 2;
+  const float* k1 = a.kpts1 + (long long)b * NS * 2;
+  const float* cf = a.conf + (long long)b * NS;
   const float fx0 = a.intr0[b * 4 + 0], fy0 = a.intr0[b * 4 + 1], cx0 = a.intr0[b * 4 + 2], cy0 = a.intr0[b * 4 + 3];
   const float fx1 = a.intr1[b * 4 + 0], fy1 = a.intr1[b * 4 + 1], cx1 = a.intr1[b * 4 + 2], cy1 = a.intr1[b * 4 + 3];
-  float* k0n = a.k0n + (long long)b * N * 2;
-  float* k1n = a.k1n + (long long)b * N * 2;
-  float* cn = a.conf_n + (long long)b * N;
+  float* k0n = a.k0n + (long long)b * NS * 2;
+  float* k1n = a.k1n + (long long)b * NS * 2;
+  float* cn = a.conf_n + (long long)b * NS;
+  // padding rows beyond the effective count: neutral outputs
+  for (int i = N + tid; i < NS; i += NT) {
+    k0n[2 * i] = 0.f; k0n[2 * i + 1] = 0.f; k1n[2 * i] = 0.f; k1n[2 * i + 1] = 0.f; cn[i] = 0.f;
+    a.pos_depth[(long long)b * NS + i] = 0;
+    if (a.inliers) a.inliers[(long long)b * NS + i] = 0;
+  }
+  if (N < 8) {   // fewer than 8 keypoints: no estimate (estimate_relative_pose.py:85-86)
+    if (tid < 16) a.T021[b * 16 + tid] = (tid % 5 == 0) ? 1.f : 0.f;
+    for (int i = tid; i < N; i += NT) {
+      k0n[2 * i] = 0.f; k0n[2 * i + 1] = 0.f; k1n[2 * i] = 0.f; k1n[2 * i + 1] = 0.f; cn[i] = 0.f;
+      a.pos_depth[(long long)b * NS + i] = 0;
+      if (a.inliers) a.inliers[(long long)b * NS + i] = 0;
+    }
+    if (tid == 0 && a.success) a.success[b] = 0;
+    if (tid < 9 && a.F_out) a.F_out[b * 9 + tid] = 0.f;
+    return;
+  }
+  if (tid == 0 && a.success) a.success[b] = 1;
 
   // confidence normalisation (:87-88) and camera normalisation (:9-14, :89-90), fp32 like the ref
   double csum = 0.0;
@@ -322,14 +343,14 @@ __global__ void __launch_bounds__(NT) w8pt_kernel(W8ptArgs a) {
       triangulate_dlt(R, t, x1, y1, x2, y2, X);
       const double dpt2 = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
       const bool pos = X[2] > 0.0 && dpt2 > 0.0;
-      a.pos_depth[(long long)b * N + i] = pos ? 1 : 0;
+      a.pos_depth[(long long)b * NS + i] = pos ? 1 : 0;
       if (a.inliers) {
         const double* E = s_E;
         const double l1[3] = {E[0] * x1 + E[1] * y1 + E[2], E[3] * x1 + E[4] * y1 + E[5], E[6] * x1 + E[7] * y1 + E[8]};
         const double l2[3] = {E[0] * x2 + E[3] * y2 + E[6], E[1] * x2 + E[4] * y2 + E[7], E[2] * x2 + E[5] * y2 + E[8]};
         const double num = x2 * l1[0] + y2 * l1[1] + l1[2];
         const double d = num * num * (1.0 / (l1[0] * l1[0] + l1[1] * l1[1]) + 1.0 / (l2[0] * l2[0] + l2[1] * l2[1]));
-        a.inliers[(long long)b * N + i] = (pos && sqrt(d) <= thresh) ? 1 : 0;
+        a.inliers[(long long)b * NS + i] = (pos && sqrt(d) <= thresh) ? 1 : 0;
       }
     }
   }
@@ -342,14 +363,16 @@ extern "C" int mvm_w8pt(const float* kpts0, const float* kpts1, const float* int
                         const float* T_gt, int choose_closest, int determine_inliers, float* T021,
                         float* kpts0_norm, float* kpts1_norm, float* conf_norm,
                         unsigned char* pos_depth_mask, unsigned char* inliers, float* F_out,
-                        void* stream) {
+                        const int* n_valid, unsigned char* success, void* stream) {
+  MvmProfScope prof__(MVM_TAG_W8PT, (cudaStream_t)stream);
   MVM_REQUIRE(kpts0 && kpts1 && intr0 && intr1 && conf && T021 && kpts0_norm && kpts1_norm &&
               conf_norm && pos_depth_mask);
-  MVM_REQUIRE(batch >= 1 && n >= 8);                 // <8 keypoints -> (None, None) at the caller (:85-86)
+  MVM_REQUIRE(batch >= 1 && n >= 1);
   MVM_REQUIRE(!choose_closest || T_gt != nullptr);
   MVM_REQUIRE(!determine_inliers || inliers != nullptr);
   W8ptArgs a;
   a.kpts0 = kpts0; a.kpts1 = kpts1; a.intr0 = intr0; a.intr1 = intr1; a.conf = conf; a.T_gt = T_gt;
+  a.n_valid = n_valid; a.success = success;
   a.N = n; a.choose_closest = choose_closest; a.determine_inliers = determine_inliers;
   a.T021 = T021; a.k0n = kpts0_norm; a.k1n = kpts1_norm; a.conf_n = conf_norm;
   a.pos_depth = pos_depth_mask; a.inliers = determine_inliers ? inliers : nullptr; a.F_out = F_out;

@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_smem_kernel(PairTable tab, S
 
 int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
                     cudaStream_t stream) {
+  MvmProfScope prof__(MVM_TAG_SINKHORN, stream);
   MVM_REQUIRE(tab.n_pairs >= 1 && tab.n_pairs <= MVM_MAX_PAIRS && batch >= 1);
   static int n_sm = 0;
   static size_t max_smem = 0;

@@ -74,6 +74,7 @@ class MatcherEngine:
 
     def __init__(self):
         self._ws = {}
+        self.last = None
 
     def workspace(self, nbytes, device):
         key = str(device)
@@ -131,6 +132,9 @@ class MatcherEngine:
                 float(img_wh[0]), float(img_wh[1]), int(sinkhorn_iters), float(match_threshold),
                 pairs, n_pairs, _lib.ptr(ws), nbytes, _lib.stream_ptr())
         _lib.check(rc, 'mvm_matcher_forward')
+        # device-resident state the pose stage continues from (no host round trip)
+        self.last = {'kpts': kp, 'counts': counts, 'n_pad': n_pad, 'pairs': pairs, 'pair_ids': list(pair_ids),
+                     'outs': outs, 'batch': B, 'n_views': T}
         return outs
 
 

@@ -20,7 +20,7 @@ class BundleAdjustGaussNewton2View(object):
         self.n_it = n_iterations
         self.last_trace = None
 
-    def run(self, n_kpts0, n_kpts1, conf, extr1, return_trace=False):
+    def run(self, n_kpts0, n_kpts1, conf, extr1, return_trace=False, n_valid=None, mask=None):
         lib = _lib.lib()
         dev = n_kpts0.device
         if dev.type != 'cuda':
@@ -36,7 +36,8 @@ class BundleAdjustGaussNewton2View(object):
         trace = torch.zeros(B, self.n_it + 1, dtype=torch.float32, device=dev) if return_trace else None
         with torch.cuda.device(dev):
             rc = lib.mvm_ba2view(_lib.ptr(k0), _lib.ptr(k1), _lib.ptr(c), _lib.ptr(T0), B, N, int(self.n_it),
-                                 _lib.ptr(Tout), _lib.ptr(valid), _lib.ptr(pts), _lib.ptr(trace), _lib.stream_ptr())
+                                 _lib.ptr(Tout), _lib.ptr(valid), _lib.ptr(pts), _lib.ptr(trace), _lib.ptr(n_valid), _lib.ptr(mask),
+                                 _lib.stream_ptr())
         _lib.check(rc, 'mvm_ba2view')
         valid_batch = valid.bool()
         n_valid = int(valid_batch.sum())

@@ -42,7 +42,8 @@ def get_kpts(data, result, id0, id1):
     return keypoints0, keypoints1, intr0, intr1, confidence
 
 
-def _run_w8pt(kpts0, kpts1, intr0, intr1, conf, choose_closest, T_021, determine_inliers):
+def _run_w8pt(kpts0, kpts1, intr0, intr1, conf, choose_closest, T_021, determine_inliers, n_valid=None,
+              success=None):
     lib = _lib.lib()
     dev = kpts0.device
     if dev.type != 'cuda':
@@ -64,7 +65,7 @@ def _run_w8pt(kpts0, kpts1, intr0, intr1, conf, choose_closest, T_021, determine
         rc = lib.mvm_w8pt(_lib.ptr(k0), _lib.ptr(k1), _lib.ptr(i0), _lib.ptr(i1), _lib.ptr(c), B, N,
                           _lib.ptr(Tg), int(bool(choose_closest)), int(bool(determine_inliers)),
                           _lib.ptr(T), _lib.ptr(k0n), _lib.ptr(k1n), _lib.ptr(cn), _lib.ptr(pos),
-                          _lib.ptr(inl), _lib.ptr(F), _lib.stream_ptr())
+                          _lib.ptr(inl), _lib.ptr(F), _lib.ptr(n_valid), _lib.ptr(success), _lib.stream_ptr())
     _lib.check(rc, 'mvm_w8pt')
     return T, k0n, k1n, cn, pos.bool(), (inl.bool() if inl is not None else None), F
 

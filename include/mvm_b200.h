@@ -133,22 +133,66 @@ int mvm_extract_matches(const float* scores, int batch, int m, int n, float matc
  *   conf [B,N] (un-normalised), T_gt [B,16] target pose for choose_closest (else NULL).
  * Outputs: T021 [B,16] row-major 4x4; kpts{0,1}_norm [B,N,2]; conf_norm [B,N] = conf/(sum+1e-6);
  * pos_depth_mask / inliers [B,N] bytes (inliers only when determine_inliers); F_out [B,9] the
- * normalised essential matrix (may be NULL).  The caller handles N < 8 -> (None, None). */
+ * normalised essential matrix (may be NULL).  n_valid [B] (device, may be NULL): effective
+ * keypoints per item when the arrays are padded to n; success [B] (may be NULL) is 0 for items
+ * with fewer than 8 keypoints (the reference returns (None, None), :85-86). */
 int mvm_w8pt(const float* kpts0, const float* kpts1, const float* intr0, const float* intr1,
              const float* conf, int batch, int n, const float* T_gt, int choose_closest,
              int determine_inliers, float* T021, float* kpts0_norm, float* kpts1_norm,
              float* conf_norm, unsigned char* pos_depth_mask, unsigned char* inliers,
-             float* F_out, void* stream);
+             float* F_out, const int* n_valid, unsigned char* success, void* stream);
 
 /* run_bundle_adjust_2_view -> BundleAdjustGaussNewton2View.run
  * (estimate_relative_pose.py:138-143, bundle_adjust_gauss_newton_2_view.py:127-201):
  * LM with the reference's schedule, Schur-complement step, one CTA per batch element.
  *   conf [B,N]: entries <= 0 are invalid matches; items with <= 6 valid matches get
  *   valid_batch = 0 and T_out = T_init.  pts_ws: B*N*3 doubles.  trace: [B,n_iterations+1]
- *   residual norms per evaluation, or NULL. */
+ *   residual norms per evaluation, or NULL.  n_valid [B] (may be NULL): effective keypoints per
+ *   item; mask [B,N] (may be NULL): matches with mask == 0 are dropped (the callers'
+ *   `confidence[~pos_depth_mask] = 0`, eval_pairs.py:251-252). */
 int mvm_ba2view(const float* kpts0_norm, const float* kpts1_norm, const float* conf,
                 const float* T_init, int batch, int n, int n_iterations, float* T_out,
-                unsigned char* valid_batch, double* pts_ws, float* trace, void* stream);
+                unsigned char* valid_batch, double* pts_ws, float* trace, const int* n_valid,
+                const unsigned char* mask, void* stream);
+
+/* ---- multi-view stage (pose_optimization/multi_view/) -------------------------------- */
+
+/* Order-preserving compaction of the valid matches of every (tuple, pair):
+ * valid = matches >= 0 and conf > conf_thresh (bundle_adjust_io.py:66-98, eval_pairs.py:215-222).
+ * kpts [B*T, n_pad, 2]; pairs[p].matches_a / .conf are the matcher outputs of that pair.
+ * Outputs [B, P, n_pad, ...] zero padded; n_valid [B, P] (device). */
+int mvm_gather_matches(const float* kpts, int n_views, int n_pad, const int* counts,
+                       const mvm_pair_io* pairs, int n_pairs, int batch, float conf_thresh,
+                       float* mkpts_a, float* mkpts_b, float* mconf, int* n_valid, void* stream);
+
+/* Maximum-spanning-tree initial extrinsics (bundle_adjust_io.py:135-172).  T_rel [B,P,16] relative
+ * poses a->b, weight [B,P] edge weights (number of matches), success [B,P]; extr [B,T,16] doubles,
+ * world->cam, view 0 = identity; on_tree [B,P] (may be NULL). */
+int mvm_spanning_tree_init(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch,
+                           const float* T_rel, const int* weight, const unsigned char* success,
+                           double* extr, unsigned char* on_tree, void* stream);
+
+/* Global bundle adjustment replacing the `bundle_adjuster` binary (ba_problem.cpp:115-157,
+ * ba_problem.h:60-151, problem construction bundle_adjust_io.py:193-259): camera 0 fixed, one 3-D
+ * point per pairwise match triangulated from extr_init, weights c / (0.5 (sum c + 1e-3)),
+ * Ceres-style trust-region LM with a Schur complement, fp64.  xn_a/xn_b [B,P,n_pad,2] normalised
+ * observations, conf [B,P,n_pad], n_valid [B,P], extr_init [B,T,16] doubles, extr_out [B,T,16]. */
+size_t mvm_mvba_workspace_bytes(int n_views, int n_pairs, int batch, int n_pad);
+int mvm_multi_view_ba(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch,
+                      int n_pad, const float* xn_a, const float* xn_b, const float* conf,
+                      const int* n_valid, const double* extr_init, float* extr_out,
+                      int max_iterations, int* iterations_out, double* cost_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---- instrumentation ----------------------------------------------------------------- */
+/* Kernels launched by the library since load (bench.py's gpu_launches). */
+unsigned long long mvm_launch_count(void);
+/* Optional CUDA-event profiler: when enabled every kernel-class scope is bracketed by events on
+ * its launching stream; collect() returns summed milliseconds / scope counts per class
+ * (0 gemm, 1 attention, 2 sinkhorn, 3 score gemm, 4 match extraction, 5 confidence head,
+ * 6 keypoint encoder, 7 w8pt, 8 two-view BA, 9 multi-view BA, 10 misc). */
+void mvm_profile_enable(int on);
+int mvm_profile_collect(double* ms_per_tag, int* n_per_tag, int n_tags);
 
 /* Library/build info: returns "mvm_b200 <version> sm_100a". */
 const char* mvm_version(void);
