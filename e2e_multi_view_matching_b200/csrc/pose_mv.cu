@@ -27,7 +27,7 @@ constexpr int NT = 256;
 constexpr int NW = NT / 32;
 constexpr int MAXC = 7;                 // free cameras (views - 1)
 constexpr int MAXU = 6 * MAXC;          // reduced unknowns
-constexpr int NPART = 112;              // doubles per CTA partial record
+constexpr int NPART = 128;              // doubles per CTA partial record
 
 // ---------------------------------------------------------------------------------------------
 // order-preserving compaction of the valid matches of every (tuple, pair)
@@ -616,6 +616,9 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
         if (lane == 0) acc[e] = fmax(acc[e], gmax);
+        // raw (scaled) camera gradient J_c^T r for the gradient-tolerance test
+        for (int c = 0; c < 6; ++c) wacc(acc + 104 + c, oa.Jc[0][c] * oa.r[0] + oa.Jc[1][c] * oa.r[1], lane);
+        for (int c = 0; c < 6; ++c) wacc(acc + 110 + c, ob.Jc[0][c] * ob.r[0] + ob.Jc[1][c] * ob.r[1], lane);
       }
       // gmax is a max, not a sum: fold the per-warp maxima before publishing
       __syncthreads();
@@ -624,7 +627,7 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         for (int w = 0; w < NW; ++w) { m = fmax(m, s_acc[w][103]); s_acc[w][103] = 0.0; }
         s_acc[0][103] = m;
       }
-      exchange(104);
+      exchange(116);
 
       // ---- assemble the reduced system from all partial records.  Every output element is owned
       // by one thread and summed over the pairs in a fixed order, so all CTAs of the tuple build
@@ -663,8 +666,17 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
           cost += __ldcg(rec + 102);
           gmax = fmax(gmax, __ldcg(rec + 103));
         }
-        // (the camera part of the gradient max-norm is not tracked separately: point and camera
-        // gradients vanish together at a stationary point)
+        // camera part of the unscaled gradient max-norm (Ceres tests max |J^T r|)
+        for (int v = 1; v < T; ++v)
+          for (int c = 0; c < 6; ++c) {
+            double gc = 0.0;
+            for (int q = 0; q < P; ++q) {
+              const double* rec = xch + (long long)q * NPART;
+              if (g.a[q] == v) gc += __ldcg(rec + 104 + c);
+              if (g.b[q] == v) gc += __ldcg(rec + 110 + c);
+            }
+            gmax = fmax(gmax, fabs(gc / s_sc[v][c]));
+          }
         for (int u = 0; u < nu; ++u) s_H[u * MAXU + u] += fmin(fmax(s_hd[u], 1e-6), 1e32) / radius;
         if (need_cost0) { s_ctl[2] = cost; if (g.cost_out && p == 0) g.cost_out[bi * 2] = cost; }
         s_ctl[3] = gmax;
