@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- view-tuples/sec of the hot path on synthetic 5-view x 1024-keypoint tuples.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--tuples B]
+
+A *step* is one pass of the hot path over one batch of B synthetic tuples per GPU
+(BASELINE.json configs[2]: ScanNet-shape 5-tuple, 1024 kpts, 28-layer matcher, confidence head,
+10 x {w8pt + two-view BA}, spanning tree, global GN/LM BA).  One JSON line on rank 0; see
+DESIGN.md §measurement for every field.  `--impl reference` times the CPU port of the reference
+path (oracle/) on the host cores -- /root/reference does not exist on the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_VIEWS, N_KPTS = 5, 1024
+LAYERS = (['self'] + ['cross'] * 3) * 7
+GAIN = 12.0          # final_proj gain of the seeded weights: gives the assignment real structure
+METRIC = 'view-tuples/sec @1024 kpts 5-view'
+
+# algorithmic work: attention QK^T + PV FLOPs per (layer launch, tuple)
+D = 256
+FLOPS_SELF = 4 * N_KPTS * N_KPTS * D * T_VIEWS                       # per tuple, per self layer
+FLOPS_CROSS = 4 * N_KPTS * (T_VIEWS - 1) * N_KPTS * D * T_VIEWS       # per tuple, per cross layer
+SINKHORN_BYTES_PER_PAIR = 100 * 2 * (N_KPTS + 1) ** 2 * 4 + 2 * (N_KPTS + 1) ** 2 * 4
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'tflops': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'source': 'measured (MEASURED_PEAKS.json, bf16 sustained / copy)'}
+    return {'hbm_gbs': 6650.0, 'tflops': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q,
+                                    '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in o.stdout.strip().split(',')]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for i, name in ((3, 'hw_slowdown'), (4, 'hw_thermal_slowdown'), (5, 'sw_thermal_slowdown'), (6, 'sw_power_cap')):
+            if any(s[i].lower().startswith('active') for s in self.samples):
+                reasons.append(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU port of the reference path (oracle) -- cpu_baseline leg and the --impl reference arm
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_tuple(sd, data_np, cap2=128, cap_ba=32):
+    """One tuple through the CPU restatement of the reference: full-size matcher (5 x 1024, 28
+    layers, 100 Sinkhorn iterations, confidence head), then the pose stage on a bounded number of
+    matches per pair (the reference's dense (6+3n)^2 two-view BA and a dense global BA are
+    cubic in n; cap2 / cap_ba say what the sample was)."""
+    from oracle.matcher_torch import matcher_forward
+    from oracle import pose as P, mvba as M
+    one = {k: (v[:1] if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
+    t0 = time.time()
+    res = matcher_forward(sd, {'GNN_layers': LAYERS, 'multi_frame_matching': True}, one)
+    t1 = time.time()
+    K = one['intr0'].astype(np.float64)
+    rel, weight, pm = {}, {}, {}
+    for b in range(T_VIEWS):
+        for a in range(b):
+            m = res['matches%d_%d_%d' % (a, a, b)][0]
+            c = res['conf_scores_%d_%d' % (a, b)][0, :, 0].astype(np.float64)
+            valid = np.nonzero((m >= 0) & (c > 0))[0][:cap2]
+            if valid.size < 8:
+                continue
+            k0 = one['keypoints%d' % a][0][valid].astype(np.float64)[None]
+            k1 = one['keypoints%d' % b][0][m[valid]].astype(np.float64)[None]
+            cc = c[valid][None, :, None]
+            Tw, info = P.estimate_relative_pose_w8pt(k0, k1, K, K, cc, determine_inliers=True)
+            cn = info['confidence'].copy()
+            cn[~info['pos_depth_mask']] = 0
+            ext, vb = P.run_bundle_adjust_2_view(info['kpts0_norm'], info['kpts1_norm'], cn, Tw, 10)
+            Tp = ext[0] if vb[0] else Tw[0]
+            rel[(a, b)], weight[(a, b)] = Tp, int(valid.size)
+            pm[(a, b)] = (info['kpts0_norm'][0][:cap_ba], info['kpts1_norm'][0][:cap_ba], c[valid][:cap_ba])
+    n_ok = len(rel)
+    if n_ok:
+        extr0, _ = M.spanning_tree_extrinsics(T_VIEWS, rel, weight)
+        M.solve(M.build_problem(T_VIEWS, pm, extr0))
+    t2 = time.time()
+    return t1 - t0, t2 - t1, n_ok
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from e2e_multi_view_matching_b200.synthetic import make_state_dict, make_scene_tuple_inputs
+    sd = make_state_dict(len(LAYERS), seed=0, final_proj_gain=GAIN)
+    data = make_scene_tuple_inputs(1000, T_VIEWS, N_KPTS, batch=1)
+    cores = os.cpu_count()
+    budget = 240.0
+    t_m, t_p, _ = cpu_reference_tuple(sd, data)           # warm-up / sizing step
+    per = t_m + t_p
+    warm = 0 if per * (args.steps + 1) > budget else min(args.warmup, 1)
+    steps = max(1, min(args.steps, int(budget / per) - warm - 1))
+    for _ in range(warm):
+        cpu_reference_tuple(sd, data)
+    t0 = time.time()
+    for _ in range(steps):
+        cpu_reference_tuple(sd, data)
+    dt = time.time() - t0
+    val = steps / dt
+    sample = ('1 tuple/step: matcher full size (5x1024 kpts, 28 layers, 100 Sinkhorn iters, conf head) + pose '
+              'stage on <=128 matches/pair (two-view, dense LU like the reference) and <=32 matches/pair (global BA)')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'tuples/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (matcher) / f64 (pose)', 'data': 'synthetic',
+            'config': {'workload': 'scannet_5tuple_1024kpts_28layers_mvba', 'tuples_per_step': 1},
+            'cpu_baseline': {'value': val, 'unit': 'tuples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'tuples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--tuples', type=int, default=8, help='tuples per step per GPU')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from e2e_multi_view_matching_b200 import _lib
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    from e2e_multi_view_matching_b200.pipeline import MultiViewPipeline, pose_auc
+    from e2e_multi_view_matching_b200.synthetic import make_state_dict, make_scene_tuple_inputs
+
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.lib()
+    B = args.tuples
+
+    sd = make_state_dict(len(LAYERS), seed=0, final_proj_gain=GAIN)
+    model = MultiViewMatcher({'GNN_layers': LAYERS}).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model = model.to(dev)
+    pipe = MultiViewPipeline(model)
+
+    # tuples 1000 + (rank*B + k): every rank works on its own shard (weak scaling, no data-path collective)
+    data_np = make_scene_tuple_inputs(1000 + rank * B, T_VIEWS, N_KPTS, batch=B)
+    keys = [k for k, v in data_np.items() if isinstance(v, np.ndarray) and not k.startswith('image')]
+    host = {k: torch.from_numpy(data_np[k]).pin_memory() for k in keys}
+    meta = {k: torch.empty(v.shape, device='meta') for k, v in data_np.items() if k.startswith('image')}
+    data_dev = {k: v.to(dev) for k, v in host.items()}
+    data_dev.update(meta)
+    data_dev['ids'] = data_np['ids']
+    h2d_keys = [k for k in keys if not k.startswith('pose')]
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in h2d_keys)
+    out_host = {'extrinsics': torch.empty(B, T_VIEWS, 4, 4).pin_memory(),
+                'T_pair': torch.empty(B, 10, 4, 4).pin_memory()}
+    d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
+    loss = torch.zeros(1, device=dev)
+
+    def step_device():
+        res, pose = pipe(data_dev)
+        if world > 1:   # one scalar all-reduce per step (mirrors the val-loss all_reduce, train.py:104-106)
+            loss.copy_(pose['ba_cost'][:, 1].sum().float().reshape(1))
+            dist.all_reduce(loss)
+        return pose
+
+    def step_e2e():
+        d = {k: host[k].to(dev, non_blocking=True) for k in h2d_keys}
+        d.update(meta)
+        d['ids'] = data_np['ids']
+        res, pose = pipe(d)
+        out_host['extrinsics'].copy_(pose['extrinsics'], non_blocking=True)
+        out_host['T_pair'].copy_(pose['T_pair'], non_blocking=True)
+        if world > 1:
+            loss.copy_(pose['ba_cost'][:, 1].sum().float().reshape(1))
+            dist.all_reduce(loss)
+        return pose
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for a, b in evs:
+            flush.zero_()                      # L2 flush between timed iterations (outside the events)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.time() - t0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), wall
+
+    for _ in range(args.warmup):
+        step_device()
+        step_e2e()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.mvm_launch_count()
+    ms_dev, wall_dev = timed(step_device, args.steps)
+    launches = lib.mvm_launch_count() - n0
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+
+    # live per-kernel-class timing (CUDA events on the launching stream) over two more steps
+    lib.mvm_profile_enable(1)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        flush.zero_()
+        pose = step_device()
+    torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    lib.mvm_profile_enable(0)
+
+    if rank == 0:
+        peaks = load_peaks()
+        total_tuples = B * args.steps * world
+        value = total_tuples / (ms_dev * 1e-3)
+        e2e = total_tuples / (ms_e2e * 1e-3)
+        att_ms, att_n = prof['attention']
+        n_self, n_cross = LAYERS.count('self'), LAYERS.count('cross')
+        att_flops = (n_self * FLOPS_SELF + n_cross * FLOPS_CROSS) * B * prof_steps   # over the profiled steps
+        att_tflops = att_flops / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
+        sk_ms, sk_n = prof['sinkhorn']
+        sk_gbs = SINKHORN_BYTES_PER_PAIR * 10 * B * prof_steps / (sk_ms * 1e-3) / 1e9 if sk_ms > 0 else 0.0
+        stage_ms = {k: round(v[0] / prof_steps, 4) for k, v in prof.items() if v[1] > 0}
+        # pose AUC of the engine on its own synthetic tuples (informational; parity is in tests/)
+        errs = MultiViewPipeline.pair_errors({k: v for k, v in data_dev.items() if k.startswith('pose')}, pose, T_VIEWS)
+        auc = pose_auc([e[0] for e in errs], [5, 10, 20])
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'tuples/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32 (matcher, CUDA cores) / f64 (pose kernels)', 'data': 'synthetic',
+            'config': {'workload': 'scannet_5tuple_1024kpts_28layers_mvba', 'tuples_per_step_per_gpu': B,
+                       'views': T_VIEWS, 'kpts': N_KPTS, 'gnn_layers': len(LAYERS), 'sinkhorn_iters': 100,
+                       'pose': '10x(w8pt+10it 2-view BA) + spanning tree + global LM BA (<=50 it)',
+                       'l2': 'flushed between timed steps (256 MB write)', 'parallelism': 'dp%d' % world},
+            'e2e': {'value': e2e, 'unit': 'tuples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(launches),
+            'clocks': sampler.summary(),
+            'roofline': {'kernel': 'attention (QK^T + PV, all views of one GNN layer per launch)', 'bound': 'tensor',
+                         'achieved': att_tflops, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                         'frac': att_tflops / peaks['tflops'], 'traffic': None, 'launches_timed': att_n,
+                         'peak_source': peaks['source']},
+            'roofline_sinkhorn': {'kernel': 'sinkhorn (10 pairs x B problems per launch)', 'bound': 'hbm',
+                                  'achieved': sk_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                                  'frac': sk_gbs / peaks['hbm_gbs'], 'traffic': None, 'launches_timed': sk_n},
+            'stage_ms_per_step': stage_ms,
+            'wall_s': {'device_resident': wall_dev, 'e2e': wall_e2e},
+            'pose_auc_5_10_20': [round(100 * a, 2) for a in auc],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            t_m, t_p, n_ok = cpu_reference_tuple(sd, data_np)
+            line['cpu_baseline'] = {
+                'value': 1.0 / (t_m + t_p), 'unit': 'tuples/s', 'cores': os.cpu_count(), 'kind': 'port',
+                'sample': '1 tuple: matcher full size %.1f s + pose stage on <=128 matches/pair (2-view) and <=32 '
+                          'matches/pair (global BA) %.1f s' % (t_m, t_p)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
