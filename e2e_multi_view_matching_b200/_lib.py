@@ -71,6 +71,12 @@ def lib():
     L.mvm_linear.restype = C.c_int
     L.mvm_linear.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int,
                              _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp]
+    L.mvm_linear_tc.restype = C.c_int
+    L.mvm_linear_tc.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int,
+                                _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _fp]
+    L.mvm_set_math_mode.restype = C.c_int
+    L.mvm_set_math_mode.argtypes = [C.c_int]
+    L.mvm_get_math_mode.restype = C.c_int
     L.mvm_attention.restype = C.c_int
     L.mvm_attention.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, _fp]
     L.mvm_sinkhorn_workspace_floats.restype = C.c_size_t

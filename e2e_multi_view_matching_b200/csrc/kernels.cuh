@@ -28,6 +28,9 @@ int launch_kenc_front(const float* kpts, const float* kscores, const float* cons
 int launch_transpose_cn(const float* in, float* out, int n_views_total, int C, int n_pad,
                         cudaStream_t stream);
 
+// tcgen05 GEMM (gemm_tc.cu): n_pass 3 = fp32-faithful 3xTF32, 1 = single-pass TF32
+int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_pad, cudaStream_t stream);
+
 struct AttnSegs {
   int n_views;
   int counts[8];

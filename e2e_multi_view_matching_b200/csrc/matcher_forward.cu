@@ -61,7 +61,15 @@ GemmDesc make_gemm(const float* A, int lda, const float* W, int K, const float* 
   return g;
 }
 
-int run_gemm(const GemmDesc& g, cudaStream_t s) { return launch_gemm_simt(g, s); }
+// math mode of the 1x1-conv GEMMs and attention: 0 = fp32 CUDA cores, 3 = tcgen05 3xTF32
+// (fp32-faithful, default), 1 = tcgen05 single-pass TF32
+int g_math_mode = 0;
+
+int run_gemm(const GemmDesc& g, cudaStream_t s) {
+  if (g_math_mode != 0 && g.batch == 1 && g.N % 128 == 0 && g.K % 32 == 0 && g.K1 % 32 == 0 && g.ldc % 4 == 0)
+    return launch_gemm_tc(g, g_math_mode, nullptr, 0, 0, s);
+  return launch_gemm_simt(g, s);
+}
 
 #define MVM_TRY(x)            \
   do {                        \
@@ -182,6 +190,24 @@ int mvm_linear(const float* A, int lda, const float* A2, int lda2, int K1, const
   if (A2) { g.A2 = A2; g.lda2 = lda2; g.K1 = K1; }
   if (R) { g.R = R; g.ldr = ldr; }
   return launch_gemm_simt(g, (cudaStream_t)stream);
+}
+
+int mvm_set_math_mode(int mode) {
+  MVM_REQUIRE(mode == 0 || mode == 1 || mode == 3);
+  g_math_mode = mode;
+  return MVM_OK;
+}
+int mvm_get_math_mode(void) { return g_math_mode; }
+
+int mvm_linear_tc(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw,
+                  const float* bias, const float* R, int ldr, float* C, int ldc, int M, int N, int K,
+                  float alpha, int relu, int n_pass, void* stream) {
+  MVM_REQUIRE(A && W && C && (n_pass == 1 || n_pass == 3));
+  GemmDesc g = make_gemm(A, lda, W, K, bias, C, ldc, M, N, relu);
+  g.ldw = ldw; g.alpha = alpha;
+  if (A2) { g.A2 = A2; g.lda2 = lda2; g.K1 = K1; }
+  if (R) { g.R = R; g.ldr = ldr; }
+  return launch_gemm_tc(g, n_pass, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
 int mvm_attention(const float* qkv, float* out, int batch, int n_views, int n_pad,

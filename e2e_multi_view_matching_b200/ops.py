@@ -7,9 +7,21 @@ import torch
 from . import _lib
 
 
-def linear(a, w, bias=None, a2=None, residual=None, relu=False, alpha=1.0):
-    """act(alpha * [a|a2] @ w.T + bias) + residual on point-major activations (Conv1d k=1)."""
+def linear(a, w, bias=None, a2=None, residual=None, relu=False, alpha=1.0, tc_passes=0):
+    """act(alpha * [a|a2] @ w.T + bias) + residual on point-major activations (Conv1d k=1).
+    tc_passes: 0 = fp32 CUDA cores, 3 = tcgen05 3xTF32, 1 = tcgen05 single-pass TF32."""
     lib = _lib.lib()
+    if tc_passes:
+        M, K1 = a.shape
+        K = K1 + (a2.shape[1] if a2 is not None else 0)
+        N = w.shape[0]
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        rc = lib.mvm_linear_tc(_lib.ptr(a), a.stride(0), _lib.ptr(a2), a2.stride(0) if a2 is not None else 0,
+                               K1, _lib.ptr(w), w.stride(0), _lib.ptr(bias), _lib.ptr(residual),
+                               residual.stride(0) if residual is not None else 0, _lib.ptr(out), N, M, N, K,
+                               float(alpha), int(relu), int(tc_passes), _lib.stream_ptr())
+        _lib.check(rc, 'mvm_linear_tc')
+        return out
     M, K1 = a.shape
     K = K1 + (a2.shape[1] if a2 is not None else 0)
     N = w.shape[0]

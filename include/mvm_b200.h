@@ -101,6 +101,18 @@ int mvm_linear(const float* A, int lda, const float* A2, int lda2, int K1, const
                int ldw, const float* bias, const float* R, int ldr, float* C, int ldc, int M,
                int N, int K, float alpha, int relu, void* stream);
 
+/* Same contract on the tensor cores (tcgen05.mma kind::tf32, TMA-fed, TMEM accumulator).
+ * n_pass = 3: fp32-faithful 3xTF32 (operands split hi/lo on chip); n_pass = 1: single-pass TF32.
+ * Needs N % 128 == 0, K % 32 == 0, K1 % 32 == 0, 16-byte aligned rows. */
+int mvm_linear_tc(const float* A, int lda, const float* A2, int lda2, int K1, const float* W,
+                  int ldw, const float* bias, const float* R, int ldr, float* C, int ldc, int M,
+                  int N, int K, float alpha, int relu, int n_pass, void* stream);
+
+/* Math mode of the matcher's GEMMs/attention inside mvm_matcher_forward: 0 = fp32 CUDA cores,
+ * 3 = tcgen05 3xTF32 (fp32-faithful), 1 = tcgen05 single-pass TF32 (torch 1.10's Ampere default). */
+int mvm_set_math_mode(int mode);
+int mvm_get_math_mode(void);
+
 /* Multi-head attention over key/value segments (superglue.py:87-109 with the multi-view
  * cross source of multi_view_matcher.py:92-95).  qkv [n_views_total, n_pad, 768]
  * (q|k|v, head-contiguous); view v attends to its own keys (is_cross = 0) or to all other
