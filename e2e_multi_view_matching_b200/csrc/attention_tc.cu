@@ -1,0 +1,394 @@
+// Flash-style multi-head attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) with
+// multi-view key/value segments.  Reference semantics: attention() superglue.py:87-91,
+// MultiHeadedAttention :94-109, cross source = concatenation of the other views
+// (multi_view_matcher.py:76-78,92-95).  prob[B,4,N,M] is never materialised.
+//
+// One CTA = 128 queries of one (view, head); keys/values stream through in tiles of 64.
+//   warp 0      TMA producer   Q [128x64] once; per tile K [64x64] (from QKV) and V^T [64 d x 64 keys]
+//   warp 1      tcgen05.mma issuer (one thread): S = Q K^T  (M128 N64 K64, kind::tf32) into one of two
+//               TMEM S buffers, O_tile = P V (M128 N64 K64) into a TMEM O buffer; software pipelined so
+//               S(j+1) is issued before P(j) is awaited
+//   warps 2-5   softmax: thread r owns query row r (TMEM lane r): tcgen05.ld S row, running max / sum in
+//               registers (no shuffles), exp2, P written to shared memory in the UMMA K-major 128B-swizzle
+//               layout, O_tile folded into a register accumulator with the online-softmax correction
+//   warps 6-9   (NPASS == 3) operand splitters: tf32 hi/lo planes of Q, K, V^T tiles in shared memory so
+//               that every product is A.B + A.B_lo + A_lo.B (fp32-faithful "3xTF32")
+// All operands are K-major: Q, K rows of the fused QKV projection [rows, 768]; V^T [view*256 + h*64 + d, key]
+// is written by the QKV GEMM epilogue (gemm_tc.cu).
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BQ = 128, BKV = 64, HD = 64;
+constexpr int SUB = 32;                       // fp32 elements per 128-byte swizzle row
+constexpr int Q_SUB_BYTES = BQ * SUB * 4;     // 16 KB  [128 rows x 128 B]
+constexpr int KV_SUB_BYTES = BKV * SUB * 4;   //  8 KB  [64 rows x 128 B]
+constexpr int Q_BYTES = 2 * Q_SUB_BYTES;      // d 0-31 | d 32-63
+constexpr int K_BYTES = 2 * KV_SUB_BYTES;
+constexpr int V_BYTES = 2 * KV_SUB_BYTES;     // keys 0-31 | keys 32-63 (rows = d)
+constexpr int P_BYTES = 2 * Q_SUB_BYTES;      // keys 0-31 | keys 32-63 (rows = queries)
+
+template <int NPASS>
+struct ACfg {
+  static constexpr int KST = 2;                         // K ring depth
+  static constexpr int VST = NPASS == 3 ? 1 : 2;        // V^T ring depth
+  static constexpr int PL = NPASS == 3 ? 2 : 1;         // planes (hi [, lo])
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES * PL;
+  static constexpr int OFF_V = OFF_K + KST * K_BYTES * PL;
+  static constexpr int OFF_P = OFF_V + VST * V_BYTES * PL;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES * PL;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int NTHREADS = NPASS == 3 ? 320 : 192;
+};
+
+struct AttnTcArgs {
+  float* out;          // [V, n_pad, 256]
+  int n_pad;
+  AttnSegs segs;
+  int is_cross;
+};
+
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// element-wise hi (in place) / lo split of a landed tile (layout agnostic)
+__device__ __forceinline__ void split_tile(uint8_t* hi_base, uint8_t* lo_base, int bytes, int t, int nthr) {
+  float4* h = reinterpret_cast<float4*>(hi_base);
+  float4* l = reinterpret_cast<float4*>(lo_base);
+  for (int i = t; i < bytes / 16; i += nthr) {
+    const float4 x = h[i];
+    float4 a, b;
+    a.x = tf32_rn(x.x); a.y = tf32_rn(x.y); a.z = tf32_rn(x.z); a.w = tf32_rn(x.w);
+    b.x = tf32_rn(x.x - a.x); b.y = tf32_rn(x.y - a.y); b.z = tf32_rn(x.z - a.z); b.w = tf32_rn(x.w - a.w);
+    h[i] = a;
+    l[i] = b;
+  }
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(ACfg<NPASS>::NTHREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, AttnTcArgs g) {
+  using C_ = ACfg<NPASS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_split = bars + 1;
+  uint64_t* k_full = bars + 2;     // [2]
+  uint64_t* k_empty = bars + 4;    // [2]
+  uint64_t* k_split = bars + 6;    // [2]
+  uint64_t* v_full = bars + 8;     // [2]
+  uint64_t* v_empty = bars + 10;   // [2]
+  uint64_t* v_split = bars + 12;   // [2]
+  uint64_t* s_full = bars + 14;    // [2]
+  uint64_t* s_empty = bars + 16;   // [2]
+  uint64_t* p_ready = bars + 18;
+  uint64_t* p_empty = bars + 19;
+  uint64_t* o_full = bars + 20;
+  uint64_t* o_empty = bars + 21;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ;
+  const int h = blockIdx.y;
+  const int v = blockIdx.z;
+  const int T = g.segs.n_views;
+  const int t = v % T, b = v / T;
+  if (q0 >= g.segs.counts[t]) return;
+
+  // flattened key-tile list of this query view: segments (views) in ascending order, 64 keys per tile
+  int nt = 0;
+  for (int s = 0; s < T; ++s) {
+    if (g.is_cross ? (s == t) : (s != t)) continue;
+    nt += (g.segs.counts[s] + BKV - 1) / BKV;
+  }
+  auto tile_info = [&](int j, int& seg, int& k0, int& cnt) {
+    int acc = 0;
+    for (int s = 0; s < T; ++s) {
+      if (g.is_cross ? (s == t) : (s != t)) continue;
+      const int n = (g.segs.counts[s] + BKV - 1) / BKV;
+      if (j < acc + n) { seg = s; k0 = (j - acc) * BKV; cnt = g.segs.counts[s]; return; }
+      acc += n;
+    }
+    seg = 0; k0 = 0; cnt = 0;
+  };
+
+  uint8_t* sQ = smem + C_::OFF_Q;
+  uint8_t* sQlo = sQ + Q_BYTES;
+  auto sK = [&](int s) { return smem + C_::OFF_K + s * K_BYTES * C_::PL; };
+  auto sV = [&](int s) { return smem + C_::OFF_V + s * V_BYTES * C_::PL; };
+  uint8_t* sP = smem + C_::OFF_P;
+  uint8_t* sPlo = sP + P_BYTES;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(q_full, 1);
+    tc::mbar_init(q_split, 128);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(k_full + i, 1); tc::mbar_init(k_empty + i, 1); tc::mbar_init(k_split + i, 128);
+      tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1); tc::mbar_init(v_split + i, 128);
+      tc::mbar_init(s_full + i, 1); tc::mbar_init(s_empty + i, 128);
+    }
+    tc::mbar_init(p_ready, 128); tc::mbar_init(p_empty, 1);
+    tc::mbar_init(o_full, 1); tc::mbar_init(o_empty, 128);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV); }
+  if (warp == 1) tc::tmem_alloc<256>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      const int qrow = v * g.n_pad + q0;
+      tc::mbar_arrive_expect_tx(q_full, Q_BYTES);
+      tc::tma_load_2d(sQ, &tmQ, q_full, h * HD, qrow);
+      tc::tma_load_2d(sQ + Q_SUB_BYTES, &tmQ, q_full, h * HD + SUB, qrow);
+      auto load_K = [&](int j) {
+        int seg, k0, cnt;
+        tile_info(j, seg, k0, cnt);
+        const int s = j % C_::KST;
+        tc::mbar_wait(k_empty + s, ((j / C_::KST) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(k_full + s, K_BYTES);
+        const int krow = (b * T + seg) * g.n_pad + k0;
+        tc::tma_load_2d(sK(s), &tmK, k_full + s, 256 + h * HD, krow);
+        tc::tma_load_2d(sK(s) + KV_SUB_BYTES, &tmK, k_full + s, 256 + h * HD + SUB, krow);
+      };
+      auto load_V = [&](int j) {
+        int seg, k0, cnt;
+        tile_info(j, seg, k0, cnt);
+        const int s = j % C_::VST;
+        tc::mbar_wait(v_empty + s, ((j / C_::VST) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(v_full + s, V_BYTES);
+        const int vrow = (b * T + seg) * 256 + h * HD;
+        tc::tma_load_2d(sV(s), &tmV, v_full + s, k0, vrow);
+        tc::tma_load_2d(sV(s) + KV_SUB_BYTES, &tmV, v_full + s, k0 + SUB, vrow);
+      };
+      load_K(0);
+      for (int j = 0; j < nt; ++j) {
+        load_V(j);
+        if (j + 1 < nt) load_K(j + 1);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(BQ, BKV);   // M=128, N=64 for both products
+      tc::mbar_wait(q_full, 0);
+      if (NPASS == 3) tc::mbar_wait(q_split, 0);
+      const uint32_t q_hi = tc::smem_u32(sQ), q_lo = tc::smem_u32(sQlo);
+      auto issue_S = [&](int j) {
+        const int s = j % C_::KST, sb = j & 1;
+        tc::mbar_wait(k_full + s, (j / C_::KST) & 1);
+        if (NPASS == 3) tc::mbar_wait(k_split + s, (j / C_::KST) & 1);
+        tc::mbar_wait(s_empty + sb, ((j >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t k_hi = tc::smem_u32(sK(s)), k_lo = k_hi + K_BYTES;
+        const uint32_t d = tmem_S0 + sb * 64;
+#pragma unroll
+        for (int kk = 0; kk < HD / 8; ++kk) {
+          const uint32_t offq = (kk >> 2) * Q_SUB_BYTES + (kk & 3) * 32;
+          const uint32_t offk = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
+          const uint64_t dq = tc::make_kmajor_sw128_desc(q_hi + offq), dk = tc::make_kmajor_sw128_desc(k_hi + offk);
+          tc::umma_tf32(d, dq, dk, idesc, kk != 0);
+          if (NPASS == 3) {
+            tc::umma_tf32(d, dq, tc::make_kmajor_sw128_desc(k_lo + offk), idesc, 1);
+            tc::umma_tf32(d, tc::make_kmajor_sw128_desc(q_lo + offq), dk, idesc, 1);
+          }
+        }
+        tc::umma_commit(s_full + sb);
+        tc::umma_commit(k_empty + s);
+      };
+      issue_S(0);
+      for (int j = 0; j < nt; ++j) {
+        if (j + 1 < nt) issue_S(j + 1);
+        const int s = j % C_::VST;
+        tc::mbar_wait(p_ready, j & 1);
+        tc::mbar_wait(v_full + s, (j / C_::VST) & 1);
+        if (NPASS == 3) tc::mbar_wait(v_split + s, (j / C_::VST) & 1);
+        tc::mbar_wait(o_empty, (j & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t p_hi = tc::smem_u32(sP), p_lo = tc::smem_u32(sPlo);
+        const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BKV / 8; ++kk) {
+          const uint32_t offp = (kk >> 2) * Q_SUB_BYTES + (kk & 3) * 32;
+          const uint32_t offv = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
+          const uint64_t dp = tc::make_kmajor_sw128_desc(p_hi + offp), dv = tc::make_kmajor_sw128_desc(v_hi + offv);
+          tc::umma_tf32(tmem_O, dp, dv, idesc, kk != 0);
+          if (NPASS == 3) {
+            tc::umma_tf32(tmem_O, dp, tc::make_kmajor_sw128_desc(v_lo + offv), idesc, 1);
+            tc::umma_tf32(tmem_O, tc::make_kmajor_sw128_desc(p_lo + offp), dv, idesc, 1);
+          }
+        }
+        tc::umma_commit(o_full);
+        tc::umma_commit(v_empty + s);
+        tc::umma_commit(p_empty);
+      }
+    }
+  } else if (warp < 6) {
+    // =========================== softmax / accumulate ===========================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    float acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float scale_l2e = 0.125f * 1.4426950408889634f;
+    uint8_t* prow = sP + row * 128;
+    uint8_t* prow_lo = sPlo + row * 128;
+    const int sw = row & 7;
+
+    auto fold_O = [&](int jprev) {
+      tc::mbar_wait(o_full, jprev & 1);
+      tc::tc_fence_after();
+      float o[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tc::tmem_ld32(tmem_O + lane_addr + c * 32, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[c * 32 + i] += o[i];
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(o_empty);
+    };
+
+    for (int j = 0; j < nt; ++j) {
+      int seg, k0, cnt;
+      tile_info(j, seg, k0, cnt);
+      const int sb = j & 1;
+      tc::mbar_wait(s_full + sb, (j >> 1) & 1);
+      tc::tc_fence_after();
+      float s[BKV];
+      tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr, s);
+      tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr + 32, s + 32);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(s_empty + sb);
+      float mx = -INFINITY;
+      const int nvalid = cnt - k0;      // keys of this tile that exist
+#pragma unroll
+      for (int i = 0; i < BKV; ++i) {
+        s[i] = (i < nvalid) ? s[i] * scale_l2e : -INFINITY;
+        mx = fmaxf(mx, s[i]);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = exp2f(m_run - m_new);
+      float rs = 0.f;
+#pragma unroll
+      for (int i = 0; i < BKV; ++i) {
+        s[i] = exp2f(s[i] - m_new);
+        rs += s[i];
+      }
+      l_run = l_run * corr + rs;
+      m_run = m_new;
+      // P -> shared memory (UMMA K-major, 128B swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7))
+      tc::mbar_wait(p_empty, (j & 1) ^ 1);
+#pragma unroll
+      for (int c = 0; c < BKV / 4; ++c) {
+        const int sub = c >> 3, ch = c & 7;
+        const int off = sub * Q_SUB_BYTES + ((ch ^ sw) << 4);
+        float4 hi = make_float4(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3]);
+        if (NPASS == 3) {
+          float4 a;
+          a.x = tf32_rn(hi.x); a.y = tf32_rn(hi.y); a.z = tf32_rn(hi.z); a.w = tf32_rn(hi.w);
+          float4 lo = make_float4(tf32_rn(hi.x - a.x), tf32_rn(hi.y - a.y), tf32_rn(hi.z - a.z), tf32_rn(hi.w - a.w));
+          *reinterpret_cast<float4*>(prow + off) = a;
+          *reinterpret_cast<float4*>(prow_lo + off) = lo;
+        } else {
+          *reinterpret_cast<float4*>(prow + off) = hi;
+        }
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(p_ready);
+      // fold the previous tile's P.V while the tensor core works on this one, then rescale
+      if (j > 0) fold_O(j - 1);
+#pragma unroll
+      for (int i = 0; i < HD; ++i) acc[i] *= corr;
+    }
+    fold_O(nt - 1);
+    if (q0 + row < g.n_pad) {
+      const float inv = 1.f / l_run;
+      float4* o4 = reinterpret_cast<float4*>(g.out + ((long long)v * g.n_pad + q0 + row) * 256 + h * HD);
+#pragma unroll
+      for (int i = 0; i < HD / 4; ++i)
+        o4[i] = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+    }
+  } else {
+    // =========================== operand splitters (NPASS == 3) ===========================
+    const int st = threadIdx.x - 192;   // 0..127
+    tc::mbar_wait(q_full, 0);
+    split_tile(sQ, sQlo, Q_BYTES, st, 128);
+    tc::fence_proxy_async();
+    tc::mbar_arrive(q_split);
+    auto split_K = [&](int j) {
+      const int s = j % C_::KST;
+      tc::mbar_wait(k_full + s, (j / C_::KST) & 1);
+      split_tile(sK(s), sK(s) + K_BYTES, K_BYTES, st, 128);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(k_split + s);
+    };
+    auto split_V = [&](int j) {
+      const int s = j % C_::VST;
+      tc::mbar_wait(v_full + s, (j / C_::VST) & 1);
+      split_tile(sV(s), sV(s) + V_BYTES, V_BYTES, st, 128);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(v_split + s);
+    };
+    split_K(0);
+    for (int j = 0; j < nt; ++j) {
+      split_V(j);
+      if (j + 1 < nt) split_K(j + 1);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<256>(tmem_base);
+}
+
+template <int NPASS>
+int launch_attn(const float* qkv, const float* vt, float* out, int batch, int n_pad, const AttnSegs& segs,
+                int is_cross, cudaStream_t stream) {
+  using C_ = ACfg<NPASS>;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attention_tc_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
+    attr = true;
+  }
+  const int V = batch * segs.n_views;
+  const long long rows = (long long)V * n_pad;
+  const CUtensorMap* tQ = mvm_get_tmap_2d(qkv, rows, 768, 768, BQ);
+  const CUtensorMap* tK = mvm_get_tmap_2d(qkv, rows, 768, 768, BKV);
+  const CUtensorMap* tV = mvm_get_tmap_2d(vt, (long long)V * 256, n_pad, n_pad, BKV);
+  if (!tQ || !tK || !tV) return MVM_ERR_LAUNCH;
+  AttnTcArgs g;
+  g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross;
+  dim3 grid(mvm_div_up(n_pad, BQ), 4, V);
+  attention_tc_kernel<NPASS><<<grid, C_::NTHREADS, C_::SMEM_BYTES, stream>>>(*tQ, *tK, *tV, g);
+  MVM_CHECK_LAUNCH();
+  return MVM_OK;
+}
+
+}  // namespace
+
+// qkv [V, n_pad, 768] (q | k | unused-v), vt [V, 256, n_pad] = V^T per head; out [V, n_pad, 256]
+int launch_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_pad, AttnSegs segs,
+                        int is_cross, int n_pass, cudaStream_t stream) {
+  MVM_REQUIRE(n_pad % 64 == 0 && segs.n_views >= 1 && segs.n_views <= 8);
+  MVM_REQUIRE(!is_cross || segs.n_views >= 2);
+  MvmProfScope prof__(MVM_TAG_ATTN, stream);
+  if (n_pass == 3) return launch_attn<3>(qkv, vt, out, batch, n_pad, segs, is_cross, stream);
+  return launch_attn<1>(qkv, vt, out, batch, n_pad, segs, is_cross, stream);
+}

@@ -35,6 +35,8 @@ struct AttnSegs {
   int n_views;
   int counts[8];
 };
+int launch_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_pad, AttnSegs segs,
+                        int is_cross, int n_pass, cudaStream_t stream);
 int launch_attention_simt(const float* qkv, float* out, int batch, int n_pad, AttnSegs segs,
                           int is_cross, cudaStream_t stream);
 

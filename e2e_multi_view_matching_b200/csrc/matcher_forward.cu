@@ -10,7 +10,7 @@
 namespace {
 
 struct Workspace {
-  float *DT, *H3, *H4, *X, *QKV, *MSG, *MRG, *H, *MD;
+  float *DT, *H3, *H4, *X, *QKV, *VT, *MSG, *MRG, *H, *MD;
   float* sink_ws;
   int* match_ws;
   float *FEAT, *SC, *CF1, *CF2, *CC0, *CC1;
@@ -33,6 +33,7 @@ Workspace carve(char* base, int batch, int n_views, int n_pad, int n_pairs, int 
   w.H4 = (float*)take(rows * 256 * 4);
   w.X = (float*)take(rows * 256 * 4);
   w.QKV = (float*)take(rows * 768 * 4);
+  w.VT = (float*)take(rows * 256 * 4);
   w.MSG = (float*)take(rows * 256 * 4);
   w.MRG = (float*)take(rows * 256 * 4);
   w.H = (float*)take(rows * 512 * 4);
@@ -141,8 +142,15 @@ int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, in
   // attentional GNN (multi_view_matcher.py:87-100 / superglue.py:131-140)
   for (int l = 0; l < w->n_layers; ++l) {
     const mvm_layer_weights& L = w->layers[l];
-    MVM_TRY(run_gemm(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), s));
-    MVM_TRY(launch_attention_simt(ws.QKV, ws.MSG, batch, n_pad, segs, L.is_cross, s));
+    if (g_math_mode != 0) {
+      // tensor-core path: the QKV GEMM epilogue also writes V^T [view, 256, n_pad] for the P.V product
+      MVM_TRY(launch_gemm_tc(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), g_math_mode,
+                             ws.VT, 512, n_pad, s));
+      MVM_TRY(launch_attention_tc(ws.QKV, ws.VT, ws.MSG, batch, n_pad, segs, L.is_cross, g_math_mode, s));
+    } else {
+      MVM_TRY(run_gemm(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), s));
+      MVM_TRY(launch_attention_simt(ws.QKV, ws.MSG, batch, n_pad, segs, L.is_cross, s));
+    }
     MVM_TRY(run_gemm(make_gemm(ws.MSG, 256, L.w_merge, 256, L.b_merge, ws.MRG, 256, rows, 256, 0), s));
     {
       GemmDesc g = make_gemm(ws.X, 256, L.w_mlp0, 512, L.b_mlp0, ws.H, 512, rows, 512, 1);
@@ -230,6 +238,15 @@ int mvm_log_optimal_transport(float* scores, int batch, int m, int n, float bin_
   tab.n_pairs = 1; tab.n_views = 2; tab.a[0] = 0; tab.b[0] = 1; tab.m[0] = m; tab.n[0] = n;
   tab.scores[0] = scores; tab.ws_off[0] = 0;
   return launch_sinkhorn(tab, batch, bin_score, iters, ws, (cudaStream_t)stream);
+}
+
+int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_views, int n_pad,
+                     const int* counts, int is_cross, int n_pass, void* stream) {
+  MVM_REQUIRE(qkv && vt && out && counts && n_views >= 1 && n_views <= 8 && (n_pass == 1 || n_pass == 3));
+  AttnSegs segs;
+  segs.n_views = n_views;
+  for (int t = 0; t < 8; ++t) segs.counts[t] = t < n_views ? counts[t] : 0;
+  return launch_attention_tc(qkv, vt, out, batch, n_pad, segs, is_cross, n_pass, (cudaStream_t)stream);
 }
 
 int mvm_log_optimal_transport_ref(float* scores, int batch, int m, int n, float bin_score,

@@ -34,12 +34,18 @@ def linear(a, w, bias=None, a2=None, residual=None, relu=False, alpha=1.0, tc_pa
     return out
 
 
-def attention(qkv, batch, n_views, counts, is_cross):
+def attention(qkv, batch, n_views, counts, is_cross, tc_passes=0):
     """qkv [batch*n_views, n_pad, 768] (q|k|v, head-contiguous) -> [batch*n_views, n_pad, 256]."""
     lib = _lib.lib()
     V, n_pad, _ = qkv.shape
     out = torch.zeros(V, n_pad, 256, dtype=torch.float32, device=qkv.device)
     cnt = (C.c_int * n_views)(*counts)
+    if tc_passes:
+        vt = qkv[:, :, 512:].transpose(1, 2).contiguous()      # [V, 256, n_pad]
+        rc = lib.mvm_attention_tc(_lib.ptr(qkv), _lib.ptr(vt), _lib.ptr(out), batch, n_views, n_pad, cnt,
+                                  int(is_cross), int(tc_passes), _lib.stream_ptr())
+        _lib.check(rc, 'mvm_attention_tc')
+        return out
     rc = lib.mvm_attention(_lib.ptr(qkv), _lib.ptr(out), batch, n_views, n_pad, cnt, int(is_cross),
                            _lib.stream_ptr())
     _lib.check(rc, 'mvm_attention')

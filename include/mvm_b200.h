@@ -120,6 +120,11 @@ int mvm_get_math_mode(void);
 int mvm_attention(const float* qkv, float* out, int batch, int n_views, int n_pad,
                   const int* counts, int is_cross, void* stream);
 
+/* The same attention on the tensor cores (tcgen05/TMEM/TMA flash kernel).  vt [n_views_total, 256,
+ * n_pad] holds V^T per head (written by the QKV GEMM epilogue); the v third of qkv is not read. */
+int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_views, int n_pad,
+                     const int* counts, int is_cross, int n_pass, void* stream);
+
 /* log_optimal_transport (superglue.py:143-172).  scores: [batch, m+1, n+1] buffers whose
  * inner [m,n] block holds the raw scores on entry; on exit the full coupling matrix
  * Z + u + v - norm.  ws: mvm_sinkhorn_workspace_floats(1, batch, max(m,n)) floats.

@@ -43,7 +43,7 @@ def stable_rows(Z, tau):
     return st0, st1
 
 
-def compare_matcher_outputs(ref, got, tau=2e-4, score_tol=(2e-4, 1e-5), min_stable=0.0):
+def compare_matcher_outputs(ref, got, tau=2e-4, score_tol=(2e-4, 1e-5), min_stable=0.0, conf_tol=2e-4):
     """ref: dict of numpy arrays (reference outputs), got: dict of numpy arrays (ours).
     - coupling matrices / confidences: allclose with abs + rel tolerance
     - matches: bit-exact on every keypoint whose decision margin exceeds tau
@@ -66,14 +66,14 @@ def compare_matcher_outputs(ref, got, tau=2e-4, score_tol=(2e-4, 1e-5), min_stab
             assert got[mk].dtype == np.int64 and got[mk].shape == ref[mk].shape
             assert np.array_equal(ref[mk][st], got[mk][st]), (mk, int((ref[mk][st] != got[mk][st]).sum()))
             same = ref[mk] == got[mk]
-            np.testing.assert_allclose(got[sk][same], ref[sk][same], rtol=2e-3, atol=1e-6)
+            np.testing.assert_allclose(got[sk][same], ref[sk][same], rtol=max(2e-3, 2 * score_tol[0]), atol=1e-6)
             report['unstable'] += int((~st).sum())
             report['rows'] += int(st.size)
         ck = 'conf_scores_%s_%s' % (a, b)
         if ck in ref:
             same = (ref['matches%s_%s_%s' % (a, a, b)] == got['matches%s_%s_%s' % (a, a, b)])
             cerr = np.abs(ref[ck][..., 0] - got[ck][..., 0])[same]
-            assert (cerr < 2e-4).all(), (ck, float(cerr.max()))
+            assert (cerr < conf_tol).all(), (ck, float(cerr.max()))
             report['max_conf_err'] = max(report['max_conf_err'], float(cerr.max()) if cerr.size else 0.0)
         report['n_pairs'] += 1
     assert report['n_pairs'] > 0

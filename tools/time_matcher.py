@@ -27,5 +27,11 @@ def main(T=5, N=1024, B=1, layers=None, reps=5):
     print('T=%d N=%d B=%d layers=%d: ms per forward' % (T, N, B, len(layers)), ['%.2f' % t for t in ts])
 
 if __name__ == '__main__':
+    import e2e_multi_view_matching_b200 as pkg
+    for mode in (0, 3, 1):
+        pkg.set_math_mode(mode)
+        print('math mode', mode)
+        main(B=4)
+    sys.exit(0)
     main()
     main(T=2, N=1024, B=8, layers=['self', 'cross'] * 9)
