@@ -161,6 +161,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--tuples', type=int, default=8, help='tuples per step per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--math-mode', type=int, default=3, choices=[0, 1, 3],
+                    help='3 = tcgen05 3xTF32 (fp32-faithful, default), 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA cores')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     rank = int(os.environ.get('RANK', 0))
@@ -182,6 +184,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.lib()
+    lib.mvm_set_math_mode(args.math_mode)
     B = args.tuples
 
     sd = make_state_dict(len(LAYERS), seed=0, final_proj_gain=GAIN)
@@ -289,11 +292,12 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': 'tuples/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32 (matcher, CUDA cores) / f64 (pose kernels)', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': {3: 'tf32x3 on tcgen05 (fp32-faithful) / f64 pose kernels', 1: 'tf32 on tcgen05 / f64 pose kernels',
+                      0: 'f32 CUDA cores / f64 pose kernels'}[args.math_mode], 'data': 'synthetic',
             'config': {'workload': 'scannet_5tuple_1024kpts_28layers_mvba', 'tuples_per_step_per_gpu': B,
                        'views': T_VIEWS, 'kpts': N_KPTS, 'gnn_layers': len(LAYERS), 'sinkhorn_iters': 100,
                        'pose': '10x(w8pt+10it 2-view BA) + spanning tree + global LM BA (<=50 it)',
-                       'l2': 'flushed between timed steps (256 MB write)', 'parallelism': 'dp%d' % world},
+                       'l2': 'flushed between timed steps (256 MB write)', 'math_mode': args.math_mode, 'parallelism': 'dp%d' % world},
             'e2e': {'value': e2e, 'unit': 'tuples/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(launches),

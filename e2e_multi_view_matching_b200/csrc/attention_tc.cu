@@ -51,11 +51,7 @@ struct AttnTcArgs {
   int is_cross;
 };
 
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+using tc::tf32_rn;
 
 // element-wise hi (in place) / lo split of a landed tile (layout agnostic)
 __device__ __forceinline__ void split_tile(uint8_t* hi_base, uint8_t* lo_base, int bytes, int t, int nthr) {

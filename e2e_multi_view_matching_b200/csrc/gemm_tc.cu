@@ -137,19 +137,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kt / C_::STAGES) & 1;
         tc::mbar_wait(full + s, ph);
         // lo planes are element-wise images of the landed tiles: same (swizzled) offsets
-        const float4* a = reinterpret_cast<const float4*>(stage_A(s));
+        // hi = rn_tf32(x) replaces the landed tile in place, lo = rn_tf32(x - hi) goes to the second
+        // buffer; both are element-wise images of the tile, so the (swizzled) offsets carry over
+        float4* a = reinterpret_cast<float4*>(stage_A(s));
         float4* alo = reinterpret_cast<float4*>(stage_Alo(s));
 #pragma unroll
         for (int i = 0; i < (BM * BK / 4) / 128; ++i) {
           const float4 x = a[et + i * 128];
-          alo[et + i * 128] = make_float4(tc::tf32_lo(x.x), tc::tf32_lo(x.y), tc::tf32_lo(x.z), tc::tf32_lo(x.w));
+          float4 h;
+          h.x = tc::tf32_rn(x.x); h.y = tc::tf32_rn(x.y); h.z = tc::tf32_rn(x.z); h.w = tc::tf32_rn(x.w);
+          a[et + i * 128] = h;
+          alo[et + i * 128] = make_float4(tc::tf32_rn(x.x - h.x), tc::tf32_rn(x.y - h.y), tc::tf32_rn(x.z - h.z),
+                                          tc::tf32_rn(x.w - h.w));
         }
-        const float4* w = reinterpret_cast<const float4*>(stage_W(s));
+        float4* w = reinterpret_cast<float4*>(stage_W(s));
         float4* wlo = reinterpret_cast<float4*>(stage_Wlo(s));
 #pragma unroll
         for (int i = 0; i < (BN * BK / 4) / 128; ++i) {
           const float4 x = w[et + i * 128];
-          wlo[et + i * 128] = make_float4(tc::tf32_lo(x.x), tc::tf32_lo(x.y), tc::tf32_lo(x.z), tc::tf32_lo(x.w));
+          float4 h;
+          h.x = tc::tf32_rn(x.x); h.y = tc::tf32_rn(x.y); h.z = tc::tf32_rn(x.z); h.w = tc::tf32_rn(x.w);
+          w[et + i * 128] = h;
+          wlo[et + i * 128] = make_float4(tc::tf32_rn(x.x - h.x), tc::tf32_rn(x.y - h.y), tc::tf32_rn(x.z - h.z),
+                                          tc::tf32_rn(x.w - h.w));
         }
         tc::fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
         tc::mbar_arrive(split + s);

@@ -127,10 +127,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// tf32 operand split for the 3-pass (fp32-faithful) mode: the tensor core reads the top 19 bits of
-// an fp32 container, so hi(x) = x & 0xFFFFE000 is what "x" means to it and lo(x) = x - hi(x) is exact.
-__device__ __forceinline__ float tf32_lo(float x) {
-  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+// tf32 operand split for the 3-pass (fp32-faithful) mode: hi = rn_tf32(x), lo = rn_tf32(x - hi);
+// A.B ~= hi_a hi_b + hi_a lo_b + lo_a hi_b with a relative error of a few 2^-22 per product.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
 
 }  // namespace tc
