@@ -83,7 +83,7 @@ def lib():
     L.mvm_attention.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, _fp]
     L.mvm_sinkhorn_workspace_floats.restype = C.c_size_t
     L.mvm_sinkhorn_workspace_floats.argtypes = [C.c_int, C.c_int, C.c_int]
-    for name in ('mvm_log_optimal_transport', 'mvm_log_optimal_transport_ref'):
+    for name in ('mvm_log_optimal_transport', 'mvm_log_optimal_transport_ref', 'mvm_log_optimal_transport_logdomain'):
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp]

@@ -48,6 +48,8 @@ int launch_sinkhorn_ref(const SinkhornTable& tab, int batch, float bin_score, in
                         float* ws, cudaStream_t stream);
 int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
                     cudaStream_t stream);
+int launch_sinkhorn_log(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
+                        cudaStream_t stream);
 size_t sinkhorn_ws_floats(int n_pairs, int batch, int n_pad);
 
 // idx_ws: ints [n_pairs*batch*2*n_pad] + floats; see match.cu

@@ -249,6 +249,15 @@ int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, i
   return launch_attention_tc(qkv, vt, out, batch, n_pad, segs, is_cross, n_pass, (cudaStream_t)stream);
 }
 
+int mvm_log_optimal_transport_logdomain(float* scores, int batch, int m, int n, float bin_score, int iters,
+                                        float* ws, void* stream) {
+  MVM_REQUIRE(scores && ws && batch >= 1 && m >= 1 && n >= 1);
+  PairTable tab;
+  tab.n_pairs = 1; tab.n_views = 2; tab.a[0] = 0; tab.b[0] = 1; tab.m[0] = m; tab.n[0] = n;
+  tab.scores[0] = scores; tab.ws_off[0] = 0;
+  return launch_sinkhorn_log(tab, batch, bin_score, iters, ws, (cudaStream_t)stream);
+}
+
 int mvm_log_optimal_transport_ref(float* scores, int batch, int m, int n, float bin_score,
                                   int iters, float* ws, void* stream) {
   MVM_REQUIRE(scores && ws && batch >= 1 && m >= 1 && n >= 1);

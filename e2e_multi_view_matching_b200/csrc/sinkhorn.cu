@@ -71,7 +71,7 @@ int launch_sinkhorn_ref(const SinkhornTable& tab, int batch, float bin_score, in
 }
 
 // =======================================================================================
-// v2: shared-memory-resident Sinkhorn.  A group of G co-resident CTAs owns one problem; CTA c
+// v2 (log domain, kept as the second on-device cross-check): shared-memory-resident Sinkhorn.  A group of G co-resident CTAs owns one problem; CTA c
 // keeps rows [c*R, (c+1)*R) of the inner m x n score block in shared memory for all
 // iterations, so the coupling matrix is read from HBM/L2 exactly once and written once
 // (the reference makes 200 full passes).  Per iteration:
@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_smem_kernel(PairTable tab, S
 
 }  // namespace
 
-int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
-                    cudaStream_t stream) {
+int launch_sinkhorn_log(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
+                        cudaStream_t stream) {
   MvmProfScope prof__(MVM_TAG_SINKHORN, stream);
   MVM_REQUIRE(tab.n_pairs >= 1 && tab.n_pairs <= MVM_MAX_PAIRS && batch >= 1);
   static int n_sm = 0;

@@ -52,7 +52,7 @@ def attention(qkv, batch, n_views, counts, is_cross, tc_passes=0):
     return out
 
 
-def log_optimal_transport(scores, alpha, iters, ref_kernel=False):
+def log_optimal_transport(scores, alpha, iters, ref_kernel=False, kernel=None):
     """superglue.py:152-172: scores [B,m,n] -> couplings [B,m+1,n+1]."""
     lib = _lib.lib()
     B, m, n = scores.shape
@@ -60,7 +60,8 @@ def log_optimal_transport(scores, alpha, iters, ref_kernel=False):
     Z[:, :m, :n] = scores
     nws = lib.mvm_sinkhorn_workspace_floats(1, B, max(m, n))
     ws = torch.empty(nws, dtype=torch.float32, device=scores.device)
-    fn = lib.mvm_log_optimal_transport_ref if ref_kernel else lib.mvm_log_optimal_transport
+    fn = {None: lib.mvm_log_optimal_transport, 'ref': lib.mvm_log_optimal_transport_ref,
+          'log': lib.mvm_log_optimal_transport_logdomain}['ref' if ref_kernel else kernel]
     rc = fn(_lib.ptr(Z), B, m, n, float(alpha), int(iters), _lib.ptr(ws), _lib.stream_ptr())
     _lib.check(rc, 'mvm_log_optimal_transport')
     return Z

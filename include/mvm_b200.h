@@ -128,13 +128,17 @@ int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, i
 /* log_optimal_transport (superglue.py:143-172).  scores: [batch, m+1, n+1] buffers whose
  * inner [m,n] block holds the raw scores on entry; on exit the full coupling matrix
  * Z + u + v - norm.  ws: mvm_sinkhorn_workspace_floats(1, batch, max(m,n)) floats.
- * The shared-memory-resident multi-CTA kernel; _ref is the one-CTA-per-problem kernel that
- * walks the matrix in L2/HBM like the reference does (kept as the on-device cross-check). */
+ * mvm_log_optimal_transport is the production kernel (shared-memory-resident, stabilised scaling
+ * domain, FMA inner loops); _logdomain is the same multi-CTA layout iterating in the log domain
+ * exactly like the reference; _ref is the one-CTA-per-problem kernel that walks the matrix in
+ * L2/HBM (both kept as on-device cross-checks). */
 size_t mvm_sinkhorn_workspace_floats(int n_pairs, int batch, int n_max);
 int mvm_log_optimal_transport(float* scores, int batch, int m, int n, float bin_score,
                               int iters, float* ws, void* stream);
 int mvm_log_optimal_transport_ref(float* scores, int batch, int m, int n, float bin_score,
                                   int iters, float* ws, void* stream);
+int mvm_log_optimal_transport_logdomain(float* scores, int batch, int m, int n, float bin_score,
+                                        int iters, float* ws, void* stream);
 
 /* Mutual-nearest-neighbour extraction (multi_view_matcher.py:288-300).
  * ws: 3 * batch * round_up(max(m,n), 64) 4-byte words. */

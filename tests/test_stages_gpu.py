@@ -45,7 +45,7 @@ def test_attention_self_and_cross_ragged():
 
 
 @pytest.mark.parametrize('shape', [(1, 60, 50), (3, 128, 128), (2, 33, 200), (1, 300, 257)])
-@pytest.mark.parametrize('spread', [1.0, 12.0])
+@pytest.mark.parametrize('spread', [1.0, 12.0, 40.0])
 def test_sinkhorn_kernels_vs_oracle(shape, spread):
     from e2e_multi_view_matching_b200 import ops
     from oracle.matcher import log_optimal_transport
@@ -53,10 +53,10 @@ def test_sinkhorn_kernels_vs_oracle(shape, spread):
     rng = np.random.default_rng(m * 1000 + n)
     s = (rng.standard_normal((B, m, n)) * spread).astype(np.float32)
     ref = log_optimal_transport(s, 1.0, 100)
-    for ref_kernel in (True, False):
-        Z = ops.log_optimal_transport(torch.from_numpy(s).cuda(), 1.0, 100, ref_kernel=ref_kernel).cpu().numpy()
+    for kernel in ('ref', 'log', None):
+        Z = ops.log_optimal_transport(torch.from_numpy(s).cuda(), 1.0, 100, kernel=kernel).cpu().numpy()
         err = np.abs(Z - ref)
-        assert (err <= 1e-4 + 1e-5 * np.abs(ref)).all(), (ref_kernel, float(err.max()))
+        assert (err <= 1e-4 + 1e-5 * np.abs(ref)).all(), (kernel, float(err.max()))
 
 
 def test_sinkhorn_full_size_marginals():
