@@ -300,7 +300,7 @@ int launch_sinkhorn_log(const SinkhornTable& tab, int batch, float bin_score, in
 
 size_t sinkhorn_ws_floats(int n_pairs, int batch, int n_pad) {
   // counters + worst-case exchange ((2G+1)(n+1) per group, G*NG <= 148) and the v1 (u,v) scratch
-  const size_t xch = 256 + (size_t)(2 * 148 + 148) * (n_pad + 1);
+  const size_t xch = 256 + (size_t)(2 * 148 + 148) * (n_pad + 1) * 2;   // log-domain partials / 8-byte LL words
   const size_t uv = (size_t)n_pairs * batch * (2 * (size_t)n_pad + 2);
   return xch > uv ? xch : uv;
 }
