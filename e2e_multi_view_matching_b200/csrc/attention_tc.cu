@@ -9,8 +9,9 @@
 //               TMEM S buffers, O_tile = P V (M128 N64 K64) into a TMEM O buffer; software pipelined so
 //               S(j+1) is issued before P(j) is awaited
 //   warps 2-5   softmax: thread r owns query row r (TMEM lane r): tcgen05.ld S row, running max / sum in
-//               registers (no shuffles), exp2, P written to shared memory in the UMMA K-major 128B-swizzle
-//               layout, O_tile folded into a register accumulator with the online-softmax correction
+//               registers (no shuffles), exp2, P written back to TENSOR MEMORY (tcgen05.st) and consumed
+//               as the A operand of P.V straight from TMEM, O_tile folded into a register accumulator with
+//               the online-softmax correction
 //   warps 6-9   (NPASS == 3) operand splitters: tf32 hi/lo planes of Q, K, V^T tiles in shared memory so
 //               that every product is A.B + A.B_lo + A_lo.B (fp32-faithful "3xTF32")
 // All operands are K-major: Q, K rows of the fused QKV projection [rows, 768]; V^T [view*256 + h*64 + d, key]
@@ -33,15 +34,17 @@ constexpr int P_BYTES = 2 * Q_SUB_BYTES;      // keys 0-31 | keys 32-63 (rows = 
 template <int NPASS>
 struct ACfg {
   static constexpr int KST = 2;                         // K ring depth
-  static constexpr int VST = NPASS == 3 ? 1 : 2;        // V^T ring depth
+  static constexpr int VST = 2;                         // V^T ring depth
   static constexpr int PL = NPASS == 3 ? 2 : 1;         // planes (hi [, lo])
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + Q_BYTES * PL;
   static constexpr int OFF_V = OFF_K + KST * K_BYTES * PL;
-  static constexpr int OFF_P = OFF_V + VST * V_BYTES * PL;
-  static constexpr int OFF_BAR = OFF_P + P_BYTES * PL;
+  static constexpr int OFF_BAR = OFF_V + VST * V_BYTES * PL;
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
   static constexpr int NTHREADS = NPASS == 3 ? 320 : 192;
+  static constexpr int MIN_CTAS = NPASS == 3 ? 1 : 2;
+  // TMEM columns: S0 [0,64) S1 [64,128) O [128,192) P_hi [192,256) (P_lo [256,320))
+  static constexpr int TMEM_COLS = NPASS == 3 ? 512 : 256;
 };
 
 struct AttnTcArgs {
@@ -68,7 +71,7 @@ __device__ __forceinline__ void split_tile(uint8_t* hi_base, uint8_t* lo_base, i
 }
 
 template <int NPASS>
-__global__ void __launch_bounds__(ACfg<NPASS>::NTHREADS, 1)
+__global__ void __launch_bounds__(ACfg<NPASS>::NTHREADS, ACfg<NPASS>::MIN_CTAS)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, AttnTcArgs g) {
   using C_ = ACfg<NPASS>;
@@ -120,8 +123,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQlo = sQ + Q_BYTES;
   auto sK = [&](int s) { return smem + C_::OFF_K + s * K_BYTES * C_::PL; };
   auto sV = [&](int s) { return smem + C_::OFF_V + s * V_BYTES * C_::PL; };
-  uint8_t* sP = smem + C_::OFF_P;
-  uint8_t* sPlo = sP + P_BYTES;
 
   if (threadIdx.x == 0) {
     tc::mbar_init(q_full, 1);
@@ -136,12 +137,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV); }
-  if (warp == 1) tc::tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tc::tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192, tmem_Plo = tmem_base + 256;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -214,17 +215,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (NPASS == 3) tc::mbar_wait(v_split + s, (j / C_::VST) & 1);
         tc::mbar_wait(o_empty, (j & 1) ^ 1);
         tc::tc_fence_after();
-        const uint32_t p_hi = tc::smem_u32(sP), p_lo = tc::smem_u32(sPlo);
         const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
 #pragma unroll
         for (int kk = 0; kk < BKV / 8; ++kk) {
-          const uint32_t offp = (kk >> 2) * Q_SUB_BYTES + (kk & 3) * 32;
           const uint32_t offv = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
-          const uint64_t dp = tc::make_kmajor_sw128_desc(p_hi + offp), dv = tc::make_kmajor_sw128_desc(v_hi + offv);
-          tc::umma_tf32(tmem_O, dp, dv, idesc, kk != 0);
+          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + offv);
+          tc::umma_tf32_ts(tmem_O, tmem_P + kk * 8, dv, idesc, kk != 0);       // A = P from tensor memory
           if (NPASS == 3) {
-            tc::umma_tf32(tmem_O, dp, tc::make_kmajor_sw128_desc(v_lo + offv), idesc, 1);
-            tc::umma_tf32(tmem_O, tc::make_kmajor_sw128_desc(p_lo + offp), dv, idesc, 1);
+            tc::umma_tf32_ts(tmem_O, tmem_P + kk * 8, tc::make_kmajor_sw128_desc(v_lo + offv), idesc, 1);
+            tc::umma_tf32_ts(tmem_O, tmem_Plo + kk * 8, dv, idesc, 1);
           }
         }
         tc::umma_commit(o_full);
@@ -242,9 +241,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < HD; ++i) acc[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     const float scale_l2e = 0.125f * 1.4426950408889634f;
-    uint8_t* prow = sP + row * 128;
-    uint8_t* prow_lo = sPlo + row * 128;
-    const int sw = row & 7;
 
     auto fold_O = [&](int jprev) {
       tc::mbar_wait(o_full, jprev & 1);
@@ -290,24 +286,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       l_run = l_run * corr + rs;
       m_run = m_new;
-      // P -> shared memory (UMMA K-major, 128B swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7))
+      // P -> tensor memory (row r = lane r, keys along columns): the A operand of P.V
       tc::mbar_wait(p_empty, (j & 1) ^ 1);
+      if (NPASS == 3) {
+        float lo[32];
 #pragma unroll
-      for (int c = 0; c < BKV / 4; ++c) {
-        const int sub = c >> 3, ch = c & 7;
-        const int off = sub * Q_SUB_BYTES + ((ch ^ sw) << 4);
-        float4 hi = make_float4(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3]);
-        if (NPASS == 3) {
-          float4 a;
-          a.x = tf32_rn(hi.x); a.y = tf32_rn(hi.y); a.z = tf32_rn(hi.z); a.w = tf32_rn(hi.w);
-          float4 lo = make_float4(tf32_rn(hi.x - a.x), tf32_rn(hi.y - a.y), tf32_rn(hi.z - a.z), tf32_rn(hi.w - a.w));
-          *reinterpret_cast<float4*>(prow + off) = a;
-          *reinterpret_cast<float4*>(prow_lo + off) = lo;
-        } else {
-          *reinterpret_cast<float4*>(prow + off) = hi;
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float hi = tf32_rn(s[c * 32 + i]);
+            lo[i] = tf32_rn(s[c * 32 + i] - hi);
+            s[c * 32 + i] = hi;
+          }
+          tc::tmem_st32(tmem_Plo + lane_addr + c * 32, lo);
         }
       }
-      tc::fence_proxy_async();
+      tc::tmem_st32(tmem_P + lane_addr, s);
+      tc::tmem_st32(tmem_P + lane_addr + 32, s + 32);
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
       tc::mbar_arrive(p_ready);
       // fold the previous tile's P.V while the tensor core works on this one, then rescale
       if (j > 0) fold_O(j - 1);
@@ -351,7 +348,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<256>(tmem_base);
+  if (warp == 1) tc::tmem_dealloc<C_::TMEM_COLS>(tmem_base);
 }
 
 template <int NPASS>

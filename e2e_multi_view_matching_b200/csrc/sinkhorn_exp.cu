@@ -26,18 +26,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// "LL" exchange: a value and the tag of the step that produced it travel in one 8-byte word (a single
-// store / load transaction), so the consumer polls the data itself -- no barrier, no memory fence.
-__device__ __forceinline__ void ll_store(float2* p, float v, unsigned tag) {
-  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
-}
-__device__ __forceinline__ float ll_load(const float2* p, unsigned tag) {
-  unsigned v, t;
-  do {
-    asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(p) : "memory");
-  } while (t != tag);
-  return __uint_as_float(v);
-}
 __device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -89,8 +77,8 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
     float* ut_s = kb_s + (n + 1);             // [R]      absorbed row potentials u~_i
     float* a_s = ut_s + R;                    // [R+1]    row scalings a_i, a_s[R] = a_m (dustbin row)
     float* e_s = a_s + (R + 1);               // [R]      exp(alpha + u~_i): dustbin column of K~ / kb_n
-    float2* cpart = reinterpret_cast<float2*>(xch) + (size_t)group * cfg.xch_stride;   // [G][n+1] (partial sum, tag)
-    float2* bx = cpart + (size_t)G * (n + 1);                                           // [n+1]    (b_j, tag)
+    float* cpart = xch + (size_t)group * cfg.xch_stride;   // [G][n+1] partial column sums
+    float* bx = cpart + (size_t)G * (n + 1);               // [n+1]    merged b
 
     const float norm = -logf((float)(m + n));
     const float mu = 1.0f / (float)(m + n), mu_bin = (float)n / (float)(m + n);
@@ -110,18 +98,41 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
     __syncthreads();
 
     for (int it = 0; it < cfg.iters; ++it) {
-      const unsigned tag = (unsigned)(prob / cfg.NG) * (unsigned)cfg.iters + (unsigned)it + 1u;   // unique per (problem, iteration) of this group
       // ---- row pass: a_i = mu / (sum_j K~_ij b_j + e_i kb_n b_n) ----
+      // each lane keeps its b_j (columns 4*lane + 128*k ...) in registers for all rows of the pass
       const float bin_col = kb_s[n] * b_s[n];
       bool row_bad = false;
-      for (int r = warp; r < nrows; r += NW) {
-        const float* kr = Ks + (size_t)r * n;
-        float s = 0.f;
-        for (int j = lane; j < n; j += 32) s = fmaf(kr[j], b_s[j], s);
-        s = warp_sum(s);
-        const float a = mu / (s + e_s[r] * bin_col);
-        if (lane == 0) a_s[r] = a;
-        row_bad |= (a > ABSORB_HI) | (a < ABSORB_LO);
+      if ((n & 127) == 0 && n <= 2048) {
+        float4 breg[16];
+        const int nch = n >> 7;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k < nch) breg[k] = *reinterpret_cast<const float4*>(b_s + k * 128 + lane * 4);
+        for (int r = warp; r < nrows; r += NW) {
+          const float4* kr = reinterpret_cast<const float4*>(Ks + (size_t)r * n);
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k < nch) {
+              const float4 x = kr[k * 32 + lane];
+              s = fmaf(x.x, breg[k].x, s); s = fmaf(x.y, breg[k].y, s);
+              s = fmaf(x.z, breg[k].z, s); s = fmaf(x.w, breg[k].w, s);
+            }
+          s = warp_sum(s);
+          const float a = mu / (s + e_s[r] * bin_col);
+          if (lane == 0) a_s[r] = a;
+          row_bad |= (a > ABSORB_HI) | (a < ABSORB_LO);
+        }
+      } else {
+        for (int r = warp; r < nrows; r += NW) {
+          const float* kr = Ks + (size_t)r * n;
+          float s = 0.f;
+          for (int j = lane; j < n; j += 32) s = fmaf(kr[j], b_s[j], s);
+          s = warp_sum(s);
+          const float a = mu / (s + e_s[r] * bin_col);
+          if (lane == 0) a_s[r] = a;
+          row_bad |= (a > ABSORB_HI) | (a < ABSORB_LO);
+        }
       }
       if (warp == NW - 1) {   // dustbin row (replicated in every CTA): a_m = mu_bin / sum_j kb_j b_j
         float s = 0.f;
@@ -144,30 +155,41 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
       }
       // ---- column pass: partial c_j = sum_{own rows} K~_ij a_i ; dustbin column: kb_n sum e_i a_i ----
       for (int j = tid; j < n; j += blockDim.x) {
-        float s = 0.f;
-        for (int r = 0; r < nrows; ++r) s = fmaf(Ks[(size_t)r * n + j], a_s[r], s);
-        ll_store(cpart + (size_t)c * (n + 1) + j, s, tag);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int r = 0;
+        for (; r + 3 < nrows; r += 4) {
+          s0 = fmaf(Ks[(size_t)r * n + j], a_s[r], s0);
+          s1 = fmaf(Ks[(size_t)(r + 1) * n + j], a_s[r + 1], s1);
+          s2 = fmaf(Ks[(size_t)(r + 2) * n + j], a_s[r + 2], s2);
+          s3 = fmaf(Ks[(size_t)(r + 3) * n + j], a_s[r + 3], s3);
+        }
+        for (; r < nrows; ++r) s0 = fmaf(Ks[(size_t)r * n + j], a_s[r], s0);
+        __stcg(cpart + (size_t)c * (n + 1) + j, (s0 + s1) + (s2 + s3));
       }
       if (warp == NW - 1) {
         float s = 0.f;
         for (int r = lane; r < nrows; r += 32) s = fmaf(e_s[r], a_s[r], s);
         s = warp_sum(s);
-        if (lane == 0) ll_store(cpart + (size_t)c * (n + 1) + n, s * kb_s[n], tag);
+        if (lane == 0) __stcg(cpart + (size_t)c * (n + 1) + n, s * kb_s[n]);
       }
+      bar_count += G;
+      group_barrier(ctr, bar_count);
       // ---- merge this CTA's column slice in a fixed order: b_j = nu_j / (sum_g c_j^g + kb_j a_m) ----
       {
         const float am = a_s[R];
         for (int j = c0 + warp; j < c1; j += NW) {
           float s = 0.f;
-          for (int g = lane; g < G; g += 32) s += ll_load(cpart + (size_t)g * (n + 1) + j, tag);
+          for (int g = lane; g < G; g += 32) s += __ldcg(cpart + (size_t)g * (n + 1) + j);
           s = warp_sum(s);
-          if (lane == 0) ll_store(bx + j, (j < n ? nu : nu_bin) / (s + kb_s[j] * am), tag);
+          if (lane == 0) __stcg(bx + j, (j < n ? nu : nu_bin) / (s + kb_s[j] * am));
         }
       }
+      bar_count += G;
+      group_barrier(ctr, bar_count);
       // ---- reload b; column re-absorption decided identically by every CTA of the group ----
       float bmx = 0.f, bmn = 3.0e38f;
       for (int j = tid; j <= n; j += blockDim.x) {
-        const float bv = ll_load(bx + j, tag);
+        const float bv = __ldcg(bx + j);
         b_s[j] = bv;
         bmx = fmaxf(bmx, bv);
         bmn = fminf(bmn, bv);
@@ -250,11 +272,10 @@ int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int it
   if (G < g_min) G = g_min;
   SinkCfg cfg;
   cfg.G = G; cfg.NG = NG; cfg.batch = batch; cfg.iters = iters; cfg.alpha = bin_score;
-  cfg.xch_stride = (G + 1) * (max_n + 1);   // in float2 words
+  cfg.xch_stride = (G + 1) * (max_n + 1);
   unsigned* ctrs = reinterpret_cast<unsigned*>(ws);
   float* xch = ws + 256;
-  // counters + LL exchange words start from tag 0 (tags are >= 1)
-  cudaMemsetAsync(ws, 0, (256 + 2 * (size_t)NG * cfg.xch_stride) * sizeof(float), stream);
+  cudaMemsetAsync(ctrs, 0, 256 * sizeof(float), stream);
   const size_t smem = smem_need(G);
   sinkhorn_exp_kernel<<<G * NG, 1024, smem, stream>>>(tab, cfg, xch, ctrs);
   MVM_CHECK_LAUNCH();
