@@ -4,10 +4,11 @@
 // (multi_view_matcher.py:76-78,92-95).  prob[B,4,N,M] is never materialised.
 //
 // One CTA = 128 queries of one (view, head); keys/values stream through in tiles of 64.
-//   warp 0      TMA producer   Q [128x64] once; per tile K [64x64] (from QKV) and V^T [64 d x 64 keys]
+//   warp 0      TMA producer   per tile K [64x64] (from QKV) and V^T [64 d x 64 keys], 3-deep rings
 //   warp 1      tcgen05.mma issuer (one thread): S = Q K^T  (M128 N64 K64, kind::tf32) into one of two
-//               TMEM S buffers, O_tile = P V (M128 N64 K64) into a TMEM O buffer; software pipelined so
-//               S(j+1) is issued before P(j) is awaited
+//               TMEM S buffers, O_tile = P V (M128 N64 K64) into a TMEM O buffer; BOTH A operands (Q and P)
+//               live in tensor memory, so shared-memory bandwidth only carries the K / V^T tiles;
+//               software pipelined so S(j+1) is issued before P(j) is awaited
 //   warps 2-5   softmax: thread r owns query row r (TMEM lane r): tcgen05.ld S row, running max / sum in
 //               registers (no shuffles), exp2, P written back to TENSOR MEMORY (tcgen05.st) and consumed
 //               as the A operand of P.V straight from TMEM, O_tile folded into a register accumulator with
@@ -24,30 +25,27 @@ namespace {
 
 constexpr int BQ = 128, BKV = 64, HD = 64;
 constexpr int SUB = 32;                       // fp32 elements per 128-byte swizzle row
-constexpr int Q_SUB_BYTES = BQ * SUB * 4;     // 16 KB  [128 rows x 128 B]
 constexpr int KV_SUB_BYTES = BKV * SUB * 4;   //  8 KB  [64 rows x 128 B]
-constexpr int Q_BYTES = 2 * Q_SUB_BYTES;      // d 0-31 | d 32-63
-constexpr int K_BYTES = 2 * KV_SUB_BYTES;
+constexpr int K_BYTES = 2 * KV_SUB_BYTES;     // d 0-31 | d 32-63      (rows = keys)
 constexpr int V_BYTES = 2 * KV_SUB_BYTES;     // keys 0-31 | keys 32-63 (rows = d)
-constexpr int P_BYTES = 2 * Q_SUB_BYTES;      // keys 0-31 | keys 32-63 (rows = queries)
 
 template <int NPASS>
 struct ACfg {
-  static constexpr int KST = 2;                         // K ring depth
-  static constexpr int VST = 2;                         // V^T ring depth
+  static constexpr int ST = 3;                          // K and V^T ring depth
   static constexpr int PL = NPASS == 3 ? 2 : 1;         // planes (hi [, lo])
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + Q_BYTES * PL;
-  static constexpr int OFF_V = OFF_K + KST * K_BYTES * PL;
-  static constexpr int OFF_BAR = OFF_V + VST * V_BYTES * PL;
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + ST * K_BYTES * PL;
+  static constexpr int OFF_BAR = OFF_V + ST * V_BYTES * PL;
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
   static constexpr int NTHREADS = NPASS == 3 ? 320 : 192;
   static constexpr int MIN_CTAS = NPASS == 3 ? 1 : 2;
-  // TMEM columns: S0 [0,64) S1 [64,128) O [128,192) P_hi [192,256) (P_lo [256,320))
+  // TMEM columns: S0/P0 [0,64) S1/P1 [64,128) O [128,192) Q_hi [192,256)
+  //               (Q_lo [256,320) P0_lo [320,384) P1_lo [384,448))
   static constexpr int TMEM_COLS = NPASS == 3 ? 512 : 256;
 };
 
 struct AttnTcArgs {
+  const float* qkv;    // [V, n_pad, 768]
   float* out;          // [V, n_pad, 256]
   int n_pad;
   AttnSegs segs;
@@ -72,27 +70,24 @@ __device__ __forceinline__ void split_tile(uint8_t* hi_base, uint8_t* lo_base, i
 
 template <int NPASS>
 __global__ void __launch_bounds__(ACfg<NPASS>::NTHREADS, ACfg<NPASS>::MIN_CTAS)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, AttnTcArgs g) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, AttnTcArgs g) {
   using C_ = ACfg<NPASS>;
+  constexpr int ST = C_::ST;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_split = bars + 1;
-  uint64_t* k_full = bars + 2;     // [2]
-  uint64_t* k_empty = bars + 4;    // [2]
-  uint64_t* k_split = bars + 6;    // [2]
-  uint64_t* v_full = bars + 8;     // [2]
-  uint64_t* v_empty = bars + 10;   // [2]
-  uint64_t* v_split = bars + 12;   // [2]
-  uint64_t* s_full = bars + 14;    // [2]
-  uint64_t* s_empty = bars + 16;   // [2]
-  uint64_t* p_ready = bars + 18;
-  uint64_t* p_empty = bars + 19;
-  uint64_t* o_full = bars + 20;
-  uint64_t* o_empty = bars + 21;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* q_ready = bars + 0;    // Q rows stored to tensor memory (128 arrivals)
+  uint64_t* k_full = bars + 1;     // [ST]
+  uint64_t* k_empty = bars + 4;    // [ST]
+  uint64_t* k_split = bars + 7;    // [ST]
+  uint64_t* v_full = bars + 10;    // [ST]
+  uint64_t* v_empty = bars + 13;   // [ST]
+  uint64_t* v_split = bars + 16;   // [ST]
+  uint64_t* s_full = bars + 19;    // [2]  S(j) landed in TMEM
+  uint64_t* p_ready = bars + 21;   // [2]  P(j) stored over S(j) (128 arrivals)
+  uint64_t* o_full = bars + 23;
+  uint64_t* o_empty = bars + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
@@ -119,43 +114,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     seg = 0; k0 = 0; cnt = 0;
   };
 
-  uint8_t* sQ = smem + C_::OFF_Q;
-  uint8_t* sQlo = sQ + Q_BYTES;
   auto sK = [&](int s) { return smem + C_::OFF_K + s * K_BYTES * C_::PL; };
   auto sV = [&](int s) { return smem + C_::OFF_V + s * V_BYTES * C_::PL; };
 
   if (threadIdx.x == 0) {
-    tc::mbar_init(q_full, 1);
-    tc::mbar_init(q_split, 128);
-    for (int i = 0; i < 2; ++i) {
+    tc::mbar_init(q_ready, 128);
+    for (int i = 0; i < ST; ++i) {
       tc::mbar_init(k_full + i, 1); tc::mbar_init(k_empty + i, 1); tc::mbar_init(k_split + i, 128);
       tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1); tc::mbar_init(v_split + i, 128);
-      tc::mbar_init(s_full + i, 1); tc::mbar_init(s_empty + i, 128);
     }
-    tc::mbar_init(p_ready, 128); tc::mbar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(p_ready + i, 128); }
     tc::mbar_init(o_full, 1); tc::mbar_init(o_empty, 128);
     tc::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV); }
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV); }
   if (warp == 1) tc::tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 128, tmem_P = tmem_base + 192, tmem_Plo = tmem_base + 256;
+  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 128, tmem_Q = tmem_base + 192;
+  const uint32_t tmem_Qlo = tmem_base + 256, tmem_Plo0 = tmem_base + 320;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      const int qrow = v * g.n_pad + q0;
-      tc::mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tc::tma_load_2d(sQ, &tmQ, q_full, h * HD, qrow);
-      tc::tma_load_2d(sQ + Q_SUB_BYTES, &tmQ, q_full, h * HD + SUB, qrow);
       auto load_K = [&](int j) {
         int seg, k0, cnt;
         tile_info(j, seg, k0, cnt);
-        const int s = j % C_::KST;
-        tc::mbar_wait(k_empty + s, ((j / C_::KST) & 1) ^ 1);
+        const int s = j % ST;
+        tc::mbar_wait(k_empty + s, ((j / ST) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(k_full + s, K_BYTES);
         const int krow = (b * T + seg) * g.n_pad + k0;
         tc::tma_load_2d(sK(s), &tmK, k_full + s, 256 + h * HD, krow);
@@ -164,8 +152,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto load_V = [&](int j) {
         int seg, k0, cnt;
         tile_info(j, seg, k0, cnt);
-        const int s = j % C_::VST;
-        tc::mbar_wait(v_empty + s, ((j / C_::VST) & 1) ^ 1);
+        const int s = j % ST;
+        tc::mbar_wait(v_empty + s, ((j / ST) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(v_full + s, V_BYTES);
         const int vrow = (b * T + seg) * 256 + h * HD;
         tc::tma_load_2d(sV(s), &tmV, v_full + s, k0, vrow);
@@ -179,28 +167,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
+    // The tensor pipe executes in issue order, so S(j+1) may overwrite the buffer that held P(j-1)
+    // without an explicit wait: P(j-1).V was issued earlier.
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc_tf32(BQ, BKV);   // M=128, N=64 for both products
-      tc::mbar_wait(q_full, 0);
-      if (NPASS == 3) tc::mbar_wait(q_split, 0);
-      const uint32_t q_hi = tc::smem_u32(sQ), q_lo = tc::smem_u32(sQlo);
+      tc::mbar_wait(q_ready, 0);
+      tc::tc_fence_after();
       auto issue_S = [&](int j) {
-        const int s = j % C_::KST, sb = j & 1;
-        tc::mbar_wait(k_full + s, (j / C_::KST) & 1);
-        if (NPASS == 3) tc::mbar_wait(k_split + s, (j / C_::KST) & 1);
-        tc::mbar_wait(s_empty + sb, ((j >> 1) & 1) ^ 1);
+        const int s = j % ST, sb = j & 1;
+        tc::mbar_wait(k_full + s, (j / ST) & 1);
+        if (NPASS == 3) tc::mbar_wait(k_split + s, (j / ST) & 1);
         tc::tc_fence_after();
         const uint32_t k_hi = tc::smem_u32(sK(s)), k_lo = k_hi + K_BYTES;
         const uint32_t d = tmem_S0 + sb * 64;
 #pragma unroll
         for (int kk = 0; kk < HD / 8; ++kk) {
-          const uint32_t offq = (kk >> 2) * Q_SUB_BYTES + (kk & 3) * 32;
           const uint32_t offk = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
-          const uint64_t dq = tc::make_kmajor_sw128_desc(q_hi + offq), dk = tc::make_kmajor_sw128_desc(k_hi + offk);
-          tc::umma_tf32(d, dq, dk, idesc, kk != 0);
+          const uint64_t dk = tc::make_kmajor_sw128_desc(k_hi + offk);
+          tc::umma_tf32_ts(d, tmem_Q + kk * 8, dk, idesc, kk != 0);           // A = Q from tensor memory
           if (NPASS == 3) {
-            tc::umma_tf32(d, dq, tc::make_kmajor_sw128_desc(k_lo + offk), idesc, 1);
-            tc::umma_tf32(d, tc::make_kmajor_sw128_desc(q_lo + offq), dk, idesc, 1);
+            tc::umma_tf32_ts(d, tmem_Q + kk * 8, tc::make_kmajor_sw128_desc(k_lo + offk), idesc, 1);
+            tc::umma_tf32_ts(d, tmem_Qlo + kk * 8, dk, idesc, 1);
           }
         }
         tc::umma_commit(s_full + sb);
@@ -209,26 +196,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       issue_S(0);
       for (int j = 0; j < nt; ++j) {
         if (j + 1 < nt) issue_S(j + 1);
-        const int s = j % C_::VST;
-        tc::mbar_wait(p_ready, j & 1);
-        tc::mbar_wait(v_full + s, (j / C_::VST) & 1);
-        if (NPASS == 3) tc::mbar_wait(v_split + s, (j / C_::VST) & 1);
+        const int s = j % ST, sb = j & 1;
+        tc::mbar_wait(p_ready + sb, (j >> 1) & 1);
+        tc::mbar_wait(v_full + s, (j / ST) & 1);
+        if (NPASS == 3) tc::mbar_wait(v_split + s, (j / ST) & 1);
         tc::mbar_wait(o_empty, (j & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
+        const uint32_t p_hi = tmem_S0 + sb * 64, p_lo = tmem_Plo0 + sb * 64;
 #pragma unroll
         for (int kk = 0; kk < BKV / 8; ++kk) {
           const uint32_t offv = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
           const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + offv);
-          tc::umma_tf32_ts(tmem_O, tmem_P + kk * 8, dv, idesc, kk != 0);       // A = P from tensor memory
+          tc::umma_tf32_ts(tmem_O, p_hi + kk * 8, dv, idesc, kk != 0);        // A = P from tensor memory
           if (NPASS == 3) {
-            tc::umma_tf32_ts(tmem_O, tmem_P + kk * 8, tc::make_kmajor_sw128_desc(v_lo + offv), idesc, 1);
-            tc::umma_tf32_ts(tmem_O, tmem_Plo + kk * 8, dv, idesc, 1);
+            tc::umma_tf32_ts(tmem_O, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + offv), idesc, 1);
+            tc::umma_tf32_ts(tmem_O, p_lo + kk * 8, dv, idesc, 1);
           }
         }
         tc::umma_commit(o_full);
         tc::umma_commit(v_empty + s);
-        tc::umma_commit(p_empty);
       }
     }
   } else if (warp < 6) {
@@ -236,6 +223,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    // Q row -> tensor memory (A operand of S = Q K^T); rows past the view are read but never written back
+    {
+      const float4* qg = reinterpret_cast<const float4*>(g.qkv + ((long long)v * g.n_pad + q0 + row) * 768 + h * HD);
+      const bool in_range = (long long)v * g.n_pad + q0 + row < (long long)gridDim.z * g.n_pad;
+      float qr[HD];
+#pragma unroll
+      for (int i = 0; i < HD / 4; ++i) {
+        const float4 x = in_range ? qg[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        qr[4 * i] = x.x; qr[4 * i + 1] = x.y; qr[4 * i + 2] = x.z; qr[4 * i + 3] = x.w;
+      }
+      if (NPASS == 3) {
+        float lo[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float hi = tf32_rn(qr[c * 32 + i]);
+            lo[i] = tf32_rn(qr[c * 32 + i] - hi);
+            qr[c * 32 + i] = hi;
+          }
+          tc::tmem_st32(tmem_Qlo + lane_addr + c * 32, lo);
+        }
+      }
+      tc::tmem_st32(tmem_Q + lane_addr, qr);
+      tc::tmem_st32(tmem_Q + lane_addr + 32, qr + 32);
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(q_ready);
+    }
     float acc[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) acc[i] = 0.f;
@@ -267,8 +283,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr, s);
       tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr + 32, s + 32);
       tc::tmem_ld_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(s_empty + sb);
       float mx = -INFINITY;
       const int nvalid = cnt - k0;      // keys of this tile that exist
 #pragma unroll
@@ -286,8 +300,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       l_run = l_run * corr + rs;
       m_run = m_new;
-      // P -> tensor memory (row r = lane r, keys along columns): the A operand of P.V
-      tc::mbar_wait(p_empty, (j & 1) ^ 1);
+      // P(j) overwrites S(j) in tensor memory (row r = lane r, keys along columns): A operand of P.V
       if (NPASS == 3) {
         float lo[32];
 #pragma unroll
@@ -298,14 +311,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             lo[i] = tf32_rn(s[c * 32 + i] - hi);
             s[c * 32 + i] = hi;
           }
-          tc::tmem_st32(tmem_Plo + lane_addr + c * 32, lo);
+          tc::tmem_st32(tmem_Plo0 + sb * 64 + lane_addr + c * 32, lo);
         }
       }
-      tc::tmem_st32(tmem_P + lane_addr, s);
-      tc::tmem_st32(tmem_P + lane_addr + 32, s + 32);
+      tc::tmem_st32(tmem_S0 + sb * 64 + lane_addr, s);
+      tc::tmem_st32(tmem_S0 + sb * 64 + lane_addr + 32, s + 32);
       tc::tmem_st_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(p_ready);
+      tc::mbar_arrive(p_ready + sb);
       // fold the previous tile's P.V while the tensor core works on this one, then rescale
       if (j > 0) fold_O(j - 1);
 #pragma unroll
@@ -322,20 +335,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else {
     // =========================== operand splitters (NPASS == 3) ===========================
     const int st = threadIdx.x - 192;   // 0..127
-    tc::mbar_wait(q_full, 0);
-    split_tile(sQ, sQlo, Q_BYTES, st, 128);
-    tc::fence_proxy_async();
-    tc::mbar_arrive(q_split);
     auto split_K = [&](int j) {
-      const int s = j % C_::KST;
-      tc::mbar_wait(k_full + s, (j / C_::KST) & 1);
+      const int s = j % ST;
+      tc::mbar_wait(k_full + s, (j / ST) & 1);
       split_tile(sK(s), sK(s) + K_BYTES, K_BYTES, st, 128);
       tc::fence_proxy_async();
       tc::mbar_arrive(k_split + s);
     };
     auto split_V = [&](int j) {
-      const int s = j % C_::VST;
-      tc::mbar_wait(v_full + s, (j / C_::VST) & 1);
+      const int s = j % ST;
+      tc::mbar_wait(v_full + s, (j / ST) & 1);
       split_tile(sV(s), sV(s) + V_BYTES, V_BYTES, st, 128);
       tc::fence_proxy_async();
       tc::mbar_arrive(v_split + s);
@@ -362,14 +371,13 @@ int launch_attn(const float* qkv, const float* vt, float* out, int batch, int n_
   }
   const int V = batch * segs.n_views;
   const long long rows = (long long)V * n_pad;
-  const CUtensorMap* tQ = mvm_get_tmap_2d(qkv, rows, 768, 768, BQ);
   const CUtensorMap* tK = mvm_get_tmap_2d(qkv, rows, 768, 768, BKV);
   const CUtensorMap* tV = mvm_get_tmap_2d(vt, (long long)V * 256, n_pad, n_pad, BKV);
-  if (!tQ || !tK || !tV) return MVM_ERR_LAUNCH;
+  if (!tK || !tV) return MVM_ERR_LAUNCH;
   AttnTcArgs g;
-  g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross;
+  g.qkv = qkv; g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross;
   dim3 grid(mvm_div_up(n_pad, BQ), 4, V);
-  attention_tc_kernel<NPASS><<<grid, C_::NTHREADS, C_::SMEM_BYTES, stream>>>(*tQ, *tK, *tV, g);
+  attention_tc_kernel<NPASS><<<grid, C_::NTHREADS, C_::SMEM_BYTES, stream>>>(*tK, *tV, g);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }
