@@ -99,40 +99,16 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
 
     for (int it = 0; it < cfg.iters; ++it) {
       // ---- row pass: a_i = mu / (sum_j K~_ij b_j + e_i kb_n b_n) ----
-      // each lane keeps its b_j (columns 4*lane + 128*k ...) in registers for all rows of the pass
       const float bin_col = kb_s[n] * b_s[n];
       bool row_bad = false;
-      if ((n & 127) == 0 && n <= 2048) {
-        float4 breg[16];
-        const int nch = n >> 7;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (k < nch) breg[k] = *reinterpret_cast<const float4*>(b_s + k * 128 + lane * 4);
-        for (int r = warp; r < nrows; r += NW) {
-          const float4* kr = reinterpret_cast<const float4*>(Ks + (size_t)r * n);
-          float s = 0.f;
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            if (k < nch) {
-              const float4 x = kr[k * 32 + lane];
-              s = fmaf(x.x, breg[k].x, s); s = fmaf(x.y, breg[k].y, s);
-              s = fmaf(x.z, breg[k].z, s); s = fmaf(x.w, breg[k].w, s);
-            }
-          s = warp_sum(s);
-          const float a = mu / (s + e_s[r] * bin_col);
-          if (lane == 0) a_s[r] = a;
-          row_bad |= (a > ABSORB_HI) | (a < ABSORB_LO);
-        }
-      } else {
-        for (int r = warp; r < nrows; r += NW) {
-          const float* kr = Ks + (size_t)r * n;
-          float s = 0.f;
-          for (int j = lane; j < n; j += 32) s = fmaf(kr[j], b_s[j], s);
-          s = warp_sum(s);
-          const float a = mu / (s + e_s[r] * bin_col);
-          if (lane == 0) a_s[r] = a;
-          row_bad |= (a > ABSORB_HI) | (a < ABSORB_LO);
-        }
+      for (int r = warp; r < nrows; r += NW) {
+        const float* kr = Ks + (size_t)r * n;
+        float s = 0.f;
+        for (int j = lane; j < n; j += 32) s = fmaf(kr[j], b_s[j], s);
+        s = warp_sum(s);
+        const float a = mu / (s + e_s[r] * bin_col);
+        if (lane == 0) a_s[r] = a;
+        row_bad |= (a > ABSORB_HI) | (a < ABSORB_LO);
       }
       if (warp == NW - 1) {   // dustbin row (replicated in every CTA): a_m = mu_bin / sum_j kb_j b_j
         float s = 0.f;
@@ -155,16 +131,9 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
       }
       // ---- column pass: partial c_j = sum_{own rows} K~_ij a_i ; dustbin column: kb_n sum e_i a_i ----
       for (int j = tid; j < n; j += blockDim.x) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int r = 0;
-        for (; r + 3 < nrows; r += 4) {
-          s0 = fmaf(Ks[(size_t)r * n + j], a_s[r], s0);
-          s1 = fmaf(Ks[(size_t)(r + 1) * n + j], a_s[r + 1], s1);
-          s2 = fmaf(Ks[(size_t)(r + 2) * n + j], a_s[r + 2], s2);
-          s3 = fmaf(Ks[(size_t)(r + 3) * n + j], a_s[r + 3], s3);
-        }
-        for (; r < nrows; ++r) s0 = fmaf(Ks[(size_t)r * n + j], a_s[r], s0);
-        __stcg(cpart + (size_t)c * (n + 1) + j, (s0 + s1) + (s2 + s3));
+        float s = 0.f;
+        for (int r = 0; r < nrows; ++r) s = fmaf(Ks[(size_t)r * n + j], a_s[r], s);
+        __stcg(cpart + (size_t)c * (n + 1) + j, s);
       }
       if (warp == NW - 1) {
         float s = 0.f;
