@@ -78,7 +78,8 @@ def lib():
     L.mvm_set_math_mode.argtypes = [C.c_int]
     L.mvm_get_math_mode.restype = C.c_int
     L.mvm_attention_tc.restype = C.c_int
-    L.mvm_attention_tc.argtypes = [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, _fp]
+    L.mvm_attention_tc.argtypes = [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, _fp,
+                                   _fp, _fp]
     L.mvm_attention.restype = C.c_int
     L.mvm_attention.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, _fp]
     L.mvm_sinkhorn_workspace_floats.restype = C.c_size_t

@@ -13,8 +13,9 @@
 //               registers (no shuffles), exp2, P written back to TENSOR MEMORY (tcgen05.st) and consumed
 //               as the A operand of P.V straight from TMEM, O_tile folded into a register accumulator with
 //               the online-softmax correction
-//   warps 6-9   (NPASS == 3) operand splitters: tf32 hi/lo planes of Q, K, V^T tiles in shared memory so
-//               that every product is A.B + A.B_lo + A_lo.B (fp32-faithful "3xTF32")
+//   (NPASS == 3) every product is A.B + A.B_lo + A_lo.B (fp32-faithful "3xTF32"): the tf32 hi/lo planes of
+//               K and V^T are produced by the QKV GEMM epilogue and arrive by TMA; Q and P are split in
+//               registers by the softmax threads before they are stored to tensor memory
 // All operands are K-major: Q, K rows of the fused QKV projection [rows, 768]; V^T [view*256 + h*64 + d, key]
 // is written by the QKV GEMM epilogue (gemm_tc.cu).
 #include "common.cuh"
@@ -37,7 +38,7 @@ struct ACfg {
   static constexpr int OFF_V = OFF_K + ST * K_BYTES * PL;
   static constexpr int OFF_BAR = OFF_V + ST * V_BYTES * PL;
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
-  static constexpr int NTHREADS = NPASS == 3 ? 320 : 192;
+  static constexpr int NTHREADS = 192;
   static constexpr int MIN_CTAS = NPASS == 3 ? 1 : 2;
   // TMEM columns: S0/P0 [0,64) S1/P1 [64,128) O [128,192) Q_hi [192,256)
   //               (Q_lo [256,320) P0_lo [320,384) P1_lo [384,448))
@@ -70,7 +71,8 @@ __device__ __forceinline__ void split_tile(uint8_t* hi_base, uint8_t* lo_base, i
 
 template <int NPASS>
 __global__ void __launch_bounds__(ACfg<NPASS>::NTHREADS, ACfg<NPASS>::MIN_CTAS)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, AttnTcArgs g) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo, AttnTcArgs g) {
   using C_ = ACfg<NPASS>;
   constexpr int ST = C_::ST;
   extern __shared__ uint8_t smem_raw[];
@@ -127,7 +129,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     tc::mbar_init(o_full, 1); tc::mbar_init(o_empty, 128);
     tc::fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV); }
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
+    if (NPASS == 3) { tc::prefetch_tmap(&tmKlo); tc::prefetch_tmap(&tmVlo); }
+  }
   if (warp == 1) tc::tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
@@ -144,20 +149,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         tile_info(j, seg, k0, cnt);
         const int s = j % ST;
         tc::mbar_wait(k_empty + s, ((j / ST) & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(k_full + s, K_BYTES);
+        tc::mbar_arrive_expect_tx(k_full + s, K_BYTES * C_::PL);
         const int krow = (b * T + seg) * g.n_pad + k0;
         tc::tma_load_2d(sK(s), &tmK, k_full + s, 256 + h * HD, krow);
         tc::tma_load_2d(sK(s) + KV_SUB_BYTES, &tmK, k_full + s, 256 + h * HD + SUB, krow);
+        if (NPASS == 3) {
+          tc::tma_load_2d(sK(s) + K_BYTES, &tmKlo, k_full + s, h * HD, krow);
+          tc::tma_load_2d(sK(s) + K_BYTES + KV_SUB_BYTES, &tmKlo, k_full + s, h * HD + SUB, krow);
+        }
       };
       auto load_V = [&](int j) {
         int seg, k0, cnt;
         tile_info(j, seg, k0, cnt);
         const int s = j % ST;
         tc::mbar_wait(v_empty + s, ((j / ST) & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(v_full + s, V_BYTES);
+        tc::mbar_arrive_expect_tx(v_full + s, V_BYTES * C_::PL);
         const int vrow = (b * T + seg) * 256 + h * HD;
         tc::tma_load_2d(sV(s), &tmV, v_full + s, k0, vrow);
         tc::tma_load_2d(sV(s) + KV_SUB_BYTES, &tmV, v_full + s, k0 + SUB, vrow);
+        if (NPASS == 3) {
+          tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, k0, vrow);
+          tc::tma_load_2d(sV(s) + V_BYTES + KV_SUB_BYTES, &tmVlo, v_full + s, k0 + SUB, vrow);
+        }
       };
       load_K(0);
       for (int j = 0; j < nt; ++j) {
@@ -176,7 +189,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       auto issue_S = [&](int j) {
         const int s = j % ST, sb = j & 1;
         tc::mbar_wait(k_full + s, (j / ST) & 1);
-        if (NPASS == 3) tc::mbar_wait(k_split + s, (j / ST) & 1);
         tc::tc_fence_after();
         const uint32_t k_hi = tc::smem_u32(sK(s)), k_lo = k_hi + K_BYTES;
         const uint32_t d = tmem_S0 + sb * 64;
@@ -199,7 +211,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         const int s = j % ST, sb = j & 1;
         tc::mbar_wait(p_ready + sb, (j >> 1) & 1);
         tc::mbar_wait(v_full + s, (j / ST) & 1);
-        if (NPASS == 3) tc::mbar_wait(v_split + s, (j / ST) & 1);
         tc::mbar_wait(o_empty, (j & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
@@ -332,28 +343,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       for (int i = 0; i < HD / 4; ++i)
         o4[i] = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
     }
-  } else {
-    // =========================== operand splitters (NPASS == 3) ===========================
-    const int st = threadIdx.x - 192;   // 0..127
-    auto split_K = [&](int j) {
-      const int s = j % ST;
-      tc::mbar_wait(k_full + s, (j / ST) & 1);
-      split_tile(sK(s), sK(s) + K_BYTES, K_BYTES, st, 128);
-      tc::fence_proxy_async();
-      tc::mbar_arrive(k_split + s);
-    };
-    auto split_V = [&](int j) {
-      const int s = j % ST;
-      tc::mbar_wait(v_full + s, (j / ST) & 1);
-      split_tile(sV(s), sV(s) + V_BYTES, V_BYTES, st, 128);
-      tc::fence_proxy_async();
-      tc::mbar_arrive(v_split + s);
-    };
-    split_K(0);
-    for (int j = 0; j < nt; ++j) {
-      split_V(j);
-      if (j + 1 < nt) split_K(j + 1);
-    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -361,8 +350,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 }
 
 template <int NPASS>
-int launch_attn(const float* qkv, const float* vt, float* out, int batch, int n_pad, const AttnSegs& segs,
-                int is_cross, cudaStream_t stream) {
+int launch_attn(const float* qkv, const float* vt, const float* klo, const float* vtlo, float* out, int batch, int n_pad,
+                const AttnSegs& segs, int is_cross, cudaStream_t stream) {
   using C_ = ACfg<NPASS>;
   static bool attr = false;
   if (!attr) {
@@ -373,11 +362,13 @@ int launch_attn(const float* qkv, const float* vt, float* out, int batch, int n_
   const long long rows = (long long)V * n_pad;
   const CUtensorMap* tK = mvm_get_tmap_2d(qkv, rows, 768, 768, BKV);
   const CUtensorMap* tV = mvm_get_tmap_2d(vt, (long long)V * 256, n_pad, n_pad, BKV);
-  if (!tK || !tV) return MVM_ERR_LAUNCH;
+  const CUtensorMap* tKlo = klo ? mvm_get_tmap_2d(klo, rows, 256, 256, BKV) : tK;
+  const CUtensorMap* tVlo = vtlo ? mvm_get_tmap_2d(vtlo, (long long)V * 256, n_pad, n_pad, BKV) : tV;
+  if (!tK || !tV || !tKlo || !tVlo) return MVM_ERR_LAUNCH;
   AttnTcArgs g;
   g.qkv = qkv; g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross;
   dim3 grid(mvm_div_up(n_pad, BQ), 4, V);
-  attention_tc_kernel<NPASS><<<grid, C_::NTHREADS, C_::SMEM_BYTES, stream>>>(*tK, *tV, g);
+  attention_tc_kernel<NPASS><<<grid, C_::NTHREADS, C_::SMEM_BYTES, stream>>>(*tK, *tV, *tKlo, *tVlo, g);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }
@@ -386,10 +377,13 @@ int launch_attn(const float* qkv, const float* vt, float* out, int batch, int n_
 
 // qkv [V, n_pad, 768] (q | k | unused-v), vt [V, 256, n_pad] = V^T per head; out [V, n_pad, 256]
 int launch_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_pad, AttnSegs segs,
-                        int is_cross, int n_pass, cudaStream_t stream) {
+                        int is_cross, int n_pass, cudaStream_t stream, const float* klo, const float* vtlo) {
   MVM_REQUIRE(n_pad % 64 == 0 && segs.n_views >= 1 && segs.n_views <= 8);
   MVM_REQUIRE(!is_cross || segs.n_views >= 2);
   MvmProfScope prof__(MVM_TAG_ATTN, stream);
-  if (n_pass == 3) return launch_attn<3>(qkv, vt, out, batch, n_pad, segs, is_cross, stream);
-  return launch_attn<1>(qkv, vt, out, batch, n_pad, segs, is_cross, stream);
+  if (n_pass == 3) {
+    MVM_REQUIRE(klo && vtlo);
+    return launch_attn<3>(qkv, vt, klo, vtlo, out, batch, n_pad, segs, is_cross, stream);
+  }
+  return launch_attn<1>(qkv, vt, nullptr, nullptr, out, batch, n_pad, segs, is_cross, stream);
 }

@@ -34,6 +34,9 @@ struct GemmTcArgs {
   int relu;
   // optional transposed output for columns >= vt_col0: VT[(m / n_pad), n - vt_col0, m % n_pad]
   float* VT; int vt_col0; int n_pad;
+  // optional tf32 hi/lo planes for the attention operands (3xTF32 mode): columns [256,512) (= K) are
+  // stored as rn_tf32 in C with the remainder in KLO [M,256]; V^T likewise in VT / VTLO
+  float* KLO; float* VTLO;
 };
 
 template <int BN, int NPASS>
@@ -194,9 +197,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (g.VT && nb >= g.vt_col0) {
           const int slab = m / g.n_pad, i = m % g.n_pad;
-          float* o = g.VT + ((long long)slab * (g.N - g.vt_col0) + (nb - g.vt_col0)) * g.n_pad + i;
+          const long long off = ((long long)slab * (g.N - g.vt_col0) + (nb - g.vt_col0)) * g.n_pad + i;
+          if (g.VTLO) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[(long long)j * g.n_pad] = v[j];
+            for (int j = 0; j < 32; ++j) {
+              const float hi = tc::tf32_rn(v[j]);
+              g.VT[off + (long long)j * g.n_pad] = hi;
+              g.VTLO[off + (long long)j * g.n_pad] = tc::tf32_rn(v[j] - hi);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g.VT[off + (long long)j * g.n_pad] = v[j];
+          }
+        } else if (g.KLO && nb >= 256 && nb < 512) {
+          float4* o = reinterpret_cast<float4*>(g.C + (long long)m * g.ldc + nb);
+          float4* ol = reinterpret_cast<float4*>(g.KLO + (long long)m * 256 + (nb - 256));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 h;
+            h.x = tc::tf32_rn(v[4 * j]); h.y = tc::tf32_rn(v[4 * j + 1]); h.z = tc::tf32_rn(v[4 * j + 2]); h.w = tc::tf32_rn(v[4 * j + 3]);
+            o[j] = h;
+            ol[j] = make_float4(tc::tf32_rn(v[4 * j] - h.x), tc::tf32_rn(v[4 * j + 1] - h.y), tc::tf32_rn(v[4 * j + 2] - h.z),
+                                tc::tf32_rn(v[4 * j + 3] - h.w));
+          }
         } else {
           float4* o = reinterpret_cast<float4*>(g.C + (long long)m * g.ldc + nb);
 #pragma unroll
@@ -229,7 +252,7 @@ std::map<TmKey, CUtensorMap*> g_tmaps;
 std::mutex g_tmap_mu;
 
 template <int BN, int NPASS>
-int launch_cfg(const GemmDesc& d, float* VT, int vt_col0, int n_pad, cudaStream_t stream) {
+int launch_cfg(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO, cudaStream_t stream) {
   using C_ = Cfg<BN, NPASS>;
   static bool attr = false;
   if (!attr) {
@@ -242,7 +265,7 @@ int launch_cfg(const GemmDesc& d, float* VT, int vt_col0, int n_pad, cudaStream_
   if (!tA || !tA2 || !tW) return MVM_ERR_LAUNCH;
   GemmTcArgs g;
   g.bias = d.bias; g.R = d.R; g.ldr = d.ldr; g.C = d.C; g.ldc = d.ldc; g.M = d.M; g.N = d.N; g.K = d.K;
-  g.K1 = d.K1; g.alpha = d.alpha; g.relu = d.relu; g.VT = VT; g.vt_col0 = vt_col0; g.n_pad = n_pad;
+  g.K1 = d.K1; g.alpha = d.alpha; g.relu = d.relu; g.VT = VT; g.vt_col0 = vt_col0; g.n_pad = n_pad; g.KLO = KLO; g.VTLO = VTLO;
   dim3 grid(d.N / BN, mvm_div_up(d.M, BM));
   gemm_tc_kernel<BN, NPASS><<<grid, NTHREADS, C_::SMEM_BYTES, stream>>>(*tA, *tA2, *tW, g);
   MVM_CHECK_LAUNCH();
@@ -283,11 +306,12 @@ const CUtensorMap* mvm_get_tmap_2d(const float* base, long long rows, long long 
 
 // GEMM on the tensor cores.  Requirements: K, K1 multiples of 32, N multiple of 128, 16-byte aligned
 // rows (lda/ldw/ldc/ldr multiples of 4).  n_pass: 3 = fp32-faithful 3xTF32, 1 = single-pass TF32.
-int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_pad, cudaStream_t stream) {
+int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_pad, cudaStream_t stream,
+                   float* KLO, float* VTLO) {
   MVM_REQUIRE(d.batch == 1 && d.K % BK == 0 && d.K1 % BK == 0 && d.N % 128 == 0);
   MVM_REQUIRE(d.lda % 4 == 0 && d.ldw % 4 == 0 && d.ldc % 4 == 0 && (d.R == nullptr || d.ldr % 4 == 0));
   MVM_REQUIRE(d.A2 == nullptr || d.lda2 % 4 == 0);
   MvmProfScope prof__(MVM_TAG_GEMM, stream);
-  if (n_pass == 3) return launch_cfg<128, 3>(d, VT, vt_col0, n_pad, stream);
-  return launch_cfg<128, 1>(d, VT, vt_col0, n_pad, stream);
+  if (n_pass == 3) return launch_cfg<128, 3>(d, VT, vt_col0, n_pad, KLO, VTLO, stream);
+  return launch_cfg<128, 1>(d, VT, vt_col0, n_pad, nullptr, nullptr, stream);
 }

@@ -29,14 +29,17 @@ int launch_transpose_cn(const float* in, float* out, int n_views_total, int C, i
                         cudaStream_t stream);
 
 // tcgen05 GEMM (gemm_tc.cu): n_pass 3 = fp32-faithful 3xTF32, 1 = single-pass TF32
-int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_pad, cudaStream_t stream);
+int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_pad, cudaStream_t stream,
+                   float* KLO = nullptr, float* VTLO = nullptr);
 
 struct AttnSegs {
   int n_views;
   int counts[8];
 };
+// klo / vtlo: tf32 remainder planes of K [rows,256] and V^T (n_pass == 3; K and V^T then hold the rn_tf32 parts)
 int launch_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_pad, AttnSegs segs,
-                        int is_cross, int n_pass, cudaStream_t stream);
+                        int is_cross, int n_pass, cudaStream_t stream, const float* klo = nullptr,
+                        const float* vtlo = nullptr);
 int launch_attention_simt(const float* qkv, float* out, int batch, int n_pad, AttnSegs segs,
                           int is_cross, cudaStream_t stream);
 

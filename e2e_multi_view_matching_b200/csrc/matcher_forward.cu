@@ -10,7 +10,7 @@
 namespace {
 
 struct Workspace {
-  float *DT, *H3, *H4, *X, *QKV, *VT, *MSG, *MRG, *H, *MD;
+  float *DT, *H3, *H4, *X, *QKV, *VT, *KLO, *VTLO, *MSG, *MRG, *H, *MD;
   float* sink_ws;
   int* match_ws;
   float *FEAT, *SC, *CF1, *CF2, *CC0, *CC1;
@@ -34,6 +34,8 @@ Workspace carve(char* base, int batch, int n_views, int n_pad, int n_pairs, int 
   w.X = (float*)take(rows * 256 * 4);
   w.QKV = (float*)take(rows * 768 * 4);
   w.VT = (float*)take(rows * 256 * 4);
+  w.KLO = (float*)take(rows * 256 * 4);
+  w.VTLO = (float*)take(rows * 256 * 4);
   w.MSG = (float*)take(rows * 256 * 4);
   w.MRG = (float*)take(rows * 256 * 4);
   w.H = (float*)take(rows * 512 * 4);
@@ -144,9 +146,11 @@ int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, in
     const mvm_layer_weights& L = w->layers[l];
     if (g_math_mode != 0) {
       // tensor-core path: the QKV GEMM epilogue also writes V^T [view, 256, n_pad] for the P.V product
+      float* klo = g_math_mode == 3 ? ws.KLO : nullptr;
+      float* vtlo = g_math_mode == 3 ? ws.VTLO : nullptr;
       MVM_TRY(launch_gemm_tc(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), g_math_mode,
-                             ws.VT, 512, n_pad, s));
-      MVM_TRY(launch_attention_tc(ws.QKV, ws.VT, ws.MSG, batch, n_pad, segs, L.is_cross, g_math_mode, s));
+                             ws.VT, 512, n_pad, s, klo, vtlo));
+      MVM_TRY(launch_attention_tc(ws.QKV, ws.VT, ws.MSG, batch, n_pad, segs, L.is_cross, g_math_mode, s, klo, vtlo));
     } else {
       MVM_TRY(run_gemm(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), s));
       MVM_TRY(launch_attention_simt(ws.QKV, ws.MSG, batch, n_pad, segs, L.is_cross, s));
@@ -241,12 +245,13 @@ int mvm_log_optimal_transport(float* scores, int batch, int m, int n, float bin_
 }
 
 int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_views, int n_pad,
-                     const int* counts, int is_cross, int n_pass, void* stream) {
+                     const int* counts, int is_cross, int n_pass, const float* klo, const float* vtlo, void* stream) {
   MVM_REQUIRE(qkv && vt && out && counts && n_views >= 1 && n_views <= 8 && (n_pass == 1 || n_pass == 3));
   AttnSegs segs;
   segs.n_views = n_views;
   for (int t = 0; t < 8; ++t) segs.counts[t] = t < n_views ? counts[t] : 0;
-  return launch_attention_tc(qkv, vt, out, batch, n_pad, segs, is_cross, n_pass, (cudaStream_t)stream);
+  MVM_REQUIRE(n_pass == 1 || (klo && vtlo));
+  return launch_attention_tc(qkv, vt, out, batch, n_pad, segs, is_cross, n_pass, (cudaStream_t)stream, klo, vtlo);
 }
 
 int mvm_log_optimal_transport_logdomain(float* scores, int batch, int m, int n, float bin_score, int iters,

@@ -42,8 +42,20 @@ def attention(qkv, batch, n_views, counts, is_cross, tc_passes=0):
     cnt = (C.c_int * n_views)(*counts)
     if tc_passes:
         vt = qkv[:, :, 512:].transpose(1, 2).contiguous()      # [V, 256, n_pad]
+        klo = vtlo = None
+        if tc_passes == 3:      # what the QKV GEMM epilogue does in 3xTF32 mode: rn_tf32 planes + remainders
+            def rn(x):          # round to nearest (ties away) on the 13 dropped mantissa bits
+                return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+            qkv = qkv.clone()
+            k = qkv[:, :, 256:512].contiguous()
+            khi = rn(k)
+            klo = rn(k - khi).reshape(-1, 256).contiguous()
+            qkv[:, :, 256:512] = khi
+            vhi = rn(vt)
+            vtlo = rn(vt - vhi).contiguous()
+            vt = vhi
         rc = lib.mvm_attention_tc(_lib.ptr(qkv), _lib.ptr(vt), _lib.ptr(out), batch, n_views, n_pad, cnt,
-                                  int(is_cross), int(tc_passes), _lib.stream_ptr())
+                                  int(is_cross), int(tc_passes), _lib.ptr(klo), _lib.ptr(vtlo), _lib.stream_ptr())
         _lib.check(rc, 'mvm_attention_tc')
         return out
     rc = lib.mvm_attention(_lib.ptr(qkv), _lib.ptr(out), batch, n_views, n_pad, cnt, int(is_cross),

@@ -121,9 +121,12 @@ int mvm_attention(const float* qkv, float* out, int batch, int n_views, int n_pa
                   const int* counts, int is_cross, void* stream);
 
 /* The same attention on the tensor cores (tcgen05/TMEM/TMA flash kernel).  vt [n_views_total, 256,
- * n_pad] holds V^T per head (written by the QKV GEMM epilogue); the v third of qkv is not read. */
+ * n_pad] holds V^T per head (written by the QKV GEMM epilogue); the v third of qkv is not read.
+ * n_pass == 3 (3xTF32): the k third of qkv and vt must hold rn_tf32 values and klo [rows,256] / vtlo
+ * their tf32-rounded remainders (the QKV GEMM epilogue writes all four); NULL for n_pass == 1. */
 int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_views, int n_pad,
-                     const int* counts, int is_cross, int n_pass, void* stream);
+                     const int* counts, int is_cross, int n_pass, const float* klo, const float* vtlo,
+                     void* stream);
 
 /* log_optimal_transport (superglue.py:143-172).  scores: [batch, m+1, n+1] buffers whose
  * inner [m,n] block holds the raw scores on entry; on exit the full coupling matrix

@@ -395,7 +395,7 @@ def multi_view_pipeline(scene, conf_thresh=0.0, n_it2=10, max_iterations=50):
             rel[(a, b)] = Tp[0]
             weight[(a, b)] = int(valid.sum())
             pm[(a, b)] = (info['kpts0_norm'][0], info['kpts1_norm'][0], c[valid])
-            info_all[(a, b)] = {'T_w8pt': Tw[0], 'inliers': info['inliers'][0]}
+            info_all[(a, b)] = {'T_w8pt': Tw[0], 'inliers': info['inliers'][0], 'vote_counts': info['vote_counts'][0]}
     extr0, tree = spanning_tree_extrinsics(T, rel, weight)
     pb = build_problem(T, pm, extr0)
     cams, pts, info = solve(pb, max_iterations=max_iterations)

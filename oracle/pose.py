@@ -224,6 +224,7 @@ def estimate_relative_pose_w8pt(kpts0, kpts1, intr0, intr1, confidence, choose_c
     k0n = normalize(kpts0, intr0)
     k1n = normalize(kpts1, intr1)
     B = intr0.shape[0]
+    vote_counts = None
     Fs = find_fundamental(k0n, k1n, confidence[..., 0])
     T = np.tile(np.eye(4, dtype=dt), (B, 1, 1))
     if choose_closest:
@@ -238,7 +239,7 @@ def estimate_relative_pose_w8pt(kpts0, kpts1, intr0, intr1, confidence, choose_c
             min_err[upd] = err[upd]
             T[upd] = P[upd]
     else:
-        R, t, _, _ = motion_from_essential_choose_solution(Fs, k0n, k1n)
+        R, t, _, vote_counts = motion_from_essential_choose_solution(Fs, k0n, k1n)
         T[:, :3, :3] = R
         T[:, :3, 3] = t[..., 0]
     P0 = np.tile(np.eye(4, dtype=dt)[:3], (B, 1, 1))
@@ -252,7 +253,7 @@ def estimate_relative_pose_w8pt(kpts0, kpts1, intr0, intr1, confidence, choose_c
         thresh = 3.0 / ((intr0[:, 0, 0] + intr0[:, 1, 1] + intr1[:, 0, 0] + intr1[:, 1, 1]) / 4.0)
         inliers = pos & (epi <= thresh[:, None])
     info = {'kpts0_norm': k0n, 'kpts1_norm': k1n, 'confidence': confidence, 'inliers': inliers,
-            'pos_depth_mask': pos, 'F': Fs}
+            'pos_depth_mask': pos, 'F': Fs, 'vote_counts': vote_counts}
     return T, info
 
 

@@ -56,7 +56,7 @@ def test_sinkhorn_kernels_vs_oracle(shape, spread):
     for kernel in ('ref', 'log', None):
         Z = ops.log_optimal_transport(torch.from_numpy(s).cuda(), 1.0, 100, kernel=kernel).cpu().numpy()
         err = np.abs(Z - ref)
-        lim = (1e-4 if spread < 20 else 3e-4) + 1e-5 * np.abs(ref)
+        lim = (1e-4 if spread < 20 else 6e-4) + 1e-5 * np.abs(ref)
         assert (err <= lim).all(), (kernel, float(err.max()), float((err - lim).max()))
 
 
