@@ -23,7 +23,7 @@ class LayerWeights(C.Structure):
 
 
 class MatcherWeights(C.Structure):
-    _fields_ = [('n_layers', C.c_int),
+    _fields_ = [('n_layers', C.c_int), ('hi_offset', C.c_longlong), ('lo_offset', C.c_longlong),
                 ('kenc_w', _fp * 5), ('kenc_b', _fp * 5),
                 ('layers', LayerWeights * MVM_MAX_LAYERS),
                 ('w_final', _fp), ('b_final', _fp),

@@ -66,6 +66,7 @@ struct GemmDesc {
   const float* A;  int lda;
   const float* A2; int lda2; int K1;
   const float* W;  int ldw;
+  const float* Whi; const float* Wlo;          // optional pre-split tf32 planes of W (3xTF32 mode)
   const float* bias;
   const float* R;  int ldr;
   float* C;        int ldc;

@@ -48,10 +48,10 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, bool PRE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmW, GemmTcArgs g) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo, GemmTcArgs g) {
   using C_ = Cfg<BN, NPASS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -98,11 +98,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = kt % C_::STAGES;
         const uint32_t ph = (kt / C_::STAGES) & 1;
         tc::mbar_wait(empty + s, ph ^ 1);
-        tc::mbar_arrive_expect_tx(full + s, C_::A_BYTES + C_::W_BYTES);
+        tc::mbar_arrive_expect_tx(full + s, C_::A_BYTES + C_::W_BYTES * (PRE ? 2 : 1));
         const int k = kt * BK;
         if (k < g.K1) tc::tma_load_2d(stage_A(s), &tmA, full + s, k, m0);
         else tc::tma_load_2d(stage_A(s), &tmA2, full + s, k - g.K1, m0);
-        tc::tma_load_2d(stage_W(s), &tmW, full + s, k, n0);
+        tc::tma_load_2d(stage_W(s), &tmW, full + s, k, n0);            // PRE: the rn_tf32 plane of W
+        if (PRE) tc::tma_load_2d(stage_Wlo(s), &tmWlo, full + s, k, n0);
       }
     }
   } else if (warp == 1) {
@@ -156,7 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float4* w = reinterpret_cast<float4*>(stage_W(s));
         float4* wlo = reinterpret_cast<float4*>(stage_Wlo(s));
 #pragma unroll
-        for (int i = 0; i < (BN * BK / 4) / 128; ++i) {
+        for (int i = 0; i < (PRE ? 0 : (BN * BK / 4) / 128); ++i) {
           const float4 x = w[et + i * 128];
           float4 h;
           h.x = tc::tf32_rn(x.x); h.y = tc::tf32_rn(x.y); h.z = tc::tf32_rn(x.z); h.w = tc::tf32_rn(x.w);
@@ -251,23 +252,24 @@ typedef std::tuple<const void*, long long, long long, long long, long long, long
 std::map<TmKey, CUtensorMap*> g_tmaps;
 std::mutex g_tmap_mu;
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, bool PRE>
 int launch_cfg(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO, cudaStream_t stream) {
   using C_ = Cfg<BN, NPASS>;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
     attr = true;
   }
   const CUtensorMap* tA = mvm_get_tmap_2d(d.A, d.M, d.K1, d.lda, BM);
   const CUtensorMap* tA2 = d.A2 ? mvm_get_tmap_2d(d.A2, d.M, d.K - d.K1, d.lda2, BM) : tA;
-  const CUtensorMap* tW = mvm_get_tmap_2d(d.W, d.N, d.K, d.ldw, BN);
-  if (!tA || !tA2 || !tW) return MVM_ERR_LAUNCH;
+  const CUtensorMap* tW = mvm_get_tmap_2d(PRE ? d.Whi : d.W, d.N, d.K, d.ldw, BN);
+  const CUtensorMap* tWlo = PRE ? mvm_get_tmap_2d(d.Wlo, d.N, d.K, d.ldw, BN) : tW;
+  if (!tA || !tA2 || !tW || !tWlo) return MVM_ERR_LAUNCH;
   GemmTcArgs g;
   g.bias = d.bias; g.R = d.R; g.ldr = d.ldr; g.C = d.C; g.ldc = d.ldc; g.M = d.M; g.N = d.N; g.K = d.K;
   g.K1 = d.K1; g.alpha = d.alpha; g.relu = d.relu; g.VT = VT; g.vt_col0 = vt_col0; g.n_pad = n_pad; g.KLO = KLO; g.VTLO = VTLO;
   dim3 grid(d.N / BN, mvm_div_up(d.M, BM));
-  gemm_tc_kernel<BN, NPASS><<<grid, NTHREADS, C_::SMEM_BYTES, stream>>>(*tA, *tA2, *tW, g);
+  gemm_tc_kernel<BN, NPASS, PRE><<<grid, NTHREADS, C_::SMEM_BYTES, stream>>>(*tA, *tA2, *tW, *tWlo, g);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }
@@ -312,6 +314,7 @@ int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_
   MVM_REQUIRE(d.lda % 4 == 0 && d.ldw % 4 == 0 && d.ldc % 4 == 0 && (d.R == nullptr || d.ldr % 4 == 0));
   MVM_REQUIRE(d.A2 == nullptr || d.lda2 % 4 == 0);
   MvmProfScope prof__(MVM_TAG_GEMM, stream);
-  if (n_pass == 3) return launch_cfg<128, 3>(d, VT, vt_col0, n_pad, KLO, VTLO, stream);
-  return launch_cfg<128, 1>(d, VT, vt_col0, n_pad, nullptr, nullptr, stream);
+  if (n_pass == 3 && d.Whi && d.Wlo) return launch_cfg<128, 3, true>(d, VT, vt_col0, n_pad, KLO, VTLO, stream);
+  if (n_pass == 3) return launch_cfg<128, 3, false>(d, VT, vt_col0, n_pad, KLO, VTLO, stream);
+  return launch_cfg<128, 1, false>(d, VT, vt_col0, n_pad, nullptr, nullptr, stream);
 }

@@ -58,7 +58,7 @@ GemmDesc make_gemm(const float* A, int lda, const float* W, int K, const float* 
                    int ldc, int M, int N, int relu) {
   GemmDesc g;
   g.A = A; g.lda = lda; g.A2 = nullptr; g.lda2 = 0; g.K1 = K;
-  g.W = W; g.ldw = K; g.bias = bias; g.R = nullptr; g.ldr = 0;
+  g.W = W; g.ldw = K; g.Whi = nullptr; g.Wlo = nullptr; g.bias = bias; g.R = nullptr; g.ldr = 0;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = 1.f; g.relu = relu;
   g.batch = 1; g.sA = g.sA2 = g.sW = g.sR = g.sC = 0;
   return g;
@@ -68,7 +68,11 @@ GemmDesc make_gemm(const float* A, int lda, const float* W, int K, const float* 
 // (fp32-faithful, default), 1 = tcgen05 single-pass TF32
 int g_math_mode = 0;
 
-int run_gemm(const GemmDesc& g, cudaStream_t s) {
+long long g_hi_off = 0, g_lo_off = 0;   // set per forward from mvm_matcher_weights
+
+int run_gemm(const GemmDesc& g_in, cudaStream_t s) {
+  GemmDesc g = g_in;
+  if (g_math_mode == 3 && g_lo_off != 0) { g.Whi = g.W + g_hi_off; g.Wlo = g.W + g_lo_off; }
   if (g_math_mode != 0 && g.batch == 1 && g.N % 128 == 0 && g.K % 32 == 0 && g.K1 % 32 == 0 && g.ldc % 4 == 0)
     return launch_gemm_tc(g, g_math_mode, nullptr, 0, 0, s);
   return launch_gemm_simt(g, s);
@@ -125,6 +129,7 @@ int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, in
   Workspace ws = carve((char*)workspace, batch, n_views, n_pad, n_pairs, w->has_conf);
   if (ws.total > workspace_bytes) return MVM_ERR_WORKSPACE;
 
+  g_hi_off = w->hi_offset; g_lo_off = w->lo_offset;
   const int V = batch * n_views;
   const int rows = V * n_pad;
   AttnSegs segs;
@@ -148,8 +153,9 @@ int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, in
       // tensor-core path: the QKV GEMM epilogue also writes V^T [view, 256, n_pad] for the P.V product
       float* klo = g_math_mode == 3 ? ws.KLO : nullptr;
       float* vtlo = g_math_mode == 3 ? ws.VTLO : nullptr;
-      MVM_TRY(launch_gemm_tc(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), g_math_mode,
-                             ws.VT, 512, n_pad, s, klo, vtlo));
+      GemmDesc gq = make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0);
+      if (g_math_mode == 3 && g_lo_off != 0) { gq.Whi = gq.W + g_hi_off; gq.Wlo = gq.W + g_lo_off; }
+      MVM_TRY(launch_gemm_tc(gq, g_math_mode, ws.VT, 512, n_pad, s, klo, vtlo));
       MVM_TRY(launch_attention_tc(ws.QKV, ws.VT, ws.MSG, batch, n_pad, segs, L.is_cross, g_math_mode, s, klo, vtlo));
     } else {
       MVM_TRY(run_gemm(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), s));

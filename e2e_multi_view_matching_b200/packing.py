@@ -109,7 +109,12 @@ class PackedMatcher:
         flat = torch.zeros(off, dtype=torch.float32)
         for name, t in tensors:
             flat[offsets[name]:offsets[name] + t.numel()] = t.reshape(-1).float()
-        self.flat = flat.to(device)
+        # three planes in one allocation: raw fp32 | rn_tf32(w) | rn_tf32(w - rn_tf32(w))
+        def rn_tf32(x):     # cvt.rna.tf32.f32: round to nearest, ties away, on the 13 dropped bits
+            return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+        hi = rn_tf32(flat)
+        lo = rn_tf32(flat - hi)
+        self.flat = torch.cat([flat, hi, lo]).to(device)
         self.offsets = offsets
         base = self.flat.data_ptr()
 
@@ -118,6 +123,8 @@ class PackedMatcher:
 
         W = _lib.MatcherWeights()
         W.n_layers = len(layer_names)
+        W.hi_offset = off
+        W.lo_offset = 2 * off
         for i in range(n_kenc):
             W.kenc_w[i] = P('kenc_w%d' % i)
             W.kenc_b[i] = P('kenc_b%d' % i)

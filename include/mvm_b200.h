@@ -45,6 +45,9 @@ typedef struct mvm_layer_weights {
 /* Whole matcher (multi_view_matcher.py:103-148).  Device pointers; BN folded everywhere. */
 typedef struct mvm_matcher_weights {
   int n_layers;
+  /* tf32 hi / lo copies of the whole flat weight buffer for the 3xTF32 mode, as float offsets from any
+   * weight pointer below (0 = not provided: the GEMM splits the weight tiles on chip) */
+  long long hi_offset, lo_offset;
   /* KeypointEncoder 3->32->64->128->256->256 (multi_view_matcher.py:24-37) */
   const float* kenc_w[5];
   const float* kenc_b[5];
