@@ -39,6 +39,7 @@ struct SinkCfg {
   int G, NG, batch, iters;
   float alpha;
   int xch_stride;
+  long long* timing;   // optional [8] cycle counters of CTA 0 (debug/profiling), or null
 };
 
 constexpr float ABSORB_HI = 2980.958f;     // e^8
@@ -97,7 +98,9 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
     for (int j = tid; j <= n; j += blockDim.x) { b_s[j] = 1.f; vt_s[j] = 0.f; kb_s[j] = 1.f; }
     __syncthreads();
 
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
     for (int it = 0; it < cfg.iters; ++it) {
+      long long t0 = clock64();
       // ---- row pass: a_i = mu / (sum_j K~_ij b_j + e_i kb_n b_n) ----
       const float bin_col = kb_s[n] * b_s[n];
       bool row_bad = false;
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
         }
         __syncthreads();
       }
+      { long long t1 = clock64(); tacc[0] += t1 - t0; t0 = t1; }
       // ---- column pass: partial c_j = sum_{own rows} K~_ij a_i ; dustbin column: kb_n sum e_i a_i ----
       for (int j = tid; j < n; j += blockDim.x) {
         float s = 0.f;
@@ -141,8 +145,10 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
         s = warp_sum(s);
         if (lane == 0) __stcg(cpart + (size_t)c * (n + 1) + n, s * kb_s[n]);
       }
+      { long long t1 = clock64(); tacc[1] += t1 - t0; t0 = t1; }
       bar_count += G;
       group_barrier(ctr, bar_count);
+      { long long t1 = clock64(); tacc[2] += t1 - t0; t0 = t1; }
       // ---- merge this CTA's column slice in a fixed order: b_j = nu_j / (sum_g c_j^g + kb_j a_m) ----
       {
         const float am = a_s[R];
@@ -153,8 +159,10 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
           if (lane == 0) __stcg(bx + j, (j < n ? nu : nu_bin) / (s + kb_s[j] * am));
         }
       }
+      { long long t1 = clock64(); tacc[3] += t1 - t0; t0 = t1; }
       bar_count += G;
       group_barrier(ctr, bar_count);
+      { long long t1 = clock64(); tacc[4] += t1 - t0; t0 = t1; }
       // ---- reload b; column re-absorption decided identically by every CTA of the group ----
       float bmx = 0.f, bmn = 3.0e38f;
       for (int j = tid; j <= n; j += blockDim.x) {
@@ -178,6 +186,8 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
       }
     }
 
+    if (cfg.timing && blockIdx.x == 0 && tid == 0 && prob == 0)
+      for (int i = 0; i < 5; ++i) cfg.timing[i] = tacc[i];
     // ---- output: Z + u + v - norm with u = u~ + log a, v = v~ + log b ----
     for (int j = tid; j <= n; j += blockDim.x) vt_s[j] += logf(b_s[j]);
     __syncthreads();
@@ -197,6 +207,9 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
 }
 
 }  // namespace
+
+long long* g_sink_timing = nullptr;
+extern "C" void mvm_debug_set_sinkhorn_timing(long long* p) { g_sink_timing = p; }
 
 int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
                     cudaStream_t stream) {
@@ -242,6 +255,7 @@ int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int it
   SinkCfg cfg;
   cfg.G = G; cfg.NG = NG; cfg.batch = batch; cfg.iters = iters; cfg.alpha = bin_score;
   cfg.xch_stride = (G + 1) * (max_n + 1);
+  cfg.timing = g_sink_timing;
   unsigned* ctrs = reinterpret_cast<unsigned*>(ws);
   float* xch = ws + 256;
   cudaMemsetAsync(ctrs, 0, 256 * sizeof(float), stream);
