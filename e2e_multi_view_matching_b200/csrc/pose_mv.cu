@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
   __shared__ double s_acc[NW][NPART];
   __shared__ double s_tot[NPART];
   __shared__ double s_H[MAXU * MAXU];
-  __shared__ double s_rhs[MAXU], s_hd[MAXU];
+  __shared__ double s_rhs[MAXU], s_hd[MAXU], s_gc[MAXU];
+  __shared__ double s_pc[MVM_MAX_PAIRS], s_pg[MVM_MAX_PAIRS], s_dec[4 * MVM_MAX_PAIRS];
   __shared__ double s_cam[MVM_MAX_VIEWS][6], s_camn[MVM_MAX_VIEWS][6];
   __shared__ double s_Ra[9], s_Rb[9], s_sc[MVM_MAX_VIEWS][6];
   __shared__ double s_ctl[8];   // radius, decrease, cost, flags
@@ -649,34 +650,26 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
       }
       if (tid < nu) {
         const int cu = tid / 6 + 1, c = tid % 6;
-        double rs = 0.0, hd = 0.0;
+        double rs = 0.0, hd = 0.0, gc = 0.0;
         for (int q = 0; q < P; ++q) {
           const double* rec = xch + (long long)q * NPART;
-          if (g.a[q] == cu) { rs += __ldcg(rec + 78 + c); hd += __ldcg(rec + 90 + c); }
-          if (g.b[q] == cu) { rs += __ldcg(rec + 84 + c); hd += __ldcg(rec + 96 + c); }
+          if (g.a[q] == cu) { rs += __ldcg(rec + 78 + c); hd += __ldcg(rec + 90 + c); gc += __ldcg(rec + 104 + c); }
+          if (g.b[q] == cu) { rs += __ldcg(rec + 84 + c); hd += __ldcg(rec + 96 + c); gc += __ldcg(rec + 110 + c); }
         }
         s_rhs[tid] = rs;
         s_hd[tid] = hd;
+        s_gc[tid] = fabs(gc / s_sc[cu][c]);   // camera part of the unscaled gradient (Ceres tests max |J^T r|)
+      }
+      if (tid >= 64 && tid < 64 + P) {        // per-pair cost / point-gradient records, one load per thread
+        const double* rec = xch + (long long)(tid - 64) * NPART;
+        s_pc[tid - 64] = __ldcg(rec + 102);
+        s_pg[tid - 64] = __ldcg(rec + 103);
       }
       __syncthreads();
       if (tid == 0) {
         double cost = 0.0, gmax = 0.0;
-        for (int q = 0; q < P; ++q) {
-          const double* rec = xch + (long long)q * NPART;
-          cost += __ldcg(rec + 102);
-          gmax = fmax(gmax, __ldcg(rec + 103));
-        }
-        // camera part of the unscaled gradient max-norm (Ceres tests max |J^T r|)
-        for (int v = 1; v < T; ++v)
-          for (int c = 0; c < 6; ++c) {
-            double gc = 0.0;
-            for (int q = 0; q < P; ++q) {
-              const double* rec = xch + (long long)q * NPART;
-              if (g.a[q] == v) gc += __ldcg(rec + 104 + c);
-              if (g.b[q] == v) gc += __ldcg(rec + 110 + c);
-            }
-            gmax = fmax(gmax, fabs(gc / s_sc[v][c]));
-          }
+        for (int q = 0; q < P; ++q) { cost += s_pc[q]; gmax = fmax(gmax, s_pg[q]); }   // fixed order
+        for (int u = 0; u < nu; ++u) gmax = fmax(gmax, s_gc[u]);
         for (int u = 0; u < nu; ++u) s_H[u * MAXU + u] += fmin(fmax(s_hd[u], 1e-6), 1e32) / radius;
         if (need_cost0) { s_ctl[2] = cost; if (g.cost_out && p == 0) g.cost_out[bi * 2] = cost; }
         s_ctl[3] = gmax;
@@ -771,11 +764,12 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         }
       }
       exchange(4);
+      if (tid < 4 * P) s_dec[tid] = __ldcg(xch + (long long)(tid >> 2) * NPART + (tid & 3));
+      __syncthreads();
       if (tid == 0) {
         double cnew = 0.0, mod = 0.0, dn2 = 0.0, xn2 = 0.0;
-        for (int q = 0; q < P; ++q) {
-          const double* rec = xch + (long long)q * NPART;
-          cnew += __ldcg(rec); mod += __ldcg(rec + 1); dn2 += __ldcg(rec + 2); xn2 += __ldcg(rec + 3);
+        for (int q = 0; q < P; ++q) {     // fixed order: identical on every CTA of the tuple
+          cnew += s_dec[4 * q]; mod += s_dec[4 * q + 1]; dn2 += s_dec[4 * q + 2]; xn2 += s_dec[4 * q + 3];
         }
         for (int v = 1; v < T; ++v)
           for (int c = 0; c < 6; ++c) {
