@@ -405,6 +405,7 @@ __device__ __forceinline__ void wacc(double* dst, double v, int lane) {
 }
 
 __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
+  extern __shared__ double s_rec[];   // [P][NPART] all partial records of the tuple, staged once per exchange
   __shared__ double s_acc[NW][NPART];
   __shared__ double s_tot[NPART];
   __shared__ double s_H[MAXU * MAXU];
@@ -423,7 +424,8 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
   const bool fix_a = va == 0, fix_b = vb == 0;
   unsigned* ctr = g.ctrs + group;
   unsigned bar = 0;
-  double* xch = g.xch + (long long)group * P * NPART;
+  double* xch_base = g.xch + (long long)group * 2 * P * NPART;   // two buffers, used alternately
+  unsigned xk = 0;
   const int nu = 6 * (T - 1);
 
   auto zero_acc = [&]() {
@@ -432,6 +434,10 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
   };
   // publish this CTA's partial record, barrier, then every CTA sums all P records
   auto exchange = [&](int n) {
+    // ping-pong exchange buffers: a CTA can only reach exchange k+2 (which reuses buffer k) after the
+    // barrier of exchange k+1, which every CTA passes after it has staged the records of exchange k
+    double* xch = xch_base + (long long)(xk & 1u) * P * NPART;
+    ++xk;
     __syncthreads();
     for (int e = tid; e < n; e += NT) {
       double s = 0.0;
@@ -440,6 +446,8 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
     }
     bar += P;
     group_barrier(ctr, bar);
+    for (int e = tid; e < P * n; e += NT) s_rec[(e / n) * NPART + (e % n)] = __ldcg(xch + (long long)(e / n) * NPART + (e % n));
+    __syncthreads();
   };
 
   for (int bi = group; bi < g.batch; bi += g.n_groups) {
@@ -470,10 +478,8 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
       exchange(1);
     }
     double csum = 0.0;
-    for (int q = 0; q < P; ++q) csum += __ldcg(xch + (long long)q * NPART);
+    for (int q = 0; q < P; ++q) csum += s_rec[q * NPART];
     const double wscale = 1.0 / (0.5 * (csum + 1e-3));
-    bar += P;
-    group_barrier(ctr, bar);       // everyone has read the sums before xch is reused
 
     // ---- initial points: DLT with the initial extrinsics ----
     {
@@ -519,14 +525,13 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
       const int v = tid / 6, c = tid % 6;
       double s = 0.0;
       for (int q = 0; q < P; ++q) {
-        if (g.a[q] == v) s += __ldcg(xch + (long long)q * NPART + c);
-        if (g.b[q] == v) s += __ldcg(xch + (long long)q * NPART + 6 + c);
+        if (g.a[q] == v) s += s_rec[q * NPART + c];
+        if (g.b[q] == v) s += s_rec[q * NPART + 6 + c];
       }
       s_sc[v][c] = 1.0 / (1.0 + sqrt(s));
     }
     if (tid == 0) { s_ctl[0] = 1e4; s_ctl[1] = 2.0; s_ctl[2] = -1.0; s_flag[0] = 0; }
-    bar += P;
-    group_barrier(ctr, bar);
+    __syncthreads();
 
     int it = 0;
     bool need_cost0 = true;
@@ -638,13 +643,13 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         const int cu = u / 6 + 1, r = u % 6, cv = v / 6 + 1, c = v % 6;
         double s = 0.0;
         for (int q = 0; q < P; ++q) {
-          const double* rec = xch + (long long)q * NPART;
+          const double* rec = s_rec + q * NPART;
           const int lo = r < c ? r : c, hi = r < c ? c : r;
           const int sym = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
-          if (g.a[q] == cu && g.a[q] == cv) s += __ldcg(rec + sym);
-          if (g.b[q] == cu && g.b[q] == cv) s += __ldcg(rec + 21 + sym);
-          if (g.a[q] == cu && g.b[q] == cv) s += __ldcg(rec + 42 + r * 6 + c);
-          if (g.b[q] == cu && g.a[q] == cv) s += __ldcg(rec + 42 + c * 6 + r);
+          if (g.a[q] == cu && g.a[q] == cv) s += *(rec + sym);
+          if (g.b[q] == cu && g.b[q] == cv) s += *(rec + 21 + sym);
+          if (g.a[q] == cu && g.b[q] == cv) s += *(rec + 42 + r * 6 + c);
+          if (g.b[q] == cu && g.a[q] == cv) s += *(rec + 42 + c * 6 + r);
         }
         s_H[u * MAXU + v] = s;
       }
@@ -652,18 +657,18 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         const int cu = tid / 6 + 1, c = tid % 6;
         double rs = 0.0, hd = 0.0, gc = 0.0;
         for (int q = 0; q < P; ++q) {
-          const double* rec = xch + (long long)q * NPART;
-          if (g.a[q] == cu) { rs += __ldcg(rec + 78 + c); hd += __ldcg(rec + 90 + c); gc += __ldcg(rec + 104 + c); }
-          if (g.b[q] == cu) { rs += __ldcg(rec + 84 + c); hd += __ldcg(rec + 96 + c); gc += __ldcg(rec + 110 + c); }
+          const double* rec = s_rec + q * NPART;
+          if (g.a[q] == cu) { rs += *(rec + 78 + c); hd += *(rec + 90 + c); gc += *(rec + 104 + c); }
+          if (g.b[q] == cu) { rs += *(rec + 84 + c); hd += *(rec + 96 + c); gc += *(rec + 110 + c); }
         }
         s_rhs[tid] = rs;
         s_hd[tid] = hd;
         s_gc[tid] = fabs(gc / s_sc[cu][c]);   // camera part of the unscaled gradient (Ceres tests max |J^T r|)
       }
       if (tid >= 64 && tid < 64 + P) {        // per-pair cost / point-gradient records, one load per thread
-        const double* rec = xch + (long long)(tid - 64) * NPART;
-        s_pc[tid - 64] = __ldcg(rec + 102);
-        s_pg[tid - 64] = __ldcg(rec + 103);
+        const double* rec = s_rec + (tid - 64) * NPART;
+        s_pc[tid - 64] = *(rec + 102);
+        s_pg[tid - 64] = *(rec + 103);
       }
       __syncthreads();
       if (tid == 0) {
@@ -680,8 +685,7 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         const bool ok = chol_solve_warp(s_H, s_rhs, nu, lane);
         if (lane == 0) s_flag[1] = ok ? 1 : 0;
       }
-      bar += P;
-      group_barrier(ctr, bar);      // all CTAs finished reading the records
+      __syncthreads();
       const bool solved = s_flag[1] != 0;
       const double cost_cur = s_ctl[2];
       if (s_ctl[3] <= 1e-10) { if (tid == 0) s_flag[0] = 1; __syncthreads(); break; }   // gradient tolerance
@@ -764,7 +768,7 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         }
       }
       exchange(4);
-      if (tid < 4 * P) s_dec[tid] = __ldcg(xch + (long long)(tid >> 2) * NPART + (tid & 3));
+      if (tid < 4 * P) s_dec[tid] = s_rec[(tid >> 2) * NPART + (tid & 3)];
       __syncthreads();
       if (tid == 0) {
         double cnew = 0.0, mod = 0.0, dn2 = 0.0, xn2 = 0.0;
@@ -800,8 +804,7 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         s_ctl[0] = radius_n; s_ctl[1] = dec;
         s_flag[2] = accept; s_flag[3] = stop;
       }
-      bar += P;
-      group_barrier(ctr, bar);
+      __syncthreads();
       if (s_flag[2]) {
         if (tid < T)
           for (int c = 0; c < 6; ++c) s_cam[tid][c] = s_camn[tid][c];
@@ -873,7 +876,7 @@ int mvm_spanning_tree_init(const int* pair_a, const int* pair_b, int n_views, in
 size_t mvm_mvba_workspace_bytes(int n_views, int n_pairs, int batch, int n_pad) {
   const size_t pts = (size_t)batch * n_pairs * 2 * n_pad * 3 * sizeof(double);
   const size_t psc = (size_t)batch * n_pairs * n_pad * 3 * sizeof(double);
-  const size_t xch = (size_t)160 * n_pairs * NPART * sizeof(double);
+  const size_t xch = (size_t)2 * 160 * n_pairs * NPART * sizeof(double);
   return pts + psc + xch + 1024;
 }
 
@@ -908,7 +911,7 @@ int mvm_multi_view_ba(const int* pair_a, const int* pair_b, int n_views, int n_p
   g.pscale = (double*)w; w += (size_t)batch * n_pairs * n_pad * 3 * sizeof(double);
   g.xch = (double*)w;
   cudaMemsetAsync(g.ctrs, 0, 1024, stream);
-  mvba_kernel<<<groups * n_pairs, NT, 0, stream>>>(g);
+  mvba_kernel<<<groups * n_pairs, NT, (size_t)n_pairs * NPART * sizeof(double), stream>>>(g);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }
