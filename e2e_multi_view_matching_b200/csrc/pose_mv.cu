@@ -398,6 +398,43 @@ __device__ bool chol_solve_warp(double* A, double* x, int n, int lane) {
   return true;
 }
 
+
+// Sum 32 per-lane quantities across the warp with 31 shuffle steps (instead of 32 x 5): after the
+// call q[0] of lane l holds the warp total of quantity l.  Fixed order => deterministic.
+__device__ __forceinline__ void warp_reduce_transpose32(double (&q)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const double send = up ? q[i] : q[i + off];
+      const double keep = up ? q[i + off] : q[i];
+      q[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+__device__ constexpr int kSymR[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
+__device__ constexpr int kSymC[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
+// flat record layout of pass A: S_aa (21) | S_bb (21) | S_ab (36) | rhs_a (6) | rhs_b (6) | hdiag_a (6) |
+// hdiag_b (6) | cost | (gmax, handled separately) | gc_a (6) | gc_b (6)
+__device__ __forceinline__ double passA_quantity(int idx, const Obs& oa, const Obs& ob, const double (&Ua)[2][6],
+                                                 const double (&Ub)[2][6], const double (&Uab)[2][6],
+                                                 const double (&ra)[2], const double (&rb)[2], double cost) {
+  if (idx < 21) { const int r = kSymR[idx], c = kSymC[idx]; return oa.Jc[0][r] * Ua[0][c] + oa.Jc[1][r] * Ua[1][c]; }
+  if (idx < 42) { const int r = kSymR[idx - 21], c = kSymC[idx - 21]; return ob.Jc[0][r] * Ub[0][c] + ob.Jc[1][r] * Ub[1][c]; }
+  if (idx < 78) { const int r = (idx - 42) / 6, c = (idx - 42) % 6; return oa.Jc[0][r] * Uab[0][c] + oa.Jc[1][r] * Uab[1][c]; }
+  if (idx < 84) { const int c = idx - 78; return oa.Jc[0][c] * ra[0] + oa.Jc[1][c] * ra[1]; }
+  if (idx < 90) { const int c = idx - 84; return ob.Jc[0][c] * rb[0] + ob.Jc[1][c] * rb[1]; }
+  if (idx < 96) { const int c = idx - 90; return oa.Jc[0][c] * oa.Jc[0][c] + oa.Jc[1][c] * oa.Jc[1][c]; }
+  if (idx < 102) { const int c = idx - 96; return ob.Jc[0][c] * ob.Jc[0][c] + ob.Jc[1][c] * ob.Jc[1][c]; }
+  if (idx == 102) return cost;
+  if (idx >= 104 && idx < 110) { const int c = idx - 104; return oa.Jc[0][c] * oa.r[0] + oa.Jc[1][c] * oa.r[1]; }
+  if (idx >= 110 && idx < 116) { const int c = idx - 110; return ob.Jc[0][c] * ob.r[0] + ob.Jc[1][c] * ob.r[1]; }
+  return 0.0;
+}
+
 // accumulate v (per lane) into dst: warp reduce, lane 0 adds
 __device__ __forceinline__ void wacc(double* dst, double v, int lane) {
   v = warp_sum_d(v);
@@ -605,26 +642,19 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
             for (int c = 0; c < 6; ++c) { Ua[r][c] = Ub[r][c] = Uab[r][c] = oa.Jc[r][c] = ob.Jc[r][c] = 0.0; }
           }
         }
-        // accumulate: S_aa (21) | S_bb (21) | S_ab (36) | rhs_a (6) | rhs_b (6) | hdiag_a (6) | hdiag_b (6) | cost | gmax
+        // accumulate the 116 sums of this 32-point batch: four transposed warp reductions of 32 quantities
         double* acc = s_acc[warp];
-        int e = 0;
-        for (int r = 0; r < 6; ++r)
-          for (int c = r; c < 6; ++c) wacc(acc + e++, oa.Jc[0][r] * Ua[0][c] + oa.Jc[1][r] * Ua[1][c], lane);
-        for (int r = 0; r < 6; ++r)
-          for (int c = r; c < 6; ++c) wacc(acc + e++, ob.Jc[0][r] * Ub[0][c] + ob.Jc[1][r] * Ub[1][c], lane);
-        for (int r = 0; r < 6; ++r)
-          for (int c = 0; c < 6; ++c) wacc(acc + e++, oa.Jc[0][r] * Uab[0][c] + oa.Jc[1][r] * Uab[1][c], lane);
-        for (int c = 0; c < 6; ++c) wacc(acc + e++, oa.Jc[0][c] * ra[0] + oa.Jc[1][c] * ra[1], lane);
-        for (int c = 0; c < 6; ++c) wacc(acc + e++, ob.Jc[0][c] * rb[0] + ob.Jc[1][c] * rb[1], lane);
-        for (int c = 0; c < 6; ++c) wacc(acc + e++, oa.Jc[0][c] * oa.Jc[0][c] + oa.Jc[1][c] * oa.Jc[1][c], lane);
-        for (int c = 0; c < 6; ++c) wacc(acc + e++, ob.Jc[0][c] * ob.Jc[0][c] + ob.Jc[1][c] * ob.Jc[1][c], lane);
-        wacc(acc + e++, cost, lane);
+#pragma unroll
+        for (int grp = 0; grp < 4; ++grp) {
+          double q[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) q[i] = passA_quantity(grp * 32 + i, oa, ob, Ua, Ub, Uab, ra, rb, cost);
+          warp_reduce_transpose32(q, lane);
+          if (grp * 32 + lane != 103) acc[grp * 32 + lane] += q[0];
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-        if (lane == 0) acc[e] = fmax(acc[e], gmax);
-        // raw (scaled) camera gradient J_c^T r for the gradient-tolerance test
-        for (int c = 0; c < 6; ++c) wacc(acc + 104 + c, oa.Jc[0][c] * oa.r[0] + oa.Jc[1][c] * oa.r[1], lane);
-        for (int c = 0; c < 6; ++c) wacc(acc + 110 + c, ob.Jc[0][c] * ob.r[0] + ob.Jc[1][c] * ob.r[1], lane);
+        if (lane == 0) acc[103] = fmax(acc[103], gmax);
       }
       // gmax is a max, not a sum: fold the per-warp maxima before publishing
       __syncthreads();
