@@ -102,6 +102,9 @@ def lib():
     L.mvm_spanning_tree_init.restype = C.c_int
     L.mvm_spanning_tree_init.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
                                          _fp, _fp, _fp, _fp, _fp, _fp]
+    L.mvm_ba_initialize.restype = C.c_int
+    L.mvm_ba_initialize.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
+                                    _fp, _fp, _fp, _fp, _fp, C.c_int, _fp, _fp, _fp]
     L.mvm_mvba_workspace_bytes.restype = C.c_size_t
     L.mvm_mvba_workspace_bytes.argtypes = [C.c_int] * 4
     L.mvm_multi_view_ba.restype = C.c_int

@@ -26,7 +26,6 @@ namespace {
 constexpr int NT = 256;
 constexpr int NW = NT / 32;
 constexpr int MAXC = 7;                 // free cameras (views - 1)
-constexpr int MAXU = 6 * MAXC;          // reduced unknowns
 constexpr int NPART = 128;              // doubles per CTA partial record
 
 // ---------------------------------------------------------------------------------------------
@@ -219,50 +218,6 @@ __device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();
 }
 
-__device__ void aa_to_R(const double* w, double* R) {
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
-  if (th2 > 2.220446049250313e-16) {
-    const double th = sqrt(th2), k0 = w[0] / th, k1 = w[1] / th, k2 = w[2] / th;
-    const double c = cos(th), s = sin(th), v = 1.0 - c;
-    // I + s K + (1-c) K^2, K = hat(k)
-    R[0] = 1 + v * (-(k1 * k1 + k2 * k2)); R[1] = -s * k2 + v * k0 * k1; R[2] = s * k1 + v * k0 * k2;
-    R[3] = s * k2 + v * k0 * k1; R[4] = 1 + v * (-(k0 * k0 + k2 * k2)); R[5] = -s * k0 + v * k1 * k2;
-    R[6] = -s * k1 + v * k0 * k2; R[7] = s * k0 + v * k1 * k2; R[8] = 1 + v * (-(k0 * k0 + k1 * k1));
-  } else {
-    R[0] = 1; R[1] = -w[2]; R[2] = w[1]; R[3] = w[2]; R[4] = 1; R[5] = -w[0]; R[6] = -w[1]; R[7] = w[0]; R[8] = 1;
-  }
-}
-
-__device__ void R_to_aa(const double* R, double* w) {
-  // ceres::RotationMatrixToAngleAxis via the quaternion
-  double q[4];
-  const double tr = R[0] + R[4] + R[8];
-  if (tr >= 0.0) {
-    double t = sqrt(tr + 1.0);
-    q[0] = 0.5 * t; t = 0.5 / t;
-    q[1] = (R[7] - R[5]) * t; q[2] = (R[2] - R[6]) * t; q[3] = (R[3] - R[1]) * t;
-  } else {
-    int i = 0;
-    if (R[4] > R[0]) i = 1;
-    if (R[8] > R[i * 4]) i = 2;
-    const int j = (i + 1) % 3, k = (j + 1) % 3;
-    double t = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
-    q[i + 1] = 0.5 * t; t = 0.5 / t;
-    q[0] = (R[k * 3 + j] - R[j * 3 + k]) * t;
-    q[j + 1] = (R[j * 3 + i] + R[i * 3 + j]) * t;
-    q[k + 1] = (R[k * 3 + i] + R[i * 3 + k]) * t;
-  }
-  const double s2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
-  if (s2 > 0.0) {
-    const double s = sqrt(s2);
-    const double th = q[0] < 0.0 ? 2.0 * atan2(-s, -q[0]) : 2.0 * atan2(s, q[0]);
-    const double k = th / s;
-    w[0] = q[1] * k; w[1] = q[2] * k; w[2] = q[3] * k;
-  } else {
-    w[0] = q[1] * 2.0; w[1] = q[2] * 2.0; w[2] = q[3] * 2.0;
-  }
-}
-
 // d(R(w) p)/dw = -R [p]x (w w^T + (R^T - I)[w]x) / |w|^2   (-[p]x at w = 0)
 __device__ void dRp_dw(const double* w, const double* R, const double* p, double* D) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
@@ -361,43 +316,6 @@ __device__ __forceinline__ void eval_obs(bool fixed, const double* cam, const do
     }
   }
 }
-
-// warp-cooperative Cholesky solve of the n x n SPD system in shared memory (n <= 42).
-// A (row-major, ld = MAXU) is overwritten, x holds rhs on entry / solution on exit.
-__device__ bool chol_solve_warp(double* A, double* x, int n, int lane) {
-  bool ok = true;
-  for (int k = 0; k < n; ++k) {
-    __syncwarp();
-    double d = A[k * MAXU + k];
-    if (!(d > 0.0)) { ok = false; break; }
-    d = sqrt(d);
-    __syncwarp();
-    if (lane == 0) A[k * MAXU + k] = d;
-    for (int i = k + 1 + lane; i < n; i += 32) A[i * MAXU + k] /= d;
-    __syncwarp();
-    for (int j = k + 1; j < n; ++j) {
-      const double ljk = A[j * MAXU + k];
-      for (int i = j + lane; i < n; i += 32) A[i * MAXU + j] -= A[i * MAXU + k] * ljk;
-    }
-  }
-  __syncwarp();
-  if (!ok) return false;
-  if (lane == 0) {
-    for (int i = 0; i < n; ++i) {
-      double s = x[i];
-      for (int j = 0; j < i; ++j) s -= A[i * MAXU + j] * x[j];
-      x[i] = s / A[i * MAXU + i];
-    }
-    for (int i = n - 1; i >= 0; --i) {
-      double s = x[i];
-      for (int j = i + 1; j < n; ++j) s -= A[j * MAXU + i] * x[j];
-      x[i] = s / A[i * MAXU + i];
-    }
-  }
-  __syncwarp();
-  return true;
-}
-
 
 // Sum 32 per-lane quantities across the warp with 31 shuffle steps (instead of 32 x 5): after the
 // call q[0] of lane l holds the warp total of quantity l.  Fixed order => deterministic.

@@ -8,8 +8,8 @@ stream-ordered kernel launches with no host synchronisation:
   mvm_spanning_tree_init maximum spanning tree + chaining  (bundle_adjust_io.py:135-172)
   mvm_multi_view_ba      global BA, camera 0 fixed         (ba_problem.cpp:115-157)
 
-The Theia rotation-averaging / LUD step of `ba_initializer` (ba_init.cpp:77-91) is NOT built yet
-(SURVEY.md §8 f-1): the global BA starts from the spanning-tree poses.
+  mvm_ba_initialize      rotation averaging + LUD positions (ba_init.cpp:77-91, the `ba_initializer` binary)
+between the spanning tree and the global BA (six launches in total).
 """
 import ctypes as C
 
@@ -23,10 +23,13 @@ def _intr4(intr):
 
 
 class MultiViewPoseEngine:
-    def __init__(self, conf_thresh=0.0, n_iterations_2view=10, max_iterations_ba=50):
+    def __init__(self, conf_thresh=0.0, n_iterations_2view=10, max_iterations_ba=50, use_ba_init=True,
+                 min_inliers=20):
         self.conf_thresh = conf_thresh
         self.n_it2 = n_iterations_2view
         self.max_it = max_iterations_ba
+        self.use_ba_init = use_ba_init
+        self.min_inliers = min_inliers
         self._ws = None
 
     def run(self, state, intr, global_ba=True):
@@ -76,8 +79,15 @@ class MultiViewPoseEngine:
             pa = (C.c_int * P)(*[a for a, _ in pair_ids])
             pb = (C.c_int * P)(*[b for _, b in pair_ids])
             extr0 = torch.empty(B, T, 4, 4, dtype=torch.float64, device=dev)
+            on_tree = torch.empty(B, P, dtype=torch.uint8, device=dev)
             _lib.check(lib.mvm_spanning_tree_init(pa, pb, T, P, B, _lib.ptr(T_ba), _lib.ptr(n_valid), _lib.ptr(succ),
-                                                  _lib.ptr(extr0), None, sp), 'mvm_spanning_tree_init')
+                                                  _lib.ptr(extr0), _lib.ptr(on_tree), sp), 'mvm_spanning_tree_init')
+            extr_tree = extr0
+            if self.use_ba_init:
+                extr0 = torch.empty(B, T, 4, 4, dtype=torch.float64, device=dev)
+                _lib.check(lib.mvm_ba_initialize(pa, pb, T, P, B, n_pad, _lib.ptr(extr_tree), _lib.ptr(T_ba),
+                                                 _lib.ptr(succ), _lib.ptr(on_tree), _lib.ptr(inl), int(self.min_inliers),
+                                                 _lib.ptr(extr0), None, sp), 'mvm_ba_initialize')
             nbytes = lib.mvm_mvba_workspace_bytes(T, P, B, n_pad)
             if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
                 self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -88,7 +98,7 @@ class MultiViewPoseEngine:
                                              _lib.ptr(n_valid), _lib.ptr(extr0), _lib.ptr(extr), int(self.max_it),
                                              _lib.ptr(iters), _lib.ptr(cost), _lib.ptr(self._ws), nbytes, sp),
                        'mvm_multi_view_ba')
-            out.update({'extrinsics_init': extr0, 'extrinsics': extr, 'ba_iterations': iters, 'ba_cost': cost,
+            out.update({'extrinsics_tree': extr_tree, 'extrinsics_init': extr0, 'extrinsics': extr, 'ba_iterations': iters, 'ba_cost': cost,
                         'kpts_norm_a': k0n, 'kpts_norm_b': k1n, 'mconf': mconf})
         return out
 

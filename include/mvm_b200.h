@@ -199,6 +199,16 @@ int mvm_spanning_tree_init(const int* pair_a, const int* pair_b, int n_views, in
                            const float* T_rel, const int* weight, const unsigned char* success,
                            double* extr, unsigned char* on_tree, void* stream);
 
+/* Replacement of the `ba_initializer` binary (ba_init.cpp:77-91: Theia RobustRotationEstimator, initialised
+ * from the spanning-tree rotations, then LeastUnsquaredDeviationPositionEstimator; restated in
+ * oracle/ba_init.py).  Edges = successful pairs with >= min_inliers inliers or on the spanning tree
+ * (bundle_adjust_io.py:181-190; the reference uses min_inliers = 20).  extr_tree / extr_out [B,T,16]
+ * doubles (world->cam), inliers [B,P,n_pad] bytes, n_edges_out [B] (may be NULL). */
+int mvm_ba_initialize(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch, int n_pad,
+                      const double* extr_tree, const float* T_rel, const unsigned char* success,
+                      const unsigned char* on_tree, const unsigned char* inliers, int min_inliers,
+                      double* extr_out, int* n_edges_out, void* stream);
+
 /* Global bundle adjustment replacing the `bundle_adjuster` binary (ba_problem.cpp:115-157,
  * ba_problem.h:60-151, problem construction bundle_adjust_io.py:193-259): camera 0 fixed, one 3-D
  * point per pairwise match triangulated from extr_init, weights c / (0.5 (sum c + 1e-3)),

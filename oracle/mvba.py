@@ -367,7 +367,7 @@ def make_multi_view_scene(seed, n_views, n_kpts, outlier_frac=0.1, noise_px=0.5,
     return {'kpts': kpts, 'K': K.astype(np.float32), 'poses': np.array(poses), 'matches': matches, 'conf': conf}
 
 
-def multi_view_pipeline(scene, conf_thresh=0.0, n_it2=10, max_iterations=50):
+def multi_view_pipeline(scene, conf_thresh=0.0, n_it2=10, max_iterations=50, use_ba_init=True, min_inliers=20):
     """eval_bundle_adjust (eval_multi_view.py:21-68) without the Theia averaging step (the engine
     does not build it yet): per pair compaction -> w8pt -> two-view BA -> spanning tree -> global BA.
     fp64 throughout."""
@@ -397,7 +397,12 @@ def multi_view_pipeline(scene, conf_thresh=0.0, n_it2=10, max_iterations=50):
             pm[(a, b)] = (info['kpts0_norm'][0], info['kpts1_norm'][0], c[valid])
             info_all[(a, b)] = {'T_w8pt': Tw[0], 'inliers': info['inliers'][0], 'vote_counts': info['vote_counts'][0]}
     extr0, tree = spanning_tree_extrinsics(T, rel, weight)
+    extr_tree = extr0
+    if use_ba_init:     # ba_initializer: pairs written to ba_init_in.csv (bundle_adjust_io.py:181-190)
+        from .ba_init import ba_initialize
+        keep = {k: v for k, v in rel.items() if int(info_all[k]['inliers'].sum()) >= min_inliers or k in tree}
+        extr0 = ba_initialize(T, extr_tree, keep)
     pb = build_problem(T, pm, extr0)
     cams, pts, info = solve(pb, max_iterations=max_iterations)
-    return {'rel': rel, 'extr_init': extr0, 'extr': cams_to_extrinsics(cams), 'info': info, 'pairs': info_all,
+    return {'rel': rel, 'extr_tree': extr_tree, 'extr_init': extr0, 'extr': cams_to_extrinsics(cams), 'info': info, 'pairs': info_all,
             'weight': weight}
