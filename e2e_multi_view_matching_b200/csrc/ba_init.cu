@@ -3,7 +3,7 @@
 // oracle/ba_init.py.  One warp per tuple, fp64, everything in shared memory (<= 8 views, <= 28 pairs).
 //
 //   rotation averaging  residual_e = log(R_j^T R_ij R_i), A = (-I at view i, +I at view j), view 0 fixed
-//       L1 phase   <= 5 x { ADMM for min |A d - r|_1 (rho = alpha = 1, <= 1000 iterations,
+//       L1 phase   <= 5 x { ADMM for min |A d - r|_1 (rho = alpha = 1, 5 iterations doubling every pass,
 //                           abs 1e-4 / rel 1e-2 stopping rule); R_v <- R_v exp(d_v); mean step <= 1e-3 stops }
 //       IRLS phase <= 100 x { w_e = sigma / (|r_e|^2 + sigma^2)^2, sigma = 5 deg; (A^T W A) d = A^T W r }
 //       A^T A is the graph Laplacian (x) I_3, so both phases only ever factor (views-1)^2 systems.
@@ -202,11 +202,12 @@ __global__ void __launch_bounds__(32) ba_init_kernel(BaInitArgs g) {
 
   // ================= rotation averaging: L1 phase =================
   build_laplacian_inverse(nullptr);
-  for (int outer = 0; outer < 5; ++outer) {
+  int admm_iters = 5;   // 5 ADMM iterations in the first pass, doubled in every following one
+  for (int outer = 0; outer < 5; ++outer, admm_iters *= 2) {
     residuals();
     for (int k = lane; k < m3; k += 32) { z[k] = 0.0; u[k] = 0.0; }
     __syncwarp();
-    for (int it = 0; it < 1000; ++it) {
+    for (int it = 0; it < admm_iters; ++it) {
       for (int k = lane; k < m3; k += 32) ax[k] = r[k] + z[k] - u[k];
       __syncwarp();
       At_mul(ax, nullptr, y);

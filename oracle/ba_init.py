@@ -16,8 +16,9 @@ t_i = -R_i c_i (ba_init.cpp:58-75).
 
 Rotation averaging (robust_rotation_estimator.cc):
   residual_e = log(R_j^T R_ij R_i);  A has -I at view i and +I at view j (view 0 fixed);
-  L1 phase: <= 5 times { solve min |A d - r|_1 by ADMM (rho = 1, alpha = 1, <= 1000 iterations,
-  abs tol 1e-4, rel tol 1e-2); R_v <- R_v exp(d_v); stop when the mean step <= 1e-3 };
+  L1 phase: <= 5 times { min |A d - r|_1 by ADMM (rho = 1, alpha = 1, abs tol 1e-4, rel tol 1e-2) with
+  5 ADMM iterations in the first pass and twice as many in every following one; R_v <- R_v exp(d_v);
+  stop when the mean step <= 1e-3 };
   IRLS phase: <= 100 times { w_e = sigma / (|r_e|^2 + sigma^2)^2, sigma = 5 deg; solve
   (A^T W A) d = A^T W r; update; stop when the mean step <= 1e-3 }.
 Position estimation (least_unsquared_deviation_position_estimator.cc):
@@ -89,9 +90,11 @@ def robust_rotation_averaging(n_views, pair_rot, init_rot, max_l1=5, max_irls=10
             rot[v] = _mul(rot[v], step[3 * (v - 1):3 * v])
         return np.mean([np.linalg.norm(step[3 * (v - 1):3 * v]) for v in range(1, n_views)])
 
+    admm_iters = 5                       # robust_rotation_estimator.cc: 5 ADMM iterations, doubled every outer pass
     for _ in range(max_l1):
-        if update(l1_admm(A, residuals())) <= step_tol:
+        if update(l1_admm(A, residuals(), max_iter=admm_iters)) <= step_tol:
             break
+        admm_iters *= 2
     for _ in range(max_irls):
         r = residuals()
         w = np.repeat([SIGMA / (r[3 * e:3 * e + 3] @ r[3 * e:3 * e + 3] + SIGMA ** 2) ** 2 for e in range(len(edges))], 3)

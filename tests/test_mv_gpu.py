@@ -69,7 +69,7 @@ def test_multi_view_pipeline_vs_oracle(T, n, outl):
             continue
         np.testing.assert_allclose(out['extrinsics_tree'][b].cpu().numpy(), ref['extr_tree'], atol=5e-5)
         np.testing.assert_allclose(out['extrinsics_init'][b].cpu().numpy(), ref['extr_init'], atol=2e-4)
-        np.testing.assert_allclose(out['ba_cost'][b, 0].item(), ref['info']['initial_cost'], rtol=1e-4)
+        np.testing.assert_allclose(out['ba_cost'][b, 0].item(), ref['info']['initial_cost'], rtol=1e-3)
         np.testing.assert_allclose(out['ba_cost'][b, 1].item(), ref['info']['final_cost'], rtol=2e-2)
         # the problem has a free global scale (only camera 0 is fixed): compare rotations and
         # translation directions, which is also what the reference evaluates (eval_multi_view.py:54-66)
