@@ -52,7 +52,7 @@ __device__ inline double wsum(double v) { return warp_sum_d(v); }
 __global__ void __launch_bounds__(32) ba_init_kernel(BaInitArgs g) {
   __shared__ double rot[MV][3], prot[ME][3], ppos[ME][3], dirs[ME][3], cpos[MV][3], cprev[MV][3];
   __shared__ int ei[ME], ej[ME];
-  __shared__ double Lw[(MV - 1) * (MV - 1)], Linv[(MV - 1) * (MV - 1)];
+  __shared__ double GJ[(MV - 1) * 2 * (MV - 1)], Linv[(MV - 1) * (MV - 1)];
   __shared__ double r[NR], z[NR], u[NR], zold[NR], ax[NR];
   __shared__ double x[NU], y[NU];
   __shared__ double wgt[ME], sc[ME];
@@ -110,37 +110,38 @@ __global__ void __launch_bounds__(32) ba_init_kernel(BaInitArgs g) {
   }
   const int m3 = 3 * E, n3 = 3 * nf;
 
-  // weighted Laplacian of the free views -> Lw; inverse -> Linv (Gauss-Jordan, lane 0)
+  // weighted Laplacian of the free views -> inverse Linv (warp-cooperative Gauss-Jordan in shared memory;
+  // the Laplacian of a connected graph with view 0 removed is SPD, so no pivoting is needed)
   auto build_laplacian_inverse = [&](const double* w) {
-    if (lane == 0) {
-      for (int i = 0; i < nf * nf; ++i) Lw[i] = 0.0;
+    const int nc2 = 2 * nf;
+    for (int k = lane; k < nf * nc2; k += 32) GJ[k] = (k % nc2 == nf + k / nc2) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int k = lane; k < nf * nf; k += 32) {
+      const int a = k / nf + 1, b = k % nf + 1;
+      double s = 0.0;
       for (int e = 0; e < E; ++e) {
-        const int i = ei[e] - 1, j = ej[e] - 1;
         const double we = w ? w[e] : 1.0;
-        if (i >= 0) Lw[i * nf + i] += we;
-        if (j >= 0) Lw[j * nf + j] += we;
-        if (i >= 0 && j >= 0) { Lw[i * nf + j] -= we; Lw[j * nf + i] -= we; }
+        if (a == b) { if (ei[e] == a || ej[e] == a) s += we; }
+        else if ((ei[e] == a && ej[e] == b) || (ei[e] == b && ej[e] == a)) s -= we;
       }
-      double M[(MV - 1) * 2 * (MV - 1)];
-      for (int i = 0; i < nf; ++i)
-        for (int j = 0; j < nf; ++j) { M[i * 2 * nf + j] = Lw[i * nf + j]; M[i * 2 * nf + nf + j] = i == j ? 1.0 : 0.0; }
-      for (int k = 0; k < nf; ++k) {
-        int piv = k;
-        for (int i = k + 1; i < nf; ++i)
-          if (fabs(M[i * 2 * nf + k]) > fabs(M[piv * 2 * nf + k])) piv = i;
-        if (piv != k)
-          for (int j = 0; j < 2 * nf; ++j) { const double t = M[k * 2 * nf + j]; M[k * 2 * nf + j] = M[piv * 2 * nf + j]; M[piv * 2 * nf + j] = t; }
-        const double inv = 1.0 / M[k * 2 * nf + k];
-        for (int j = 0; j < 2 * nf; ++j) M[k * 2 * nf + j] *= inv;
-        for (int i = 0; i < nf; ++i)
-          if (i != k) {
-            const double f = M[i * 2 * nf + k];
-            for (int j = 0; j < 2 * nf; ++j) M[i * 2 * nf + j] -= f * M[k * 2 * nf + j];
-          }
-      }
-      for (int i = 0; i < nf; ++i)
-        for (int j = 0; j < nf; ++j) Linv[i * nf + j] = M[i * 2 * nf + nf + j];
+      GJ[(a - 1) * nc2 + (b - 1)] = s;
     }
+    __syncwarp();
+    for (int k = 0; k < nf; ++k) {
+      const double inv = 1.0 / GJ[k * nc2 + k];
+      __syncwarp();
+      for (int j = lane; j < nc2; j += 32) GJ[k * nc2 + j] *= inv;
+      __syncwarp();
+      for (int idx = lane; idx < nf * nc2; idx += 32) {
+        const int i = idx / nc2, j = idx % nc2;
+        if (i != k && j != k) GJ[idx] -= GJ[i * nc2 + k] * GJ[k * nc2 + j];
+      }
+      __syncwarp();
+      for (int i = lane; i < nf; i += 32)
+        if (i != k) GJ[i * nc2 + k] = 0.0;
+      __syncwarp();
+    }
+    for (int k = lane; k < nf * nf; k += 32) Linv[k] = GJ[(k / nf) * nc2 + nf + k % nf];
     __syncwarp();
   };
   // y = A^T (w .* v)  (n3),  lanes over unknowns

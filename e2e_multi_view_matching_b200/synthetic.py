@@ -43,7 +43,7 @@ def _put_bn(sd, key, bn):
 
 
 def make_state_dict(n_layers, seed=0, conf_mlp=True, desc_dim=256,
-                    kenc_layers=(32, 64, 128, 256), bin_score=1.0, final_proj_gain=1.0):
+                    kenc_layers=(32, 64, 128, 256), bin_score=1.0, final_proj_gain=1.0, residual_gain=1.0):
     """Deterministic random state dict (numpy arrays) with the reference's keys."""
     rng = np.random.default_rng(seed)
     sd = {}
@@ -65,7 +65,9 @@ def make_state_dict(n_layers, seed=0, conf_mlp=True, desc_dim=256,
         _put_conv(sd, p + 'mlp.0', w, b)
         _put_bn(sd, p + 'mlp.1', _bn(rng, 2 * d))
         w, b = _conv(rng, d, 2 * d, zero_bias=True)
-        _put_conv(sd, p + 'mlp.3', w, b)
+        # residual_gain < 1 shrinks the (random) update every GNN layer adds to the descriptors, so that the
+        # landmark structure of the synthetic descriptors survives 18-28 random layers
+        _put_conv(sd, p + 'mlp.3', w * np.float32(residual_gain), b)
     w, b = _conv(rng, d, d)
     # gain > 1 sharpens the (otherwise nearly flat, random-weight) assignment so
     # that match margins sit well above fp32 noise and Sinkhorn sees a wide range
@@ -190,6 +192,7 @@ def make_scene_tuple_inputs(seed, n_views=5, n_kpts=1024, batch=1, width=640, he
             for key, val in (('keypoints%d' % i, px), ('scores%d' % i, sc), ('descriptors%d' % i, de.T),
                              ('intr%d' % i, K), ('pose%d' % i, T)):
                 out.setdefault(key, []).append(val.astype(np.float32))
+            out.setdefault('landmark%d' % i, []).append(sel.astype(np.int64))
     for k in list(out.keys()):
         out[k] = np.stack(out[k], 0)
     for i in range(n_views):
