@@ -161,6 +161,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--tuples', type=int, default=8, help='tuples per step per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gemm-tile', type=int, default=128, choices=[128, 256])
     ap.add_argument('--math-mode', type=int, default=3, choices=[0, 1, 3],
                     help='3 = tcgen05 3xTF32 (fp32-faithful, default), 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA cores')
     args = ap.parse_args()
@@ -185,6 +186,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.lib()
     lib.mvm_set_math_mode(args.math_mode)
+    lib.mvm_debug_set_gemm_tile(args.gemm_tile)
     B = args.tuples
 
     sd = make_state_dict(len(LAYERS), seed=0, final_proj_gain=GAIN)
@@ -195,7 +197,8 @@ def main():
 
     # tuples 1000 + (rank*B + k): every rank works on its own shard (weak scaling, no data-path collective)
     data_np = make_scene_tuple_inputs(1000 + rank * B, T_VIEWS, N_KPTS, batch=B)
-    keys = [k for k, v in data_np.items() if isinstance(v, np.ndarray) and not k.startswith('image')]
+    keys = [k for k, v in data_np.items() if isinstance(v, np.ndarray) and not k.startswith('image')
+            and not k.startswith('landmark')]
     host = {k: torch.from_numpy(data_np[k]).pin_memory() for k in keys}
     meta = {k: torch.empty(v.shape, device='meta') for k, v in data_np.items() if k.startswith('image')}
     data_dev = {k: v.to(dev) for k, v in host.items()}
@@ -208,8 +211,11 @@ def main():
     d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
     loss = torch.zeros(1, device=dev)
 
+    last = {}
+
     def step_device():
         res, pose = pipe(data_dev)
+        last['res'] = res
         if world > 1:   # one scalar all-reduce per step (mirrors the val-loss all_reduce, train.py:104-106)
             loss.copy_(pose['ba_cost'][:, 1].sum().float().reshape(1))
             dist.all_reduce(loss)
@@ -264,6 +270,17 @@ def main():
     ms_e2e, wall_e2e = timed(step_e2e, args.steps)
     sampler.stop_flag = True
 
+    # secondary line: the same steps in single-pass TF32 (what torch 1.10 ran on Ampere by default)
+    tf32 = None
+    if args.math_mode == 3:
+        lib.mvm_set_math_mode(1)
+        for _ in range(2):
+            step_device()
+        ms_tf32, _ = timed(step_device, args.steps)
+        ms_tf32_e2e, _ = timed(step_e2e, args.steps)
+        lib.mvm_set_math_mode(3)
+        tf32 = (ms_tf32, ms_tf32_e2e)
+
     # live per-kernel-class timing (CUDA events on the launching stream) over two more steps
     lib.mvm_profile_enable(1)
     prof_steps = 2
@@ -289,6 +306,7 @@ def main():
         # pose AUC of the engine on its own synthetic tuples (informational; parity is in tests/)
         errs = MultiViewPipeline.pair_errors({k: v for k, v in data_dev.items() if k.startswith('pose')}, pose, T_VIEWS)
         auc = pose_auc([e[0] for e in errs], [5, 10, 20])
+        last_res = last['res']
         line = {
             'metric': METRIC, 'value': value, 'unit': 'tuples/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -313,6 +331,19 @@ def main():
             'wall_s': {'device_resident': wall_dev, 'e2e': wall_e2e},
             'pose_auc_5_10_20': [round(100 * a, 2) for a in auc],
         }
+        if tf32 is not None:
+            line['tf32_single_pass'] = {'value': total_tuples / (tf32[0] * 1e-3), 'e2e': total_tuples / (tf32[1] * 1e-3),
+                                        'unit': 'tuples/s', 'note': 'math mode 1 (tcgen05 kind::tf32, one pass)'}
+        # quality of the synthetic assignment: fraction of returned matches that join the same landmark
+        hits = tot = 0
+        for b_ in range(T_VIEWS):
+            for a_ in range(b_):
+                m = last_res['matches%d_%d_%d' % (a_, a_, b_)].cpu().numpy()
+                la, lb = data_np['landmark%d' % a_], data_np['landmark%d' % b_]
+                for i in range(B):
+                    v = m[i] >= 0
+                    hits += int((la[i][v] == lb[i][m[i][v]]).sum()); tot += int(v.sum())
+        line['match_precision'] = round(hits / max(tot, 1), 4)
         if world == 1 and not args.no_cpu_baseline:
             t_m, t_p, n_ok = cpu_reference_tuple(sd, data_np)
             line['cpu_baseline'] = {

@@ -268,9 +268,10 @@ __global__ void __launch_bounds__(32) ba_init_kernel(BaInitArgs g) {
   }
   for (int k = lane; k < 3 * MV; k += 32) { (&cpos[0][0])[k] = 0.0; (&cprev[0][0])[k] = 0.0; }
   __syncwarp();
+  // active set of s_e >= 1: all active at the start, warm-started across the reweightings
+  for (int e = lane; e < E; e += 32) { act[e] = 1; sc[e] = 1.0; }
+  __syncwarp();
   for (int rw = 0; rw < 40; ++rw) {
-    for (int e = lane; e < E; e += 32) { act[e] = 1; sc[e] = 1.0; }
-    __syncwarp();
     for (int as = 0; as < 2 * E + 2; ++as) {
       // H = sum_e w_e B_e^T Q_e B_e,  g = sum_active w_e B_e^T Q_e d_e
       for (int k = lane; k < n3 * n3; k += 32) {

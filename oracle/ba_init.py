@@ -105,12 +105,11 @@ def robust_rotation_averaging(n_views, pair_rot, init_rot, max_l1=5, max_irls=10
     return rot
 
 
-def _bounded_wls(n_views, edges, dirs, w):
+def _bounded_wls(n_views, edges, dirs, w, active):
     """min sum_e w_e |c_j - c_i - s_e d_e|^2  s.t. s_e >= 1, c_0 = 0.  For a given active set the free
     scales are eliminated analytically (s_e = d_e.(c_j - c_i) / |d_e|^2), leaving a 3(n-1) system in the
     positions: H = sum_e w_e B_e^T Q_e B_e, Q_e = I - d d^T/|d|^2 (free) or I (active, s_e = 1)."""
     nc, E = 3 * (n_views - 1), len(edges)
-    active = np.ones(E, bool)          # start from s_e = 1 everywhere (the all-free problem is scale-degenerate)
     c = np.zeros((n_views, 3))
     s = np.ones(E)
     for _ in range(2 * E + 2):
@@ -159,8 +158,11 @@ def lud_positions(n_views, pair_pos, rot, max_reweight=40, tol=1e-9):
     dirs = [angle_axis_to_R(rot[i]).T @ np.asarray(pair_pos[(i, j)], float) for (i, j) in edges]
     w = np.ones(len(edges))
     c_prev = None
+    # active set of the bounds s_e >= 1: starts from s_e = 1 everywhere (the all-free problem is
+    # scale-degenerate) and is carried over from one reweighting to the next (warm start)
+    active = np.ones(len(edges), bool)
     for _ in range(max_reweight):
-        c, s = _bounded_wls(n_views, edges, dirs, w)
+        c, s = _bounded_wls(n_views, edges, dirs, w, active)
         call = np.vstack([np.zeros(3), c])
         res = np.array([np.linalg.norm(call[j] - call[i] - s[e] * dirs[e]) for e, (i, j) in enumerate(edges)])
         w = 1.0 / np.maximum(res, 1e-6)

@@ -15,3 +15,12 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden_dir():
     return os.path.join(ROOT, 'tests', 'golden')
+
+
+@pytest.fixture(autouse=True)
+def _default_math_mode(request):
+    """Every GPU test starts from the library default (tcgen05 3xTF32) regardless of what ran before."""
+    if request.node.get_closest_marker('gpu') is not None:
+        import e2e_multi_view_matching_b200 as pkg
+        pkg.set_math_mode(3)
+    yield

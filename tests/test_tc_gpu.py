@@ -41,12 +41,9 @@ def test_matcher_tensor_core_modes(name, mode):
     meta, ref = load_case(name)
     sd, data = case_inputs(meta)
     pkg.set_math_mode(mode)
-    try:
-        got = run_ours(meta, sd, data)
-    finally:
-        pkg.set_math_mode(0)
+    got = run_ours(meta, sd, data)
     if mode == 3:
-        rep = compare_matcher_outputs(ref, got, tau=2e-3, score_tol=(1e-3, 3e-5))
+        rep = compare_matcher_outputs(ref, got, tau=2e-3, score_tol=(3e-4, 3e-5))
     else:
         rep = compare_matcher_outputs(ref, got, tau=0.15, score_tol=(0.15, 2e-2), conf_tol=5e-2)
     print(name, mode, rep)
