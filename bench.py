@@ -44,13 +44,40 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.  In-process NVML (a few microseconds
+    per query) -- an `nvidia-smi` subprocess takes ~0.5 s per sample and stalls kernel launches while it
+    holds the driver lock, which showed up as a 100 ms hiccup inside the e2e timing; it is only the
+    fallback when NVML cannot be loaded."""
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.samples = []
         self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID('GPU-' + str(torch.cuda.get_device_properties(gpu_index).uuid))
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        act = lambda bit: 'Active' if (r & bit) else 'Not Active'
+        # NVML reason bits: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+        return [str(sm), str(mx), '', act(0x8), act(0x40), act(0x20), act(0x4)]
 
     def run(self):
         q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -58,6 +85,10 @@ class ClockSampler(threading.Thread):
              'clocks_event_reasons.sw_power_cap')
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                    time.sleep(0.02)
+                    continue
                 o = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q,
                                     '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
                 f = [x.strip() for x in o.stdout.strip().split(',')]
@@ -76,7 +107,7 @@ class ClockSampler(threading.Thread):
             if any(s[i].lower().startswith('active') for s in self.samples):
                 reasons.append(name)
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
-                'samples': len(self.samples)}
+                'samples': len(self.samples), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -161,7 +192,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--tuples', type=int, default=8, help='tuples per step per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--gemm-tile', type=int, default=128, choices=[128, 256])
+    ap.add_argument('--gemm-tile', type=int, default=256, choices=[128, 256])
     ap.add_argument('--math-mode', type=int, default=3, choices=[0, 1, 3],
                     help='3 = tcgen05 3xTF32 (fp32-faithful, default), 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA cores')
     args = ap.parse_args()

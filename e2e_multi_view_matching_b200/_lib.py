@@ -110,6 +110,13 @@ def lib():
     L.mvm_multi_view_ba.restype = C.c_int
     L.mvm_multi_view_ba.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
                                     _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]
+    L.mvm_multi_view_ba_ex.restype = C.c_int
+    L.mvm_multi_view_ba_ex.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
+                                       _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,
+                                       C.c_size_t, _fp]
+    L.mvm_triangulate_pairs.restype = C.c_int
+    L.mvm_triangulate_pairs.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
+                                        _fp, _fp, _fp, _fp, _fp, _fp]
     L.mvm_launch_count.restype = C.c_ulonglong
     L.mvm_profile_enable.argtypes = [C.c_int]
     L.mvm_profile_collect.restype = C.c_int

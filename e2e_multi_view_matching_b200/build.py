@@ -25,7 +25,7 @@ def _needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith('.o') and f != 'cli']
     deps.append(os.path.join(os.path.dirname(HERE), 'include', 'mvm_b200.h'))
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -39,8 +39,30 @@ def _compile(src, verbose):
     return obj, r.stderr
 
 
+BIN = os.path.join(HERE, 'bin')
+CLI_SRC = os.path.join(CSRC, 'cli', 'ba_cli.cpp')
+CLI = {'bundle_adjuster': [], 'ba_initializer': ['-DMVM_CLI_BA_INIT']}
+
+
+def build_cli(force=False):
+    """The two CLI-compatible binaries (same names and file protocol as the reference's
+    bundle_adjustment/build/{bundle_adjuster,ba_initializer}) on top of libmvm_b200.so."""
+    os.makedirs(BIN, exist_ok=True)
+    for name, defs in CLI.items():
+        out = os.path.join(BIN, name)
+        if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(CLI_SRC), os.path.getmtime(LIB)):
+            continue
+        cmd = [NVCC, '-O2', '-std=c++17'] + defs + ['-o', out, CLI_SRC, '-L' + HERE, '-lmvm_b200',
+                                                     '-Xlinker', '-rpath', '-Xlinker', '$ORIGIN/..']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('CLI build failed for %s:\n%s\n%s' % (name, r.stdout, r.stderr))
+    return BIN
+
+
 def build(force=False, verbose=False):
     if not force and not _needs_build():
+        build_cli()
         return LIB
     srcs = _sources()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
@@ -54,6 +76,7 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    build_cli(force=True)
     return LIB
 
 

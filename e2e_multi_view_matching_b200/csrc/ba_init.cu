@@ -68,8 +68,10 @@ __global__ void __launch_bounds__(32) ba_init_kernel(BaInitArgs g) {
   __syncwarp();
   for (int p = 0; p < P; ++p) {
     int cnt = 0;
-    const unsigned char* m = g.inliers + ((long long)bi * P + p) * g.n_pad;
-    for (int i = lane; i < g.n_pad; i += 32) cnt += m[i];
+    if (g.inliers) {   // null: the caller already decided the edge set (success && on_tree)
+      const unsigned char* m = g.inliers + ((long long)bi * P + p) * g.n_pad;
+      for (int i = lane; i < g.n_pad; i += 32) cnt += m[i];
+    }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0 && g.success[bi * P + p] && (cnt >= g.min_inliers || g.on_tree[bi * P + p])) {
       const int e = s_E++;
@@ -360,7 +362,7 @@ extern "C" int mvm_ba_initialize(const int* pair_a, const int* pair_b, int n_vie
                                  const unsigned char* success, const unsigned char* on_tree,
                                  const unsigned char* inliers, int min_inliers, double* extr_out,
                                  int* n_edges_out, void* stream) {
-  MVM_REQUIRE(pair_a && pair_b && extr_tree && T_rel && success && on_tree && inliers && extr_out);
+  MVM_REQUIRE(pair_a && pair_b && extr_tree && T_rel && success && on_tree && extr_out);
   MVM_REQUIRE(n_views >= 2 && n_views <= MVM_MAX_VIEWS && n_pairs >= 1 && n_pairs <= MVM_MAX_PAIRS && batch >= 1);
   MvmProfScope prof__(MVM_TAG_MISC, (cudaStream_t)stream);
   BaInitArgs g;

@@ -306,7 +306,7 @@ const CUtensorMap* mvm_get_tmap_2d(const float* base, long long rows, long long 
   return mvm_get_tmap_3d(base, 0, rows, cols, ld, 0, box_rows);
 }
 
-int g_gemm_bn = 128;   // output tile width of the tcgen05 GEMM (128 or 256), see mvm_debug_set_gemm_tile
+int g_gemm_bn = 256;   // output tile width of the tcgen05 GEMM (128 or 256), see mvm_debug_set_gemm_tile
 extern "C" void mvm_debug_set_gemm_tile(int bn) { g_gemm_bn = bn == 256 ? 256 : 128; }
 
 // GEMM on the tensor cores.  Requirements: K, K1 multiples of 32, N multiple of 128, 16-byte aligned

@@ -19,6 +19,7 @@
 #include "../../include/mvm_b200.h"
 #include "common.cuh"
 #include "kernels.cuh"
+#include <cstring>
 #include "linalg_small.cuh"
 
 namespace {
@@ -192,7 +193,10 @@ struct MvbaArgs {
   const float* conf;                    // [B,P,n_pad]
   const int* n_valid;                   // [B,P]
   const double* extr_init;              // [B,T,16]
+  const double* pts_init;               // [B,P,n_pad,3] given initial points, or null: DLT from extr_init
+  int prenorm;                          // 1: conf already holds the normalised weights of ba_in.csv
   float* extr_out;                      // [B,T,16]
+  double* extr_out64;                   // [B,T,16] optional fp64 copy of the result
   double* pts;                          // [B,P,2,n_pad,3] current / candidate points
   double* pscale;                       // [B,P,n_pad,3] Jacobi column scale of the points
   double* xch;                          // [groups, P, NPART] exchange
@@ -434,15 +438,17 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
     }
     double csum = 0.0;
     for (int q = 0; q < P; ++q) csum += s_rec[q * NPART];
-    const double wscale = 1.0 / (0.5 * (csum + 1e-3));
+    const double wscale = g.prenorm ? 1.0 : 1.0 / (0.5 * (csum + 1e-3));
 
     // ---- initial points: DLT with the initial extrinsics ----
     {
       const double* Ea = g.extr_init + ((long long)bi * T + va) * 16;
       const double* Eb = g.extr_init + ((long long)bi * T + vb) * 16;
+      const double* pin = g.pts_init ? g.pts_init + prob * g.n_pad * 3 : nullptr;
       for (int i = tid; i < n; i += NT) {
         double X[3];
-        triangulate_general(Ea, Eb, xa[2 * i], xa[2 * i + 1], xb[2 * i], xb[2 * i + 1], X);
+        if (pin) { X[0] = pin[3 * i]; X[1] = pin[3 * i + 1]; X[2] = pin[3 * i + 2]; }
+        else triangulate_general(Ea, Eb, xa[2 * i], xa[2 * i + 1], xb[2 * i], xb[2 * i + 1], X);
         pcur[3 * i] = X[0]; pcur[3 * i + 1] = X[1]; pcur[3 * i + 2] = X[2];
       }
     }
@@ -772,6 +778,14 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         E[i * 4 + 3] = (float)s_cam[tid][3 + i];
       }
       E[12] = 0.f; E[13] = 0.f; E[14] = 0.f; E[15] = 1.f;
+      if (g.extr_out64) {
+        double* D = g.extr_out64 + ((long long)bi * T + tid) * 16;
+        for (int i = 0; i < 3; ++i) {
+          for (int j = 0; j < 3; ++j) D[i * 4 + j] = R[i * 3 + j];
+          D[i * 4 + 3] = s_cam[tid][3 + i];
+        }
+        D[12] = 0.0; D[13] = 0.0; D[14] = 0.0; D[15] = 1.0;
+      }
       if (tid == 0) {
         if (g.iters_out) g.iters_out[bi] = it;
         if (g.cost_out) g.cost_out[bi * 2 + 1] = s_ctl[2];
@@ -779,6 +793,25 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
     }
     bar += P;
     group_barrier(ctr, bar);
+  }
+}
+
+// cv2.triangulatePoints of every match of every (tuple, pair) with given extrinsics
+// (write_bundle_adjust_problem, bundle_adjust_io.py:219-225)
+__global__ void __launch_bounds__(NT) triangulate_pairs_kernel(MvbaArgs g, double* __restrict__ out) {
+  const int P = g.n_pairs, T = g.n_views;
+  const long long prob = blockIdx.x;
+  const int bi = (int)(prob / P), p = (int)(prob % P);
+  const int n = g.n_valid[prob];
+  const double* Ea = g.extr_init + ((long long)bi * T + g.a[p]) * 16;
+  const double* Eb = g.extr_init + ((long long)bi * T + g.b[p]) * 16;
+  const float* xa = g.xa + prob * g.n_pad * 2;
+  const float* xb = g.xb + prob * g.n_pad * 2;
+  double* o = out + prob * g.n_pad * 3;
+  for (int i = threadIdx.x; i < g.n_pad; i += NT) {
+    double X[3] = {0.0, 0.0, 0.0};
+    if (i < n) triangulate_general(Ea, Eb, xa[2 * i], xa[2 * i + 1], xb[2 * i], xb[2 * i + 1], X);
+    o[3 * i] = X[0]; o[3 * i + 1] = X[1]; o[3 * i + 2] = X[2];
   }
 }
 
@@ -828,11 +861,12 @@ size_t mvm_mvba_workspace_bytes(int n_views, int n_pairs, int batch, int n_pad) 
   return pts + psc + xch + 1024;
 }
 
-int mvm_multi_view_ba(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch,
-                      int n_pad, const float* xn_a, const float* xn_b, const float* conf,
-                      const int* n_valid, const double* extr_init, float* extr_out, int max_iterations,
-                      int* iterations_out, double* cost_out, void* workspace, size_t workspace_bytes,
-                      void* stream_) {
+int mvm_multi_view_ba_ex(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch,
+                         int n_pad, const float* xn_a, const float* xn_b, const float* conf,
+                         const int* n_valid, const double* extr_init, const double* points_init,
+                         int weights_prenormalized, float* extr_out, double* extr_out_f64, int max_iterations,
+                         int* iterations_out, double* cost_out, void* workspace, size_t workspace_bytes,
+                         void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MVM_REQUIRE(pair_a && pair_b && xn_a && xn_b && conf && n_valid && extr_init && extr_out && workspace);
   MVM_REQUIRE(n_views >= 2 && n_views <= MVM_MAX_VIEWS && n_pairs >= 1 && n_pairs <= MVM_MAX_PAIRS);
@@ -852,6 +886,7 @@ int mvm_multi_view_ba(const int* pair_a, const int* pair_b, int n_views, int n_p
   if (groups > batch) groups = batch;
   g.n_groups = groups;
   g.xa = xn_a; g.xb = xn_b; g.conf = conf; g.n_valid = n_valid; g.extr_init = extr_init;
+  g.pts_init = points_init; g.prenorm = weights_prenormalized ? 1 : 0; g.extr_out64 = extr_out_f64;
   g.extr_out = extr_out; g.max_iter = max_iterations; g.iters_out = iterations_out; g.cost_out = cost_out;
   char* w = (char*)workspace;
   g.ctrs = (unsigned*)w; w += 1024;
@@ -860,6 +895,33 @@ int mvm_multi_view_ba(const int* pair_a, const int* pair_b, int n_views, int n_p
   g.xch = (double*)w;
   cudaMemsetAsync(g.ctrs, 0, 1024, stream);
   mvba_kernel<<<groups * n_pairs, NT, (size_t)n_pairs * NPART * sizeof(double), stream>>>(g);
+  MVM_CHECK_LAUNCH();
+  return MVM_OK;
+}
+
+int mvm_multi_view_ba(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch,
+                      int n_pad, const float* xn_a, const float* xn_b, const float* conf,
+                      const int* n_valid, const double* extr_init, float* extr_out, int max_iterations,
+                      int* iterations_out, double* cost_out, void* workspace, size_t workspace_bytes,
+                      void* stream_) {
+  return mvm_multi_view_ba_ex(pair_a, pair_b, n_views, n_pairs, batch, n_pad, xn_a, xn_b, conf, n_valid, extr_init,
+                              nullptr, 0, extr_out, nullptr, max_iterations, iterations_out, cost_out, workspace,
+                              workspace_bytes, stream_);
+}
+
+int mvm_triangulate_pairs(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch, int n_pad,
+                          const float* xn_a, const float* xn_b, const int* n_valid, const double* extr,
+                          double* points_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MVM_REQUIRE(pair_a && pair_b && xn_a && xn_b && n_valid && extr && points_out);
+  MVM_REQUIRE(n_views >= 2 && n_views <= MVM_MAX_VIEWS && n_pairs >= 1 && n_pairs <= MVM_MAX_PAIRS && batch >= 1);
+  MvmProfScope prof__(MVM_TAG_MISC, stream);
+  MvbaArgs g;
+  memset(&g, 0, sizeof(g));
+  g.n_views = n_views; g.n_pairs = n_pairs; g.batch = batch; g.n_pad = n_pad;
+  for (int p = 0; p < n_pairs; ++p) { g.a[p] = pair_a[p]; g.b[p] = pair_b[p]; MVM_REQUIRE(pair_a[p] < pair_b[p]); }
+  g.xa = xn_a; g.xb = xn_b; g.n_valid = n_valid; g.extr_init = extr;
+  triangulate_pairs_kernel<<<batch * n_pairs, NT, 0, stream>>>(g, points_out);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }

@@ -203,7 +203,8 @@ int mvm_spanning_tree_init(const int* pair_a, const int* pair_b, int n_views, in
  * from the spanning-tree rotations, then LeastUnsquaredDeviationPositionEstimator; restated in
  * oracle/ba_init.py).  Edges = successful pairs with >= min_inliers inliers or on the spanning tree
  * (bundle_adjust_io.py:181-190; the reference uses min_inliers = 20).  extr_tree / extr_out [B,T,16]
- * doubles (world->cam), inliers [B,P,n_pad] bytes, n_edges_out [B] (may be NULL). */
+ * doubles (world->cam), inliers [B,P,n_pad] bytes (NULL: edges = success && on_tree, for callers that
+ * already hold the edge list, e.g. `ba_init_in.csv`), n_edges_out [B] (may be NULL). */
 int mvm_ba_initialize(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch, int n_pad,
                       const double* extr_tree, const float* T_rel, const unsigned char* success,
                       const unsigned char* on_tree, const unsigned char* inliers, int min_inliers,
@@ -220,6 +221,25 @@ int mvm_multi_view_ba(const int* pair_a, const int* pair_b, int n_views, int n_p
                       const int* n_valid, const double* extr_init, float* extr_out,
                       int max_iterations, int* iterations_out, double* cost_out, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* Same solver for a problem stated the way `ba_in.csv` states it (ba_problem.cpp:8-95, written by
+ * write_bundle_adjust_problem, bundle_adjust_io.py:193-259): points_init [B,P,n_pad,3] doubles are the given
+ * 3-D points (NULL = triangulate as above); weights_prenormalized != 0: conf already holds the per-observation
+ * weights of the file (no re-normalisation); extr_out_f64 [B,T,16] (may be NULL) receives the result in fp64
+ * (`ba_out.csv` is written with 12 significant digits, ba_problem.cpp:97-113). */
+int mvm_multi_view_ba_ex(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch,
+                         int n_pad, const float* xn_a, const float* xn_b, const float* conf,
+                         const int* n_valid, const double* extr_init, const double* points_init,
+                         int weights_prenormalized, float* extr_out, double* extr_out_f64, int max_iterations,
+                         int* iterations_out, double* cost_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* Two-view DLT of every match of every (tuple, pair) with the given world->cam extrinsics
+ * (cv2.triangulatePoints in write_bundle_adjust_problem, bundle_adjust_io.py:219-225).
+ * points_out [B,P,n_pad,3] doubles (zero beyond n_valid). */
+int mvm_triangulate_pairs(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch, int n_pad,
+                          const float* xn_a, const float* xn_b, const int* n_valid, const double* extr,
+                          double* points_out, void* stream);
 
 /* ---- instrumentation ----------------------------------------------------------------- */
 /* Kernels launched by the library since load (bench.py's gpu_launches). */

@@ -43,7 +43,9 @@ def test_matcher_tensor_core_modes(name, mode):
     pkg.set_math_mode(mode)
     got = run_ours(meta, sd, data)
     if mode == 3:
-        rep = compare_matcher_outputs(ref, got, tau=2e-3, score_tol=(3e-4, 3e-5))
+        # 'sharp' cases scale the raw scores by gain^2 = 256: the ~1e-5 relative 3xTF32 error of the raw
+        # score shows up as an absolute error of the (O(1)) log-coupling entries
+        rep = compare_matcher_outputs(ref, got, tau=2e-3, score_tol=(1e-3 if 'sharp' in name else 3e-4, 3e-5))
     else:
         rep = compare_matcher_outputs(ref, got, tau=0.15, score_tol=(0.15, 2e-2), conf_tol=5e-2)
     print(name, mode, rep)
@@ -65,3 +67,27 @@ def test_attention_tc_vs_simt(cfg, passes):
             n = counts[v % T]
             err = (ref[v, :n] - got[v, :n]).abs().max().item()
             assert err < tol, (cfg, passes, is_cross, v, err)
+
+
+def test_gemm_tile_variants_bit_identical():
+    """The 128- and 256-column output tiles of the tcgen05 GEMM accumulate over K in the same order with
+    the same three passes, so the whole matcher must produce bit-identical outputs with either."""
+    import e2e_multi_view_matching_b200 as pkg
+    from e2e_multi_view_matching_b200 import _lib
+    from tests.test_matcher_gpu import run_ours
+    from tests.util import load_case, case_inputs
+    meta, ref = load_case('mv4_ragged_sharp')
+    sd, data = case_inputs(meta)
+    outs = []
+    try:
+        for tile in (128, 256):
+            _lib.lib().mvm_debug_set_gemm_tile(tile)
+            for mode in (3, 1):
+                pkg.set_math_mode(mode)
+                outs.append(run_ours(meta, sd, data))
+    finally:
+        _lib.lib().mvm_debug_set_gemm_tile(256)
+    for mode_i in (0, 1):
+        a, b = outs[mode_i], outs[2 + mode_i]
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (k, mode_i)
