@@ -193,6 +193,8 @@ def main():
     ap.add_argument('--tuples', type=int, default=8, help='tuples per step per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-tile', type=int, default=256, choices=[128, 256])
+    ap.add_argument('--gemm-kernel', default='persistent', choices=['persistent', 'tile'],
+                    help='3xTF32 GEMM kernel: persistent (default) or the one-tile-per-CTA kernel (A/B comparison)')
     ap.add_argument('--math-mode', type=int, default=3, choices=[0, 1, 3],
                     help='3 = tcgen05 3xTF32 (fp32-faithful, default), 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA cores')
     args = ap.parse_args()
@@ -218,6 +220,7 @@ def main():
     lib = _lib.lib()
     lib.mvm_set_math_mode(args.math_mode)
     lib.mvm_debug_set_gemm_tile(args.gemm_tile)
+    lib.mvm_debug_set_gemm_kernel(1 if args.gemm_kernel == 'persistent' else 0)
     B = args.tuples
 
     sd = make_state_dict(len(LAYERS), seed=0, final_proj_gain=GAIN)

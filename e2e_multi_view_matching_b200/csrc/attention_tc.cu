@@ -55,6 +55,17 @@ struct AttnTcArgs {
 
 using tc::tf32_rn;
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// rn_tf32 of a finite value with two integer instructions (round to nearest, ties away -- what cvt.rna does,
+// which the compiler expands to four instructions with the Inf/NaN guard)
+__device__ __forceinline__ float tf32_hi(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 // element-wise hi (in place) / lo split of a landed tile (layout agnostic)
 __device__ __forceinline__ void split_tile(uint8_t* hi_base, uint8_t* lo_base, int bytes, int t, int nthr) {
   float4* h = reinterpret_cast<float4*>(hi_base);
@@ -87,8 +98,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   uint64_t* v_split = bars + 16;   // [ST]
   uint64_t* s_full = bars + 19;    // [2]  S(j) landed in TMEM
   uint64_t* p_ready = bars + 21;   // [2]  P(j) stored over S(j) (128 arrivals)
-  uint64_t* o_full = bars + 23;
-  uint64_t* o_empty = bars + 24;
+  uint64_t* o_full = bars + 23;    // [2]  P.V(j) landed in the TMEM accumulator (alternating, see the softmax warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -126,7 +136,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1); tc::mbar_init(v_split + i, 128);
     }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(p_ready + i, 128); }
-    tc::mbar_init(o_full, 1); tc::mbar_init(o_empty, 128);
+    tc::mbar_init(o_full, 1); tc::mbar_init(o_full + 1, 1);
     tc::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -211,7 +221,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         const int s = j % ST, sb = j & 1;
         tc::mbar_wait(p_ready + sb, (j >> 1) & 1);
         tc::mbar_wait(v_full + s, (j / ST) & 1);
-        tc::mbar_wait(o_empty, (j & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
         const uint32_t p_hi = tmem_S0 + sb * 64, p_lo = tmem_Plo0 + sb * 64;
@@ -219,13 +228,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         for (int kk = 0; kk < BKV / 8; ++kk) {
           const uint32_t offv = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
           const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + offv);
-          tc::umma_tf32_ts(tmem_O, p_hi + kk * 8, dv, idesc, kk != 0);        // A = P from tensor memory
+          tc::umma_tf32_ts(tmem_O, p_hi + kk * 8, dv, idesc, (j | kk) != 0);  // A = P from tensor memory; O accumulates over tiles
           if (NPASS == 3) {
             tc::umma_tf32_ts(tmem_O, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + offv), idesc, 1);
             tc::umma_tf32_ts(tmem_O, p_lo + kk * 8, dv, idesc, 1);
           }
         }
-        tc::umma_commit(o_full);
+        tc::umma_commit(o_full + (j & 1));
         tc::umma_commit(v_empty + s);
       }
     }
@@ -263,85 +272,101 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc::tc_fence_before();
       tc::mbar_arrive(q_ready);
     }
-    float acc[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    // Online softmax with the output accumulator RESIDENT IN TENSOR MEMORY: O += P(j) V(j) accumulates over all
+    // key tiles; the running reference m_ref of a row is only raised (and O, l rescaled) when the row maximum
+    // outgrows it by more than 2^8 -- softmax is invariant to the reference, P stays <= 2^8, and the common tile
+    // costs no TMEM read of O at all.  All quantities are in log2 units (scores * log2(e) / sqrt(d)).
+    float m_ref = -INFINITY, l_run = 0.f;
     const float scale_l2e = 0.125f * 1.4426950408889634f;
-
-    auto fold_O = [&](int jprev) {
-      tc::mbar_wait(o_full, jprev & 1);
-      tc::tc_fence_after();
-      float o[32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tc::tmem_ld32(tmem_O + lane_addr + c * 32, o);
+    int j = 0;
+    for (int sg = 0; sg < T; ++sg) {
+      if (g.is_cross ? (sg == t) : (sg != t)) continue;
+      const int cnt = g.segs.counts[sg];
+      for (int k0 = 0; k0 < cnt; k0 += BKV, ++j) {
+        const int sb = j & 1;
+        const int nvalid = cnt - k0;      // keys of this tile that exist
+        tc::mbar_wait(s_full + sb, (j >> 1) & 1);
+        tc::tc_fence_after();
+        float s[BKV];
+        tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr, s);
+        tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr + 32, s + 32);
         tc::tmem_ld_wait();
+        if (nvalid < BKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[c * 32 + i] += o[i];
-      }
-      tc::tc_fence_before();
-      tc::mbar_arrive(o_empty);
-    };
-
-    for (int j = 0; j < nt; ++j) {
-      int seg, k0, cnt;
-      tile_info(j, seg, k0, cnt);
-      const int sb = j & 1;
-      tc::mbar_wait(s_full + sb, (j >> 1) & 1);
-      tc::tc_fence_after();
-      float s[BKV];
-      tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr, s);
-      tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr + 32, s + 32);
-      tc::tmem_ld_wait();
-      float mx = -INFINITY;
-      const int nvalid = cnt - k0;      // keys of this tile that exist
+          for (int i = 0; i < BKV; ++i) s[i] = (i < nvalid) ? s[i] : -INFINITY;
+        }
+        float mx = s[0];
 #pragma unroll
-      for (int i = 0; i < BKV; ++i) {
-        s[i] = (i < nvalid) ? s[i] * scale_l2e : -INFINITY;
-        mx = fmaxf(mx, s[i]);
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = exp2f(m_run - m_new);
-      float rs = 0.f;
+        for (int i = 1; i < BKV; ++i) mx = fmaxf(mx, s[i]);
+        mx *= scale_l2e;
+        const bool grow = mx > m_ref + 8.f;
+        if (__any_sync(0xffffffffu, grow)) {
+          float f = 1.f;
+          if (grow) { f = ex2_ftz(m_ref - mx); m_ref = mx; l_run *= f; }
+          if (j > 0) {
+            // every P.V issued so far must have landed before O is touched.  P.V(j) commits to o_full[j & 1]:
+            // a parity wait is only sound while the barrier is at most one phase ahead of the waiter, and
+            // barrier (j-1)&1 cannot run further ahead than P.V(j-1) (P.V(j+1) needs this warp's P(j+1))
+            tc::mbar_wait(o_full + ((j - 1) & 1), ((j - 1) >> 1) & 1);
+            tc::tc_fence_after();
+            float o[32];
 #pragma unroll
-      for (int i = 0; i < BKV; ++i) {
-        s[i] = exp2f(s[i] - m_new);
-        rs += s[i];
-      }
-      l_run = l_run * corr + rs;
-      m_run = m_new;
-      // P(j) overwrites S(j) in tensor memory (row r = lane r, keys along columns): A operand of P.V
-      if (NPASS == 3) {
-        float lo[32];
+            for (int c = 0; c < 2; ++c) {
+              tc::tmem_ld32(tmem_O + lane_addr + c * 32, o);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] *= f;
+              tc::tmem_st32(tmem_O + lane_addr + c * 32, o);
+            }
+            tc::tmem_st_wait();
+          }
+        }
+        const float nm = -m_ref;
+        float rs = 0.f;
+        // P(j) overwrites S(j) in tensor memory (row r = lane r, keys along columns): A operand of P.V
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+          float lo[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float hi = tf32_rn(s[c * 32 + i]);
-            lo[i] = tf32_rn(s[c * 32 + i] - hi);
-            s[c * 32 + i] = hi;
+            const float pv = ex2_ftz(fmaf(s[c * 32 + i], scale_l2e, nm));
+            rs += pv;
+            if (NPASS == 3) {
+              const float hi = tf32_hi(pv);
+              lo[i] = pv - hi;          // the tensor core reads the top 19 bits: truncation of lo costs 2^-21 |p|
+              s[c * 32 + i] = hi;
+            } else {
+              s[c * 32 + i] = pv;
+            }
           }
-          tc::tmem_st32(tmem_Plo0 + sb * 64 + lane_addr + c * 32, lo);
+          if (NPASS == 3) tc::tmem_st32(tmem_Plo0 + sb * 64 + lane_addr + c * 32, lo);
+          tc::tmem_st32(tmem_S0 + sb * 64 + lane_addr + c * 32, s + c * 32);
         }
+        l_run += rs;
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(p_ready + sb);
       }
-      tc::tmem_st32(tmem_S0 + sb * 64 + lane_addr, s);
-      tc::tmem_st32(tmem_S0 + sb * 64 + lane_addr + 32, s + 32);
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(p_ready + sb);
-      // fold the previous tile's P.V while the tensor core works on this one, then rescale
-      if (j > 0) fold_O(j - 1);
-#pragma unroll
-      for (int i = 0; i < HD; ++i) acc[i] *= corr;
     }
-    fold_O(nt - 1);
+    // epilogue: O / l once the last product (and, the tensor pipe being in order, every earlier one) has landed
+    tc::mbar_wait(o_full + ((j - 1) & 1), ((j - 1) >> 1) & 1);
+    tc::tc_fence_after();
     if (q0 + row < g.n_pad) {
       const float inv = 1.f / l_run;
       float4* o4 = reinterpret_cast<float4*>(g.out + ((long long)v * g.n_pad + q0 + row) * 256 + h * HD);
 #pragma unroll
-      for (int i = 0; i < HD / 4; ++i)
-        o4[i] = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+      for (int c = 0; c < 2; ++c) {
+        float o[32];
+        tc::tmem_ld32(tmem_O + lane_addr + c * 32, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o4[c * 8 + i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+      }
+    } else {
+      float o[32];                      // the loads are warp-collective: every lane takes part
+#pragma unroll
+      for (int c = 0; c < 2; ++c) { tc::tmem_ld32(tmem_O + lane_addr + c * 32, o); tc::tmem_ld_wait(); }
     }
   }
   tc::tc_fence_before();

@@ -306,8 +306,10 @@ const CUtensorMap* mvm_get_tmap_2d(const float* base, long long rows, long long 
   return mvm_get_tmap_3d(base, 0, rows, cols, ld, 0, box_rows);
 }
 
-int g_gemm_bn = 256;   // output tile width of the tcgen05 GEMM (128 or 256), see mvm_debug_set_gemm_tile
+int g_gemm_bn = 256;   // output tile width of the one-tile-per-CTA tcgen05 GEMM (128 or 256), see mvm_debug_set_gemm_tile
 extern "C" void mvm_debug_set_gemm_tile(int bn) { g_gemm_bn = bn == 256 ? 256 : 128; }
+int g_gemm_persist = 1;   // 1: the persistent kernel of gemm_tc_persist.cu serves the 3xTF32 path (default)
+extern "C" void mvm_debug_set_gemm_kernel(int persistent) { g_gemm_persist = persistent ? 1 : 0; }
 
 // GEMM on the tensor cores.  Requirements: K, K1 multiples of 32, N multiple of 128, 16-byte aligned
 // rows (lda/ldw/ldc/ldr multiples of 4).  n_pass: 3 = fp32-faithful 3xTF32, 1 = single-pass TF32.
@@ -317,6 +319,7 @@ int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_
   MVM_REQUIRE(d.lda % 4 == 0 && d.ldw % 4 == 0 && d.ldc % 4 == 0 && (d.R == nullptr || d.ldr % 4 == 0));
   MVM_REQUIRE(d.A2 == nullptr || d.lda2 % 4 == 0);
   MvmProfScope prof__(MVM_TAG_GEMM, stream);
+  if (g_gemm_persist && n_pass == 3 && d.Whi && d.Wlo) return launch_gemm_tc_persist(d, VT, vt_col0, n_pad, KLO, VTLO, stream);
   if (g_gemm_bn == 256 && d.N % 256 == 0) {
     if (n_pass == 3 && d.Whi && d.Wlo) return launch_cfg<256, 3, true>(d, VT, vt_col0, n_pad, KLO, VTLO, stream);
     if (n_pass == 1) return launch_cfg<256, 1, false>(d, VT, vt_col0, n_pad, nullptr, nullptr, stream);

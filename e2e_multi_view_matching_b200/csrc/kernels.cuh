@@ -31,6 +31,9 @@ int launch_transpose_cn(const float* in, float* out, int n_views_total, int C, i
 // tcgen05 GEMM (gemm_tc.cu): n_pass 3 = fp32-faithful 3xTF32, 1 = single-pass TF32
 int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_pad, cudaStream_t stream,
                    float* KLO = nullptr, float* VTLO = nullptr);
+// persistent 3xTF32 kernel (A operand in tensor memory, double-buffered accumulators, TMA-store epilogue)
+int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO,
+                           cudaStream_t stream);
 
 struct AttnSegs {
   int n_views;

@@ -228,6 +228,17 @@ int mvm_linear_tc(const float* A, int lda, const float* A2, int lda2, int K1, co
   return launch_gemm_tc(g, n_pass, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
+int mvm_linear_tc_presplit(const float* A, int lda, const float* A2, int lda2, int K1, const float* W_hi,
+                           const float* W_lo, int ldw, const float* bias, const float* R, int ldr, float* C, int ldc,
+                           int M, int N, int K, float alpha, int relu, void* stream) {
+  MVM_REQUIRE(A && W_hi && W_lo && C);
+  GemmDesc g = make_gemm(A, lda, W_hi, K, bias, C, ldc, M, N, relu);
+  g.ldw = ldw; g.alpha = alpha; g.Whi = W_hi; g.Wlo = W_lo;
+  if (A2) { g.A2 = A2; g.lda2 = lda2; g.K1 = K1; }
+  if (R) { g.R = R; g.ldr = ldr; }
+  return launch_gemm_tc(g, 3, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
 int mvm_attention(const float* qkv, float* out, int batch, int n_views, int n_pad,
                   const int* counts, int is_cross, void* stream) {
   MVM_REQUIRE(qkv && out && counts && n_views >= 1 && n_views <= 8);

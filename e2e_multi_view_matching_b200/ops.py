@@ -7,15 +7,32 @@ import torch
 from . import _lib
 
 
-def linear(a, w, bias=None, a2=None, residual=None, relu=False, alpha=1.0, tc_passes=0):
+def rn_tf32(x):
+    """cvt.rna.tf32.f32 on a tensor: round to nearest (ties away) on the 13 dropped mantissa bits."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def linear(a, w, bias=None, a2=None, residual=None, relu=False, alpha=1.0, tc_passes=0, presplit=False):
     """act(alpha * [a|a2] @ w.T + bias) + residual on point-major activations (Conv1d k=1).
-    tc_passes: 0 = fp32 CUDA cores, 3 = tcgen05 3xTF32, 1 = tcgen05 single-pass TF32."""
+    tc_passes: 0 = fp32 CUDA cores, 3 = tcgen05 3xTF32, 1 = tcgen05 single-pass TF32.
+    presplit (with tc_passes=3): hand W over as its tf32 hi/lo planes, like the packed matcher weights do --
+    this is the production path (persistent kernel)."""
     lib = _lib.lib()
     if tc_passes:
         M, K1 = a.shape
         K = K1 + (a2.shape[1] if a2 is not None else 0)
         N = w.shape[0]
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        if presplit:
+            assert tc_passes == 3
+            w_hi = rn_tf32(w)
+            w_lo = rn_tf32(w - w_hi)
+            rc = lib.mvm_linear_tc_presplit(_lib.ptr(a), a.stride(0), _lib.ptr(a2), a2.stride(0) if a2 is not None else 0,
+                                            K1, _lib.ptr(w_hi), _lib.ptr(w_lo), w_hi.stride(0), _lib.ptr(bias),
+                                            _lib.ptr(residual), residual.stride(0) if residual is not None else 0,
+                                            _lib.ptr(out), N, M, N, K, float(alpha), int(relu), _lib.stream_ptr())
+            _lib.check(rc, 'mvm_linear_tc_presplit')
+            return out
         rc = lib.mvm_linear_tc(_lib.ptr(a), a.stride(0), _lib.ptr(a2), a2.stride(0) if a2 is not None else 0,
                                K1, _lib.ptr(w), w.stride(0), _lib.ptr(bias), _lib.ptr(residual),
                                residual.stride(0) if residual is not None else 0, _lib.ptr(out), N, M, N, K,

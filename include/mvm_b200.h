@@ -111,6 +111,13 @@ int mvm_linear_tc(const float* A, int lda, const float* A2, int lda2, int K1, co
                   int ldw, const float* bias, const float* R, int ldr, float* C, int ldc, int M,
                   int N, int K, float alpha, int relu, int n_pass, void* stream);
 
+/* The production 3xTF32 path: W given as its two tf32 planes W_hi = rn_tf32(W), W_lo = rn_tf32(W - W_hi)
+ * (what packing.py stores next to the raw weights).  Persistent kernel: A split on chip into tensor memory,
+ * two TMEM accumulators, TMA-store epilogue.  Same shape requirements as mvm_linear_tc. */
+int mvm_linear_tc_presplit(const float* A, int lda, const float* A2, int lda2, int K1, const float* W_hi,
+                           const float* W_lo, int ldw, const float* bias, const float* R, int ldr, float* C,
+                           int ldc, int M, int N, int K, float alpha, int relu, void* stream);
+
 /* Math mode of the matcher's GEMMs/attention inside mvm_matcher_forward: 0 = fp32 CUDA cores,
  * 3 = tcgen05 3xTF32 (fp32-faithful), 1 = tcgen05 single-pass TF32 (torch 1.10's Ampere default). */
 int mvm_set_math_mode(int mode);

@@ -40,7 +40,7 @@ def _parse_ba_in(path):
             R = np.array(v[:9]).reshape(3, 3).T
             cams.append(np.concatenate([M.R_to_angle_axis(R), v[9:]]))
     assert hdr is not None and int(hdr[0]) == len(cams) and int(hdr[2]) == len(pts) and int(hdr[3]) == len(oc)
-    return M.Problem(cams, pts, oc, op, oxy, ow, fixed_cam=int(hdr[1]), intr=tuple(hdr[4:]))
+    return M.BaProblem(cams, pts, oc, op, oxy, ow, fixed_cam=int(hdr[1]), intr=tuple(hdr[4:]))
 
 
 def _parse_ba_init_in(path):
