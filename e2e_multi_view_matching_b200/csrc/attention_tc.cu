@@ -153,12 +153,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
-      auto load_K = [&](int j) {
-        int seg, k0, cnt;
-        tile_info(j, seg, k0, cnt);
-        const int s = j % ST;
-        tc::mbar_wait(k_empty + s, ((j / ST) & 1) ^ 1);
+    auto load_K = [&](int j) {
+      int seg, k0, cnt;
+      tile_info(j, seg, k0, cnt);
+      const int s = j % ST;
+      tc::mbar_wait(k_empty + s, ((j / ST) & 1) ^ 1);
+      if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(k_full + s, K_BYTES * C_::PL);
         const int krow = (b * T + seg) * g.n_pad + k0;
         tc::tma_load_2d(sK(s), &tmK, k_full + s, 256 + h * HD, krow);
@@ -167,12 +167,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           tc::tma_load_2d(sK(s) + K_BYTES, &tmKlo, k_full + s, h * HD, krow);
           tc::tma_load_2d(sK(s) + K_BYTES + KV_SUB_BYTES, &tmKlo, k_full + s, h * HD + SUB, krow);
         }
-      };
-      auto load_V = [&](int j) {
-        int seg, k0, cnt;
-        tile_info(j, seg, k0, cnt);
-        const int s = j % ST;
-        tc::mbar_wait(v_empty + s, ((j / ST) & 1) ^ 1);
+      }
+      __syncwarp();
+    };
+    auto load_V = [&](int j) {
+      int seg, k0, cnt;
+      tile_info(j, seg, k0, cnt);
+      const int s = j % ST;
+      tc::mbar_wait(v_empty + s, ((j / ST) & 1) ^ 1);
+      if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(v_full + s, V_BYTES * C_::PL);
         const int vrow = (b * T + seg) * 256 + h * HD;
         tc::tma_load_2d(sV(s), &tmV, v_full + s, k0, vrow);
@@ -181,27 +184,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, k0, vrow);
           tc::tma_load_2d(sV(s) + V_BYTES + KV_SUB_BYTES, &tmVlo, v_full + s, k0 + SUB, vrow);
         }
-      };
-      load_K(0);
-      for (int j = 0; j < nt; ++j) {
-        load_V(j);
-        if (j + 1 < nt) load_K(j + 1);
       }
+      __syncwarp();
+    };
+    load_K(0);
+    for (int j = 0; j < nt; ++j) {
+      load_V(j);
+      if (j + 1 < nt) load_K(j + 1);
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     // The tensor pipe executes in issue order, so S(j+1) may overwrite the buffer that held P(j-1)
-    // without an explicit wait: P(j-1).V was issued earlier.
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_tf32(BQ, BKV);   // M=128, N=64 for both products
-      tc::mbar_wait(q_ready, 0);
+    // without an explicit wait: P(j-1).V was issued earlier.  The whole warp walks the loop (converged) and
+    // one elected lane issues: under `if (lane == 0)` every UTCHMMA gets an elect/branch waterfall loop.
+    constexpr uint32_t idesc = tc::make_idesc_tf32(BQ, BKV);   // M=128, N=64 for both products
+    tc::mbar_wait(q_ready, 0);
+    tc::tc_fence_after();
+    auto issue_S = [&](int j) {
+      const int s = j % ST, sb = j & 1;
+      tc::mbar_wait(k_full + s, (j / ST) & 1);
       tc::tc_fence_after();
-      auto issue_S = [&](int j) {
-        const int s = j % ST, sb = j & 1;
-        tc::mbar_wait(k_full + s, (j / ST) & 1);
-        tc::tc_fence_after();
-        const uint32_t k_hi = tc::smem_u32(sK(s)), k_lo = k_hi + K_BYTES;
-        const uint32_t d = tmem_S0 + sb * 64;
+      const uint32_t k_hi = tc::smem_u32(sK(s)), k_lo = k_hi + K_BYTES;
+      const uint32_t d = tmem_S0 + sb * 64;
+      if (tc::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < HD / 8; ++kk) {
           const uint32_t offk = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
@@ -214,16 +219,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         }
         tc::umma_commit(s_full + sb);
         tc::umma_commit(k_empty + s);
-      };
-      issue_S(0);
-      for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) issue_S(j + 1);
-        const int s = j % ST, sb = j & 1;
-        tc::mbar_wait(p_ready + sb, (j >> 1) & 1);
-        tc::mbar_wait(v_full + s, (j / ST) & 1);
-        tc::tc_fence_after();
-        const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
-        const uint32_t p_hi = tmem_S0 + sb * 64, p_lo = tmem_Plo0 + sb * 64;
+      }
+      __syncwarp();
+    };
+    issue_S(0);
+    for (int j = 0; j < nt; ++j) {
+      if (j + 1 < nt) issue_S(j + 1);
+      const int s = j % ST, sb = j & 1;
+      tc::mbar_wait(p_ready + sb, (j >> 1) & 1);
+      tc::mbar_wait(v_full + s, (j / ST) & 1);
+      tc::tc_fence_after();
+      const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
+      const uint32_t p_hi = tmem_S0 + sb * 64, p_lo = tmem_Plo0 + sb * 64;
+      if (tc::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BKV / 8; ++kk) {
           const uint32_t offv = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
@@ -237,6 +245,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         tc::umma_commit(o_full + (j & 1));
         tc::umma_commit(v_empty + s);
       }
+      __syncwarp();
     }
   } else if (warp < 6) {
     // =========================== softmax / accumulate ===========================

@@ -93,11 +93,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      for (int kt = 0; kt < nk; ++kt) {
-        const int s = kt % C_::STAGES;
-        const uint32_t ph = (kt / C_::STAGES) & 1;
-        tc::mbar_wait(empty + s, ph ^ 1);
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % C_::STAGES;
+      const uint32_t ph = (kt / C_::STAGES) & 1;
+      tc::mbar_wait(empty + s, ph ^ 1);
+      if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(full + s, C_::A_BYTES + C_::W_BYTES * (PRE ? 2 : 1));
         const int k = kt * BK;
         if (k < g.K1) tc::tma_load_2d(stage_A(s), &tmA, full + s, k, m0);
@@ -105,19 +105,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::tma_load_2d(stage_W(s), &tmW, full + s, k, n0);            // PRE: the rn_tf32 plane of W
         if (PRE) tc::tma_load_2d(stage_Wlo(s), &tmWlo, full + s, k, n0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN);
-      for (int kt = 0; kt < nk; ++kt) {
-        const int s = kt % C_::STAGES;
-        const uint32_t ph = (kt / C_::STAGES) & 1;
-        tc::mbar_wait(full + s, ph);
-        if (NPASS == 3) tc::mbar_wait(split + s, ph);
-        tc::tc_fence_after();
-        const uint32_t a = tc::smem_u32(stage_A(s)), w = tc::smem_u32(stage_W(s));
-        const uint32_t alo = tc::smem_u32(stage_Alo(s)), wlo = tc::smem_u32(stage_Wlo(s));
+    // converged warp, one elected lane issues (see tc::elect_one)
+    constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN);
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % C_::STAGES;
+      const uint32_t ph = (kt / C_::STAGES) & 1;
+      tc::mbar_wait(full + s, ph);
+      if (NPASS == 3) tc::mbar_wait(split + s, ph);
+      tc::tc_fence_after();
+      const uint32_t a = tc::smem_u32(stage_A(s)), w = tc::smem_u32(stage_W(s));
+      const uint32_t alo = tc::smem_u32(stage_Alo(s)), wlo = tc::smem_u32(stage_Wlo(s));
+      if (tc::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {
           const uint32_t off = kk * 32;   // 8 tf32 = 32 bytes along K inside the 128B swizzle span
@@ -129,8 +131,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tc::umma_commit(empty + s);
+        if (kt == nk - 1) tc::umma_commit(tmem_full);
       }
-      tc::umma_commit(tmem_full);
+      __syncwarp();
     }
   } else {
     // ================================ splitters, then epilogue ================================

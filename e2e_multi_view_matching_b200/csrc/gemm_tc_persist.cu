@@ -99,13 +99,13 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN;
-        for (int kt = 0; kt < nk; ++kt, ++it) {
-          const int s = it % STAGES;
-          tc::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN;
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const int s = it % STAGES;
+        tc::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
+        if (tc::elect_one()) {
           tc::mbar_arrive_expect_tx(full + s, STAGE_BYTES);
           uint8_t* st = smem + s * STAGE_BYTES;
           const int k = kt * BK;
@@ -114,27 +114,29 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc::tma_load_2d(st + A_BYTES, &tmWhi, full + s, k, n0);
           tc::tma_load_2d(st + A_BYTES + W_BYTES, &tmWlo, full + s, k, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN);
-      uint32_t it = 0;
-      int i = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
-        const int buf = i & 1;
-        tc::mbar_wait(acc_empty + buf, ((i >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+    // the whole warp walks the loop (converged); one elected lane issues
+    constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN);
+    uint32_t it = 0;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+      const int buf = i & 1;
+      tc::mbar_wait(acc_empty + buf, ((i >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+      tc::tc_fence_after();
+      const uint32_t acc = tmem_base + TM_ACC + buf * BN;
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        tc::mbar_wait(full + s, ph);
+        tc::mbar_wait(a_ready + s, ph);
         tc::tc_fence_after();
-        const uint32_t acc = tmem_base + TM_ACC + buf * BN;
-        for (int kt = 0; kt < nk; ++kt, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          tc::mbar_wait(full + s, ph);
-          tc::mbar_wait(a_ready + s, ph);
-          tc::tc_fence_after();
-          const uint32_t whi = tc::smem_u32(smem + s * STAGE_BYTES + A_BYTES), wlo = whi + W_BYTES;
-          const uint32_t a_hi = tmem_base + TM_A + s * 64, a_lo = a_hi + 32;
+        const uint32_t whi = tc::smem_u32(smem + s * STAGE_BYTES + A_BYTES), wlo = whi + W_BYTES;
+        const uint32_t a_hi = tmem_base + TM_A + s * 64, a_lo = a_hi + 32;
+        if (tc::elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t dhi = tc::make_kmajor_sw128_desc(whi + kk * 32);
@@ -143,8 +145,9 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tc::umma_tf32_ts(acc, a_lo + kk * 8, dhi, idesc, 1);
           }
           tc::umma_commit(empty + s);
+          if (kt == nk - 1) tc::umma_commit(acc_full + buf);
         }
-        tc::umma_commit(acc_full + buf);
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
@@ -251,7 +254,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int j = 0; j < 8; ++j) so[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           tc::fence_proxy_async();
           __syncwarp();
-          if (lane == 0) { tc::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, nb, m0 + q * 32); tc::tma_store_commit(); }
+          if (tc::elect_one()) { tc::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, nb, m0 + q * 32); tc::tma_store_commit(); }
           sbuf ^= 1;
           tc::tma_store_wait_read<1>();
           __syncwarp();
@@ -260,14 +263,14 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int j = 0; j < 8; ++j) sl[j ^ (lane & 7)] = make_float4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
           tc::fence_proxy_async();
           __syncwarp();
-          if (lane == 0) { tc::tma_store_2d(&tmKLO, stg + sbuf * STG_BYTES, nb - 256, m0 + q * 32); tc::tma_store_commit(); }
+          if (tc::elect_one()) { tc::tma_store_2d(&tmKLO, stg + sbuf * STG_BYTES, nb - 256, m0 + q * 32); tc::tma_store_commit(); }
           sbuf ^= 1;
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) so[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           tc::fence_proxy_async();
           __syncwarp();
-          if (lane == 0) { tc::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, nb, m0 + q * 32); tc::tma_store_commit(); }
+          if (tc::elect_one()) { tc::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, nb, m0 + q * 32); tc::tma_store_commit(); }
           sbuf ^= 1;
         }
       }
