@@ -5,14 +5,17 @@
 //
 // One CTA = 128 queries of one (view, head); keys/values stream through in tiles of 64.
 //   warp 0      TMA producer   per tile K [64x64] (from QKV) and V^T [64 d x 64 keys], 3-deep rings
-//   warp 1      tcgen05.mma issuer (one thread): S = Q K^T  (M128 N64 K64, kind::tf32) into one of two
-//               TMEM S buffers, O_tile = P V (M128 N64 K64) into a TMEM O buffer; BOTH A operands (Q and P)
-//               live in tensor memory, so shared-memory bandwidth only carries the K / V^T tiles;
-//               software pipelined so S(j+1) is issued before P(j) is awaited
-//   warps 2-5   softmax: thread r owns query row r (TMEM lane r): tcgen05.ld S row, running max / sum in
-//               registers (no shuffles), exp2, P written back to TENSOR MEMORY (tcgen05.st) and consumed
-//               as the A operand of P.V straight from TMEM, O_tile folded into a register accumulator with
-//               the online-softmax correction
+//   warp 1      tcgen05.mma issuer for S = Q K^T  (M128 N64 K64, kind::tf32) into one of two TMEM S buffers
+//   warp 2      tcgen05.mma issuer for O_g += P V (M128 N64 K64) into the TMEM accumulator of the tile's
+//               softmax group; BOTH A operands (Q and P) live in tensor memory, so shared-memory bandwidth
+//               only carries the K / V^T tiles
+//   warps 3-6   softmax group 0 (even key tiles), warps 7-10 softmax group 1 (odd key tiles): thread r of a
+//               group owns query row r (TMEM lane r): tcgen05.ld S row, row max / sum in registers (no
+//               shuffles), exp2, P written back to TENSOR MEMORY (tcgen05.st) and consumed as the A operand
+//               of P.V straight from TMEM.  Each group has its own S/P buffer, its own output accumulator in
+//               TMEM (O_g += P(j) V(j) over its tiles) and its own softmax reference (m_g, l_g); the two
+//               partial softmaxes are merged once at the end (exact: softmax is invariant to the reference).
+//               Two groups because one 4-warp group needs ~2400 cycles per tile against 1536 cycles of MMA
 //   (NPASS == 3) every product is A.B + A.B_lo + A_lo.B (fp32-faithful "3xTF32"): the tf32 hi/lo planes of
 //               K and V^T are produced by the QKV GEMM epilogue and arrive by TMA; Q and P are split in
 //               registers by the softmax threads before they are stored to tensor memory
@@ -37,12 +40,13 @@ struct ACfg {
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + ST * K_BYTES * PL;
   static constexpr int OFF_BAR = OFF_V + ST * V_BYTES * PL;
-  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
-  static constexpr int NTHREADS = 192;
-  static constexpr int MIN_CTAS = NPASS == 3 ? 1 : 2;
-  // TMEM columns: S0/P0 [0,64) S1/P1 [64,128) O [128,192) Q_hi [192,256)
-  //               (Q_lo [256,320) P0_lo [320,384) P1_lo [384,448))
-  static constexpr int TMEM_COLS = NPASS == 3 ? 512 : 256;
+  static constexpr int OFF_ML = OFF_BAR + 512;          // (m, l) of both softmax groups: float [2][2][128]
+  static constexpr int SMEM_BYTES = OFF_ML + 2048 + 1024;
+  static constexpr int NTHREADS = 352;
+  static constexpr int MIN_CTAS = 1;
+  // TMEM columns: S0/P0 [0,64) S1/P1 [64,128) O0 [128,192) Q_hi [192,256)
+  //               Q_lo [256,320) P0_lo [320,384) P1_lo [384,448) O1 [448,512)
+  static constexpr int TMEM_COLS = 512;
 };
 
 struct AttnTcArgs {
@@ -51,7 +55,9 @@ struct AttnTcArgs {
   int n_pad;
   AttnSegs segs;
   int is_cross;
+  long long* dbg;      // optional clock64 trace of CTA (0,0,0): [tile][16] (tools/attn_timing.py)
 };
+long long* g_attn_dbg = nullptr;
 
 using tc::tf32_rn;
 
@@ -97,11 +103,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   uint64_t* v_empty = bars + 13;   // [ST]
   uint64_t* v_split = bars + 16;   // [ST]
   uint64_t* s_full = bars + 19;    // [2]  S(j) landed in TMEM
-  uint64_t* p_ready = bars + 21;   // [2]  P(j) stored over S(j) (128 arrivals)
+  uint64_t* p_ready = bars + 21;   // [2]  keys 0-31 of P(j) stored over S(j) (128 arrivals)
+  uint64_t* p_ready_b = bars + 25; // [2]  keys 32-63 of P(j) stored
   uint64_t* o_full = bars + 23;    // [2]  P.V(j) landed in the TMEM accumulator (alternating, see the softmax warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool trace_cta = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool trace = trace_cta && lane == 0;
+  // slots 6,7,13-15 are written from inside elect_one() regions (whichever lane was elected)
+  auto mark = [&](int tile, int slot) { if ((slot == 6 || slot == 7 || slot >= 13 ? trace_cta : trace) && tile < 64) g.dbg[tile * 16 + slot] = clock64(); };
+  // CTA-level trace (second half of the debug buffer): [cta][8] = smid, start, setup done, Q stored, first S read,
+  // last tile done, merged + stored
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  auto cmark = [&](int slot) {
+    if (g.dbg != nullptr && cta_lin < 2048) g.dbg[64 * 16 + cta_lin * 8 + slot] = clock64();
+  };
+  if (threadIdx.x == 0 && g.dbg != nullptr && cta_lin < 2048) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g.dbg[64 * 16 + cta_lin * 8 + 0] = smid;
+    cmark(1);
+  }
   const int q0 = blockIdx.x * BQ;
   const int h = blockIdx.y;
   const int v = blockIdx.z;
@@ -135,7 +158,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc::mbar_init(k_full + i, 1); tc::mbar_init(k_empty + i, 1); tc::mbar_init(k_split + i, 128);
       tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1); tc::mbar_init(v_split + i, 128);
     }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(p_ready + i, 128); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(p_ready + i, 128); tc::mbar_init(p_ready_b + i, 128); }
     tc::mbar_init(o_full, 1); tc::mbar_init(o_full + 1, 1);
     tc::fence_barrier_init();
   }
@@ -147,9 +170,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  if (threadIdx.x == 0) cmark(2);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 128, tmem_Q = tmem_base + 192;
-  const uint32_t tmem_Qlo = tmem_base + 256, tmem_Plo0 = tmem_base + 320;
+  const uint32_t tmem_Qlo = tmem_base + 256, tmem_Plo0 = tmem_base + 320, tmem_O1 = tmem_base + 448;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -193,17 +217,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       if (j + 1 < nt) load_K(j + 1);
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    // The tensor pipe executes in issue order, so S(j+1) may overwrite the buffer that held P(j-1)
-    // without an explicit wait: P(j-1).V was issued earlier.  The whole warp walks the loop (converged) and
-    // one elected lane issues: under `if (lane == 0)` every UTCHMMA gets an elect/branch waterfall loop.
-    constexpr uint32_t idesc = tc::make_idesc_tf32(BQ, BKV);   // M=128, N=64 for both products
+    // =========================== MMA issuer 1: S = Q K^T ===========================
+    // Two issuing warps, one per product.  A single issuer is serial -- barrier waits (~100 clk each even when
+    // the barrier has long completed), tcgen05.commit (~30-120 clk) and N=64 MMAs that execute in 32 clk, with
+    // a queue only a few entries deep: measured 2200 clk per key tile for 1536 clk of tensor work
+    // (tools/attn_timing.py).  With two instruction streams each warp's stalls are covered by the other's
+    // queued MMAs.  The ordering a single in-order stream gave for free is now explicit: S(j) overwrites the
+    // buffer P(j-2) was read from, so it waits for P.V(j-2) to complete (o_full[j & 1]).
+    // Whole warp converged, one elected lane issues (see tc::elect_one).
+    constexpr uint32_t idesc = tc::make_idesc_tf32(BQ, BKV);   // M=128, N=64
     tc::mbar_wait(q_ready, 0);
     tc::tc_fence_after();
-    auto issue_S = [&](int j) {
+    for (int j = 0; j < nt; ++j) {
       const int s = j % ST, sb = j & 1;
+      mark(j, 8);
       tc::mbar_wait(k_full + s, (j / ST) & 1);
+      // P.V(j-2) done reading P / P_lo of this buffer.  P.V(j) cannot have completed (it needs this S), so the
+      // barrier is at most one phase ahead of the phase awaited: the parity wait is sound.
+      if (j >= 2) tc::mbar_wait(o_full + sb, ((j - 2) >> 1) & 1);
       tc::tc_fence_after();
+      mark(j, 9);
       const uint32_t k_hi = tc::smem_u32(sK(s)), k_lo = k_hi + K_BYTES;
       const uint32_t d = tmem_S0 + sb * 64;
       if (tc::elect_one()) {
@@ -217,43 +250,63 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
             tc::umma_tf32_ts(d, tmem_Qlo + kk * 8, dk, idesc, 1);
           }
         }
+        mark(j, 6);
         tc::umma_commit(s_full + sb);
         tc::umma_commit(k_empty + s);
-      }
-      __syncwarp();
-    };
-    issue_S(0);
-    for (int j = 0; j < nt; ++j) {
-      if (j + 1 < nt) issue_S(j + 1);
-      const int s = j % ST, sb = j & 1;
-      tc::mbar_wait(p_ready + sb, (j >> 1) & 1);
-      tc::mbar_wait(v_full + s, (j / ST) & 1);
-      tc::tc_fence_after();
-      const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
-      const uint32_t p_hi = tmem_S0 + sb * 64, p_lo = tmem_Plo0 + sb * 64;
-      if (tc::elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < BKV / 8; ++kk) {
-          const uint32_t offv = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
-          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + offv);
-          tc::umma_tf32_ts(tmem_O, p_hi + kk * 8, dv, idesc, (j | kk) != 0);  // A = P from tensor memory; O accumulates over tiles
-          if (NPASS == 3) {
-            tc::umma_tf32_ts(tmem_O, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + offv), idesc, 1);
-            tc::umma_tf32_ts(tmem_O, p_lo + kk * 8, dv, idesc, 1);
-          }
-        }
-        tc::umma_commit(o_full + (j & 1));
-        tc::umma_commit(v_empty + s);
+        mark(j, 7);
       }
       __syncwarp();
     }
-  } else if (warp < 6) {
-    // =========================== softmax / accumulate ===========================
+  } else if (warp == 2) {
+    // =========================== MMA issuer 2: O_g += P V ===========================
+    constexpr uint32_t idesc = tc::make_idesc_tf32(BQ, HD);    // M=128, N=64
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % ST, sb = j & 1;
+      // P(j) arrives in two halves (keys 0-31, 32-63): the first 12 MMAs start while the softmax threads are
+      // still exponentiating the second half
+      tc::mbar_wait(p_ready + sb, (j >> 1) & 1);
+      tc::mbar_wait(v_full + s, (j / ST) & 1);
+      tc::tc_fence_after();
+      mark(j, 10);
+      const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
+      const uint32_t p_hi = tmem_S0 + sb * 64, p_lo = tmem_Plo0 + sb * 64;
+      const uint32_t o_acc = sb ? tmem_O1 : tmem_O;
+      auto issue_PV = [&](int kk0) {
+#pragma unroll
+        for (int kk = kk0; kk < kk0 + BKV / 16; ++kk) {
+          const uint32_t offv = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
+          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + offv);
+          tc::umma_tf32_ts(o_acc, p_hi + kk * 8, dv, idesc, ((j >> 1) | kk) != 0);  // A = P from tensor memory; O_g accumulates over the group's tiles
+          if (NPASS == 3) {
+            tc::umma_tf32_ts(o_acc, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + offv), idesc, 1);
+            tc::umma_tf32_ts(o_acc, p_lo + kk * 8, dv, idesc, 1);
+          }
+        }
+      };
+      if (tc::elect_one()) issue_PV(0);
+      __syncwarp();
+      mark(j, 11);
+      tc::mbar_wait(p_ready_b + sb, (j >> 1) & 1);
+      tc::tc_fence_after();
+      mark(j, 12);
+      if (tc::elect_one()) {
+        issue_PV(BKV / 16);
+        mark(j, 13);
+        tc::umma_commit(o_full + (j & 1));
+        mark(j, 14);
+        tc::umma_commit(v_empty + s);
+        mark(j, 15);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== softmax groups ===========================
+    const int grp = warp >= 7 ? 1 : 0;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    // Q row -> tensor memory (A operand of S = Q K^T); rows past the view are read but never written back
-    {
+    // group 0: Q row -> tensor memory (A operand of S = Q K^T); rows past the view are read but never written back
+    if (grp == 0) {
       const float4* qg = reinterpret_cast<const float4*>(g.qkv + ((long long)v * g.n_pad + q0 + row) * 768 + h * HD);
       const bool in_range = (long long)v * g.n_pad + q0 + row < (long long)gridDim.z * g.n_pad;
       float qr[HD];
@@ -280,66 +333,74 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(q_ready);
+      if (warp == 3 && lane == 0) cmark(3);
     }
-    // Online softmax with the output accumulator RESIDENT IN TENSOR MEMORY: O += P(j) V(j) accumulates over all
-    // key tiles; the running reference m_ref of a row is only raised (and O, l rescaled) when the row maximum
-    // outgrows it by more than 2^8 -- softmax is invariant to the reference, P stays <= 2^8, and the common tile
-    // costs no TMEM read of O at all.  All quantities are in log2 units (scores * log2(e) / sqrt(d)).
+    // Online softmax over this group's key tiles (j = grp, grp + 2, ...) with the output accumulator RESIDENT IN
+    // TENSOR MEMORY.  The reference m_ref of a row is only raised (and O_g, l rescaled) when the row maximum
+    // outgrows it by more than 2^8: softmax is invariant to the reference, P stays <= 2^8, and the common tile
+    // costs no TMEM read of O at all.  Log2 units throughout (scores * log2(e) / sqrt(d)).
+    const uint32_t tm_S = tmem_S0 + grp * 64, tm_Plo = tmem_Plo0 + grp * 64, tm_O = grp ? tmem_O1 : tmem_O;
+    uint64_t* my_o_full = o_full + grp;
     float m_ref = -INFINITY, l_run = 0.f;
     const float scale_l2e = 0.125f * 1.4426950408889634f;
-    int j = 0;
+    int j = 0, mine = 0;           // global tile index, tiles this group has processed
     for (int sg = 0; sg < T; ++sg) {
       if (g.is_cross ? (sg == t) : (sg != t)) continue;
       const int cnt = g.segs.counts[sg];
       for (int k0 = 0; k0 < cnt; k0 += BKV, ++j) {
-        const int sb = j & 1;
+        if ((j & 1) != grp) continue;
         const int nvalid = cnt - k0;      // keys of this tile that exist
-        tc::mbar_wait(s_full + sb, (j >> 1) & 1);
+        if (q == 3) mark(j, 0);
+        tc::mbar_wait(s_full + grp, mine & 1);
         tc::tc_fence_after();
+        if (q == 3) mark(j, 1);
+        if (warp == 3 && lane == 0 && j == 0) cmark(4);
         float s[BKV];
-        tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr, s);
-        tc::tmem_ld32(tmem_S0 + sb * 64 + lane_addr + 32, s + 32);
+        tc::tmem_ld32(tm_S + lane_addr, s);
+        tc::tmem_ld32(tm_S + lane_addr + 32, s + 32);
         tc::tmem_ld_wait();
+        if (q == 3) mark(j, 2);
         if (nvalid < BKV) {
 #pragma unroll
           for (int i = 0; i < BKV; ++i) s[i] = (i < nvalid) ? s[i] : -INFINITY;
         }
-        float mx = s[0];
+        float mx4[4] = {s[0], s[1], s[2], s[3]};          // four independent chains instead of one of 63
 #pragma unroll
-        for (int i = 1; i < BKV; ++i) mx = fmaxf(mx, s[i]);
-        mx *= scale_l2e;
+        for (int i = 4; i < BKV; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], s[i]);
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_l2e;
         const bool grow = mx > m_ref + 8.f;
         if (__any_sync(0xffffffffu, grow)) {
           float f = 1.f;
           if (grow) { f = ex2_ftz(m_ref - mx); m_ref = mx; l_run *= f; }
-          if (j > 0) {
-            // every P.V issued so far must have landed before O is touched.  P.V(j) commits to o_full[j & 1]:
-            // a parity wait is only sound while the barrier is at most one phase ahead of the waiter, and
-            // barrier (j-1)&1 cannot run further ahead than P.V(j-1) (P.V(j+1) needs this warp's P(j+1))
-            tc::mbar_wait(o_full + ((j - 1) & 1), ((j - 1) >> 1) & 1);
+          if (mine > 0) {
+            // the group's previous product P.V(j-2) has landed: S(j), issued after it, has been read (the tensor
+            // pipe is in order); the wait only makes that visible to this thread
+            tc::mbar_wait(my_o_full, (mine - 1) & 1);
             tc::tc_fence_after();
             float o[32];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-              tc::tmem_ld32(tmem_O + lane_addr + c * 32, o);
+              tc::tmem_ld32(tm_O + lane_addr + c * 32, o);
               tc::tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] *= f;
-              tc::tmem_st32(tmem_O + lane_addr + c * 32, o);
+              tc::tmem_st32(tm_O + lane_addr + c * 32, o);
             }
             tc::tmem_st_wait();
           }
         }
+        if (q == 3) mark(j, 3);
         const float nm = -m_ref;
-        float rs = 0.f;
-        // P(j) overwrites S(j) in tensor memory (row r = lane r, keys along columns): A operand of P.V
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+        // P(j) overwrites S(j) in tensor memory (row r = lane r, keys along columns): A operand of P.V,
+        // handed over in two halves
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           float lo[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float pv = ex2_ftz(fmaf(s[c * 32 + i], scale_l2e, nm));
-            rs += pv;
+            rs4[i & 3] += pv;
             if (NPASS == 3) {
               const float hi = tf32_hi(pv);
               lo[i] = pv - hi;          // the tensor core reads the top 19 bits: truncation of lo costs 2^-21 |p|
@@ -348,39 +409,60 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
               s[c * 32 + i] = pv;
             }
           }
-          if (NPASS == 3) tc::tmem_st32(tmem_Plo0 + sb * 64 + lane_addr + c * 32, lo);
-          tc::tmem_st32(tmem_S0 + sb * 64 + lane_addr + c * 32, s + c * 32);
+          if (NPASS == 3) tc::tmem_st32(tm_Plo + lane_addr + c * 32, lo);
+          tc::tmem_st32(tm_S + lane_addr + c * 32, s + c * 32);
+          tc::tmem_st_wait();
+          tc::tc_fence_before();
+          tc::mbar_arrive((c == 0 ? p_ready : p_ready_b) + grp);
+          if (q == 3) mark(j, 4 + c);
         }
-        l_run += rs;
-        tc::tmem_st_wait();
-        tc::tc_fence_before();
-        tc::mbar_arrive(p_ready + sb);
+        l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+        ++mine;
       }
     }
-    // epilogue: O / l once the last product (and, the tensor pipe being in order, every earlier one) has landed
-    tc::mbar_wait(o_full + ((j - 1) & 1), ((j - 1) >> 1) & 1);
+    // ---- merge the two partial softmaxes:  out = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1),  w_g = 2^(m_g - m)
+    if (mine > 0) {
+      tc::mbar_wait(my_o_full, (mine - 1) & 1);     // the group's last product (hence all of them) has landed
+      tc::tc_fence_after();
+    }
+    if (warp == 3 && lane == 0) cmark(5);
+    float* ml = reinterpret_cast<float*>(smem + C_::OFF_ML);
+    ml[(grp * 2 + 0) * 128 + row] = m_ref;
+    ml[(grp * 2 + 1) * 128 + row] = l_run;
+    tc::tc_fence_before();
+    asm volatile("bar.sync 2, 256;" ::: "memory");
     tc::tc_fence_after();
+    const bool has1 = j > 1;                        // group 1 saw at least one tile (uniform over the CTA)
+    const float m0 = ml[0 * 128 + row], l0 = ml[1 * 128 + row];
+    const float m1 = has1 ? ml[2 * 128 + row] : -INFINITY, l1 = has1 ? ml[3 * 128 + row] : 0.f;
+    const float mm = fmaxf(m0, m1);
+    const float w0 = ex2_ftz(m0 - mm), w1 = has1 ? ex2_ftz(m1 - mm) : 0.f;
+    const float inv = 1.f / (l0 * w0 + l1 * w1);
+    // group g writes d in [32 g, 32 g + 32) of the row
+    float o0[32], o1[32];
+    tc::tmem_ld32(tmem_O + lane_addr + grp * 32, o0);
+    if (has1) tc::tmem_ld32(tmem_O1 + lane_addr + grp * 32, o1);
+    tc::tmem_ld_wait();
     if (q0 + row < g.n_pad) {
-      const float inv = 1.f / l_run;
-      float4* o4 = reinterpret_cast<float4*>(g.out + ((long long)v * g.n_pad + q0 + row) * 256 + h * HD);
+      const float a0 = w0 * inv, a1 = w1 * inv;
+      float4* o4 = reinterpret_cast<float4*>(g.out + ((long long)v * g.n_pad + q0 + row) * 256 + h * HD + grp * 32);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float o[32];
-        tc::tmem_ld32(tmem_O + lane_addr + c * 32, o);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o4[c * 8 + i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+      for (int i = 0; i < 8; ++i) {
+        float4 r;
+        r.x = o0[4 * i] * a0; r.y = o0[4 * i + 1] * a0; r.z = o0[4 * i + 2] * a0; r.w = o0[4 * i + 3] * a0;
+        if (has1) {
+          r.x = fmaf(o1[4 * i], a1, r.x); r.y = fmaf(o1[4 * i + 1], a1, r.y);
+          r.z = fmaf(o1[4 * i + 2], a1, r.z); r.w = fmaf(o1[4 * i + 3], a1, r.w);
+        }
+        o4[i] = r;
       }
-    } else {
-      float o[32];                      // the loads are warp-collective: every lane takes part
-#pragma unroll
-      for (int c = 0; c < 2; ++c) { tc::tmem_ld32(tmem_O + lane_addr + c * 32, o); tc::tmem_ld_wait(); }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) cmark(6);
   if (warp == 1) tc::tmem_dealloc<C_::TMEM_COLS>(tmem_base);
+  if (threadIdx.x == 32) cmark(7);
 }
 
 template <int NPASS>
@@ -400,7 +482,7 @@ int launch_attn(const float* qkv, const float* vt, const float* klo, const float
   const CUtensorMap* tVlo = vtlo ? mvm_get_tmap_2d(vtlo, (long long)V * 256, n_pad, n_pad, BKV) : tV;
   if (!tK || !tV || !tKlo || !tVlo) return MVM_ERR_LAUNCH;
   AttnTcArgs g;
-  g.qkv = qkv; g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross;
+  g.qkv = qkv; g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross; g.dbg = g_attn_dbg;
   dim3 grid(mvm_div_up(n_pad, BQ), 4, V);
   attention_tc_kernel<NPASS><<<grid, C_::NTHREADS, C_::SMEM_BYTES, stream>>>(*tK, *tV, *tKlo, *tVlo, g);
   MVM_CHECK_LAUNCH();
@@ -408,6 +490,8 @@ int launch_attn(const float* qkv, const float* vt, const float* klo, const float
 }
 
 }  // namespace
+
+extern "C" void mvm_debug_set_attention_timing(long long* buf) { g_attn_dbg = buf; }
 
 // qkv [V, n_pad, 768] (q | k | unused-v), vt [V, 256, n_pad] = V^T per head; out [V, n_pad, 256]
 int launch_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_pad, AttnSegs segs,
