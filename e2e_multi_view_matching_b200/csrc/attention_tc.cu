@@ -132,6 +132,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   const int t = v % T, b = v / T;
   if (q0 >= g.segs.counts[t]) return;
 
+  // softmax group 0 (warps 3-6) owns the Q rows: issue their global loads first, so the latency runs under the
+  // barrier / TMEM set-up below (measured: 4.7k of a CTA's 130k cycles went to a serial Q load)
+  float qr[HD];
+  if (warp >= 3 && warp < 7) {
+    const int qrow = (warp & 3) * 32 + lane;
+    const float4* qg = reinterpret_cast<const float4*>(g.qkv + ((long long)v * g.n_pad + q0 + qrow) * 768 + h * HD);
+    const bool in_range = (long long)v * g.n_pad + q0 + qrow < (long long)gridDim.z * g.n_pad;
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) {
+      const float4 x = in_range ? __ldg(qg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      qr[4 * i] = x.x; qr[4 * i + 1] = x.y; qr[4 * i + 2] = x.z; qr[4 * i + 3] = x.w;
+    }
+  }
+
   // flattened key-tile list of this query view: segments (views) in ascending order, 64 keys per tile
   int nt = 0;
   for (int s = 0; s < T; ++s) {
@@ -307,14 +321,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     // group 0: Q row -> tensor memory (A operand of S = Q K^T); rows past the view are read but never written back
     if (grp == 0) {
-      const float4* qg = reinterpret_cast<const float4*>(g.qkv + ((long long)v * g.n_pad + q0 + row) * 768 + h * HD);
-      const bool in_range = (long long)v * g.n_pad + q0 + row < (long long)gridDim.z * g.n_pad;
-      float qr[HD];
-#pragma unroll
-      for (int i = 0; i < HD / 4; ++i) {
-        const float4 x = in_range ? qg[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        qr[4 * i] = x.x; qr[4 * i + 1] = x.y; qr[4 * i + 2] = x.z; qr[4 * i + 3] = x.w;
-      }
       if (NPASS == 3) {
         float lo[32];
 #pragma unroll
