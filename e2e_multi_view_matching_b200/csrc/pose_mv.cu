@@ -204,7 +204,9 @@ struct MvbaArgs {
   int max_iter;
   int* iters_out;                       // [B] or null
   double* cost_out;                     // [B,2] initial / final cost or null
+  long long* timing;                    // optional [8] phase cycle counters of CTA 0 (tools/debug_mvba.py), or null
 };
+long long* g_mvba_timing = nullptr;
 
 __device__ __forceinline__ unsigned ld_acq(const unsigned* p) {
   unsigned v;
@@ -496,7 +498,10 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
 
     int it = 0;
     bool need_cost0 = true;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (; it < g.max_iter; ++it) {
+      long long tph = clock64();
+      auto phase = [&](int k) { const long long t1 = clock64(); tacc[k] += t1 - tph; tph = t1; };
       // ================= pass A: reduced camera system at the current point =================
       if (tid == 0) { aa_to_R(s_cam[va], s_Ra); aa_to_R(s_cam[vb], s_Rb); }
       zero_acc();
@@ -587,7 +592,9 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         for (int w = 0; w < NW; ++w) { m = fmax(m, s_acc[w][103]); s_acc[w][103] = 0.0; }
         s_acc[0][103] = m;
       }
+      phase(0);
       exchange(116);
+      phase(1);
 
       // ---- assemble the reduced system from all partial records.  Every output element is owned
       // by one thread and summed over the pairs in a fixed order, so all CTAs of the tuple build
@@ -635,11 +642,13 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
       }
       __syncthreads();
       need_cost0 = false;
+      phase(2);
       if (warp == 0) {
         const bool ok = chol_solve_warp(s_H, s_rhs, nu, lane);
         if (lane == 0) s_flag[1] = ok ? 1 : 0;
       }
       __syncthreads();
+      phase(3);
       const bool solved = s_flag[1] != 0;
       const double cost_cur = s_ctl[2];
       if (s_ctl[3] <= 1e-10) { if (tid == 0) s_flag[0] = 1; __syncthreads(); break; }   // gradient tolerance
@@ -721,7 +730,9 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
           wacc(&s_acc[warp][3], xn2, lane);
         }
       }
+      phase(4);
       exchange(4);
+      phase(5);
       if (tid < 4 * P) s_dec[tid] = s_rec[(tid >> 2) * NPART + (tid & 3)];
       __syncthreads();
       if (tid == 0) {
@@ -765,7 +776,12 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         double* t = pcur; pcur = pnew; pnew = t;
       }
       __syncthreads();
+      phase(6);
       if (s_flag[3]) { ++it; break; }
+    }
+    if (g.timing && blockIdx.x == 0 && tid == 0 && bi == group) {
+      for (int k = 0; k < 7; ++k) g.timing[k] = tacc[k];
+      g.timing[7] = it;
     }
 
     // ---- result: extrinsics of every view (camera 0 untouched) ----
@@ -861,6 +877,8 @@ size_t mvm_mvba_workspace_bytes(int n_views, int n_pairs, int batch, int n_pad) 
   return pts + psc + xch + 1024;
 }
 
+void mvm_debug_set_mvba_timing(long long* p) { g_mvba_timing = p; }
+
 int mvm_multi_view_ba_ex(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch,
                          int n_pad, const float* xn_a, const float* xn_b, const float* conf,
                          const int* n_valid, const double* extr_init, const double* points_init,
@@ -888,6 +906,7 @@ int mvm_multi_view_ba_ex(const int* pair_a, const int* pair_b, int n_views, int 
   g.xa = xn_a; g.xb = xn_b; g.conf = conf; g.n_valid = n_valid; g.extr_init = extr_init;
   g.pts_init = points_init; g.prenorm = weights_prenormalized ? 1 : 0; g.extr_out64 = extr_out_f64;
   g.extr_out = extr_out; g.max_iter = max_iterations; g.iters_out = iterations_out; g.cost_out = cost_out;
+  g.timing = g_mvba_timing;
   char* w = (char*)workspace;
   g.ctrs = (unsigned*)w; w += 1024;
   g.pts = (double*)w; w += (size_t)batch * n_pairs * 2 * n_pad * 3 * sizeof(double);
