@@ -241,7 +241,50 @@ __device__ inline void R_to_aa(const double* R, double* w) {
 }
 
 
-constexpr int MAXU = 42;   // leading dimension of the small dense systems (6 x 7 free cameras)
+constexpr int MAXU = 43;   // leading dimension of the small dense systems (6 x 7 free cameras = 42 unknowns, +1: odd
+                           // in 8-byte banks, and room for the augmented right-hand-side row of chol_solve_warp_rows)
+
+// Warp Cholesky solve with one lane per matrix row (n + 1 <= 32): left-looking factorisation, lane i forms
+// L[i][j] = (A[i][j] - sum_{k<j} L[i][k] L[j][k]) / L[j][j] from its OWN row (conflict-free: the leading
+// dimension MAXU is odd in 8-byte banks) and row j (a broadcast read).  The right-hand side rides along as
+// row n of the matrix, so the forward substitution is part of the factorisation; the backward substitution is
+// column oriented.  Short loops on purpose: the fully unrolled register version of this (7 k straight-line
+// instructions, executed once per LM iteration) was slower than the shared-memory loops -- instruction fetch.
+// Measured (tools/mvba_timing.py, 24 x 24): 39 us for chol_solve_warp below, ~5 us here.
+// A: symmetric, row-major, ld = MAXU, rows 0..n used (row n = scratch), overwritten.  x: rhs in, solution out.
+__device__ inline bool chol_solve_warp_rows(double* A, double* x, int n, int lane) {
+  if (lane < n) A[n * MAXU + lane] = x[lane];
+  __syncwarp();
+  double* row = A + (lane <= n ? lane : 0) * MAXU;
+  bool ok = true;
+  for (int j = 0; j < n; ++j) {
+    const double* rj = A + j * MAXU;
+    double s = 0.0;
+    if (lane >= j && lane <= n) {
+      s = row[j];
+#pragma unroll 4
+      for (int k = 0; k < j; ++k) s -= row[k] * rj[k];
+    }
+    double d = __shfl_sync(0xffffffffu, s, j);
+    if (!(d > 0.0)) { ok = false; break; }     // uniform
+    d = sqrt(d);
+    __syncwarp();
+    if (lane == j) row[j] = d;
+    else if (lane > j && lane <= n) row[j] = s / d;
+    __syncwarp();
+  }
+  if (!ok) return false;
+  double y = lane < n ? A[n * MAXU + lane] : 0.0;      // L y = b solved above: y sits in row n
+  for (int k = n - 1; k >= 0; --k) {
+    const double xk = __shfl_sync(0xffffffffu, y, k) / A[k * MAXU + k];
+    if (lane == k) y = xk;
+    else if (lane < k) y -= A[k * MAXU + lane] * xk;
+  }
+  if (lane < n) x[lane] = y;
+  __syncwarp();
+  return true;
+}
+
 // warp-cooperative Cholesky solve of the n x n SPD system in shared memory (n <= 42).
 // A (row-major, ld = MAXU) is overwritten, x holds rhs on entry / solution on exit.
 __device__ inline bool chol_solve_warp(double* A, double* x, int n, int lane) {

@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
       need_cost0 = false;
       phase(2);
       if (warp == 0) {
-        const bool ok = chol_solve_warp(s_H, s_rhs, nu, lane);
+        const bool ok = nu < 32 ? chol_solve_warp_rows(s_H, s_rhs, nu, lane) : chol_solve_warp(s_H, s_rhs, nu, lane);
         if (lane == 0) s_flag[1] = ok ? 1 : 0;
       }
       __syncthreads();
