@@ -193,7 +193,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--tuples', type=int, default=8, help='tuples per step per GPU')
+    ap.add_argument('--tuples', type=int, default=14, help='tuples per step per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-tile', type=int, default=256, choices=[128, 256])
     ap.add_argument('--gemm-kernel', default='persistent', choices=['persistent', 'tile'],
