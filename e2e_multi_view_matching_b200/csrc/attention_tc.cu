@@ -15,7 +15,8 @@
 //               of P.V straight from TMEM.  Each group has its own S/P buffer, its own output accumulator in
 //               TMEM (O_g += P(j) V(j) over its tiles) and its own softmax reference (m_g, l_g); the two
 //               partial softmaxes are merged once at the end (exact: softmax is invariant to the reference).
-//               Two groups because one 4-warp group needs ~2400 cycles per tile against 1536 cycles of MMA
+//               Two groups so that a tile's S -> softmax -> P latency (wake-up, TMEM load, 64 exp2, split, TMEM
+//               store: ~1.2 k cycles) overlaps the other group's tile instead of idling the tensor pipe
 //   (NPASS == 3) every product is A.B + A.B_lo + A_lo.B (fp32-faithful "3xTF32"): the tf32 hi/lo planes of
 //               K and V^T are produced by the QKV GEMM epilogue and arrive by TMA; Q and P are split in
 //               registers by the softmax threads before they are stored to tensor memory
@@ -70,20 +71,6 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // which the compiler expands to four instructions with the Inf/NaN guard)
 __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-}
-
-// element-wise hi (in place) / lo split of a landed tile (layout agnostic)
-__device__ __forceinline__ void split_tile(uint8_t* hi_base, uint8_t* lo_base, int bytes, int t, int nthr) {
-  float4* h = reinterpret_cast<float4*>(hi_base);
-  float4* l = reinterpret_cast<float4*>(lo_base);
-  for (int i = t; i < bytes / 16; i += nthr) {
-    const float4 x = h[i];
-    float4 a, b;
-    a.x = tf32_rn(x.x); a.y = tf32_rn(x.y); a.z = tf32_rn(x.z); a.w = tf32_rn(x.w);
-    b.x = tf32_rn(x.x - a.x); b.y = tf32_rn(x.y - a.y); b.z = tf32_rn(x.z - a.z); b.w = tf32_rn(x.w - a.w);
-    h[i] = a;
-    l[i] = b;
-  }
 }
 
 template <int NPASS>
