@@ -37,6 +37,18 @@ SINKHORN_BYTES_PER_PAIR = 100 * 2 * (N_KPTS + 1) ** 2 * 4 + 2 * (N_KPTS + 1) ** 
 TF32_PEAK_TFLOPS = 148 * 4096 * 1.965e9 / 1e12      # tcgen05 kind::tf32 issue floor x SMs x max SM clock
 
 
+def load_traffic(tuples):
+    """Per-launch DRAM traffic of the dominant kernels from the committed ncu capture (profiles/ncu_traffic.json),
+    valid for the batch size it was captured at."""
+    try:
+        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_traffic.json')))
+        if t.get('tuples_per_step') == tuples:
+            return t['attention']['avg_bytes_per_launch'], t['sinkhorn']['avg_bytes_per_launch']
+    except Exception:
+        pass
+    return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -357,6 +369,7 @@ def main():
         total_tuples = B * args.steps * world
         value = total_tuples / (ms_dev * 1e-3)
         e2e = total_tuples / (ms_e2e * 1e-3)
+        traffic_att, traffic_sink = load_traffic(B)
         att_ms, att_n = prof['attention']
         n_self, n_cross = LAYERS.count('self'), LAYERS.count('cross')
         att_flops = (n_self * FLOPS_SELF + n_cross * FLOPS_CROSS) * B * prof_steps   # over the profiled steps
@@ -384,7 +397,7 @@ def main():
             'clocks': sampler.summary(),
             'roofline': {'kernel': 'attention (QK^T + PV, all views of one GNN layer per launch)', 'bound': 'tensor',
                          'achieved': att_tflops, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                         'frac': att_tflops / peaks['tflops'], 'traffic': None, 'launches_timed': att_n,
+                         'frac': att_tflops / peaks['tflops'], 'traffic': traffic_att, 'launches_timed': att_n,
                          'peak_source': peaks['source'],
                          # the path computes in tf32 (half the bf16 rate: M128.N.K8 every N/2 cycles = 4096 FLOP/clk/SM)
                          # and needs three passes to stay fp32-faithful: the reachable algorithmic ceiling
@@ -392,7 +405,7 @@ def main():
                          'frac_of_ceiling': att_tflops / (TF32_PEAK_TFLOPS / (3.0 if args.math_mode == 3 else 1.0))},
             'roofline_sinkhorn': {'kernel': 'sinkhorn (10 pairs x B problems per launch)', 'bound': 'hbm',
                                   'achieved': sk_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                                  'frac': sk_gbs / peaks['hbm_gbs'], 'traffic': None, 'launches_timed': sk_n},
+                                  'frac': sk_gbs / peaks['hbm_gbs'], 'traffic': traffic_sink, 'launches_timed': sk_n},
             'stage_ms_per_step': stage_ms,
             'wall_s': {'device_resident': wall_dev, 'e2e': wall_e2e},
             'pose_auc_5_10_20': [round(100 * a, 2) for a in auc],

@@ -23,6 +23,7 @@
 //   warps 6-9   epilogue: tcgen05.ld -> alpha/bias/ReLU/residual -> swizzled staging -> TMA store
 //               (V^T / lo planes of the QKV projection as in gemm_tc.cu)
 // TMEM (512 columns): accumulators [0,128) [128,256); A stages s at 256 + 64 s: hi [0,32) lo [32,64).
+#include <cstring>
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -54,15 +55,26 @@ struct PArgs {
   int tiles_m, tiles_n;
 };
 
+// SCORE mode: one launch computes every (pair, tuple) score matrix  scores = mdesc_a . mdesc_b^T * alpha  into the
+// inner [m, n] block of the [m+1, n+1] coupling buffers (multi_view_matcher.py:278-280).  A = descriptors of view
+// a (raw fp32, split on chip), W = the tf32 planes of the descriptors of view b.
+struct ScoreTab {
+  int n_pairs, batch, n_views, n_pad;
+  int a[MVM_MAX_PAIRS], b[MVM_MAX_PAIRS], m[MVM_MAX_PAIRS], n[MVM_MAX_PAIRS];
+  float* scores[MVM_MAX_PAIRS];
+};
+
 // rn_tf32 of a finite value (ties away, == cvt.rna.tf32.f32) in two integer instructions
 __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
+template <bool SCORE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                        const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
-                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmKLO, PArgs g) {
+                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmKLO, PArgs g,
+                       const __grid_constant__ ScoreTab st) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
@@ -76,7 +88,21 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = g.K / BK;
-  const int n_tiles = g.tiles_m * g.tiles_n;
+  const int per_prob = g.tiles_m * g.tiles_n;
+  const int n_tiles = SCORE ? per_prob * st.n_pairs * st.batch : per_prob;
+  // tile -> output tile origin (m0, n0) and the rows the A / W boxes start at
+  auto decode = [&](int tile, int& m0, int& n0, int& a_row, int& w_row, int& prob) {
+    if (!SCORE) {
+      m0 = (tile / g.tiles_n) * BM; n0 = (tile % g.tiles_n) * BN; a_row = m0; w_row = n0; prob = 0;
+    } else {
+      prob = tile / per_prob;
+      const int r = tile % per_prob;
+      m0 = (r / g.tiles_n) * BM; n0 = (r % g.tiles_n) * BN;
+      const int p = prob / st.batch, bi = prob % st.batch;
+      a_row = (bi * st.n_views + st.a[p]) * st.n_pad + m0;
+      w_row = (bi * st.n_views + st.b[p]) * st.n_pad + n0;
+    }
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -101,18 +127,19 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ================================ TMA producer ================================
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN;
+      int m0, n0, a_row, w_row, prob;
+      decode(tile, m0, n0, a_row, w_row, prob);
       for (int kt = 0; kt < nk; ++kt, ++it) {
         const int s = it % STAGES;
         tc::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
         if (tc::elect_one()) {
           tc::mbar_arrive_expect_tx(full + s, STAGE_BYTES);
-          uint8_t* st = smem + s * STAGE_BYTES;
+          uint8_t* sp = smem + s * STAGE_BYTES;
           const int k = kt * BK;
-          if (k < g.K1) tc::tma_load_2d(st, &tmA, full + s, k, m0);
-          else tc::tma_load_2d(st, &tmA2, full + s, k - g.K1, m0);
-          tc::tma_load_2d(st + A_BYTES, &tmWhi, full + s, k, n0);
-          tc::tma_load_2d(st + A_BYTES + W_BYTES, &tmWlo, full + s, k, n0);
+          if (k < g.K1) tc::tma_load_2d(sp, &tmA, full + s, k, a_row);
+          else tc::tma_load_2d(sp, &tmA2, full + s, k - g.K1, a_row);
+          tc::tma_load_2d(sp + A_BYTES, &tmWhi, full + s, k, w_row);
+          tc::tma_load_2d(sp + A_BYTES + W_BYTES, &tmWlo, full + s, k, w_row);
         }
         __syncwarp();
       }
@@ -189,16 +216,46 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int sbuf = 0;
     int i = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
-      const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN;
+      int m0, n0, a_row_, w_row_, prob;
+      decode(tile, m0, n0, a_row_, w_row_, prob);
       const int buf = i & 1;
       const int m = m0 + row;
       // bias of this tile's columns, shared by the four epilogue warps
       asm volatile("bar.sync 1, 128;" ::: "memory");           // previous tile's readers are done
-      s_bias[et] = g.bias ? __ldg(g.bias + n0 + et) : 0.f;
+      s_bias[et] = (!SCORE && g.bias) ? __ldg(g.bias + n0 + et) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       tc::mbar_wait(acc_full + buf, (i >> 1) & 1);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + TM_ACC + buf * BN + lane_addr;
+      if (SCORE) {
+        // rows of the coupling buffer are n+1 floats long (not 16-byte aligned): no TMA store.  Each warp
+        // transposes its 32 x 32 block through an XOR-swizzled staging tile so that a store instruction writes
+        // 32 consecutive floats of one row.
+        const int p = prob / st.batch, bi = prob % st.batch;
+        const int pm = st.m[p], pn = st.n[p];
+        float* Cp = st.scores[p] + (long long)bi * (pm + 1) * (pn + 1);
+        float* sw = reinterpret_cast<float*>(stg);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tc::tmem_ld32(taddr + c * 32, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sw[lane * 32 + (j ^ lane)] = g.alpha * v[j];
+          __syncwarp();
+          const int gn = n0 + c * 32 + lane;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int gm = m0 + q * 32 + rr;
+            const float x = sw[rr * 32 + (lane ^ rr)];
+            if (gm < pm && gn < pn) Cp[(long long)gm * (pn + 1) + gn] = x;
+          }
+          __syncwarp();
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(acc_empty + buf);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int nb = n0 + c * 32;
@@ -294,7 +351,7 @@ int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad,
   static bool attr = false;
   static int n_sm = 0;
   if (!attr) {
-    cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -314,7 +371,65 @@ int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad,
   g.tiles_m = mvm_div_up(d.M, BM); g.tiles_n = d.N / BN;
   const int n_tiles = g.tiles_m * g.tiles_n;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  gemm_tc_persist_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, g);
+  ScoreTab none;
+  none.n_pairs = 0; none.batch = 0; none.n_views = 0; none.n_pad = 0;
+  gemm_tc_persist_kernel<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, g, none);
+  MVM_CHECK_LAUNCH();
+  return MVM_OK;
+}
+
+namespace {
+// hi = rn_tf32(x), lo = rn_tf32(x - hi) of a whole buffer (the W-operand planes of the score GEMM)
+__global__ void split_planes_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
+                                    long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    float4 h, l;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    l.x = tf32_hi(v.x - h.x); l.y = tf32_hi(v.y - h.y); l.z = tf32_hi(v.z - h.z); l.w = tf32_hi(v.w - h.w);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+}  // namespace
+
+// All (pair, tuple) score matrices on the tensor cores (3xTF32).  mdesc [rows_total, 256] point-major; hi / lo:
+// scratch planes of the same size (filled here).
+int launch_score_gemm_tc(const float* mdesc, float* hi, float* lo, int n_pad, const PairTable& tab, int batch,
+                         float alpha, cudaStream_t stream) {
+  MvmProfScope prof__(MVM_TAG_SCORE, stream);
+  static bool attr = false;
+  static int n_sm = 0;
+  if (!attr) {
+    cudaFuncSetAttribute(gemm_tc_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  const long long rows = (long long)batch * tab.n_views * n_pad;
+  split_planes_kernel<<<n_sm * 4, 256, 0, stream>>>(reinterpret_cast<const float4*>(mdesc), reinterpret_cast<float4*>(hi),
+                                                    reinterpret_cast<float4*>(lo), rows * 256 / 4);
+  MVM_CHECK_LAUNCH();
+  const CUtensorMap* tA = mvm_get_tmap_2d(mdesc, rows, 256, 256, BM);
+  const CUtensorMap* tWhi = mvm_get_tmap_2d(hi, rows, 256, 256, BN);
+  const CUtensorMap* tWlo = mvm_get_tmap_2d(lo, rows, 256, 256, BN);
+  if (!tA || !tWhi || !tWlo) return MVM_ERR_LAUNCH;
+  ScoreTab st;
+  st.n_pairs = tab.n_pairs; st.batch = batch; st.n_views = tab.n_views; st.n_pad = n_pad;
+  int max_m = 0, max_n = 0;
+  for (int p = 0; p < tab.n_pairs; ++p) {
+    st.a[p] = tab.a[p]; st.b[p] = tab.b[p]; st.m[p] = tab.m[p]; st.n[p] = tab.n[p]; st.scores[p] = tab.scores[p];
+    max_m = tab.m[p] > max_m ? tab.m[p] : max_m;
+    max_n = tab.n[p] > max_n ? tab.n[p] : max_n;
+  }
+  PArgs g;
+  memset(&g, 0, sizeof(g));
+  g.K = 256; g.K1 = 256; g.alpha = alpha;
+  g.tiles_m = mvm_div_up(max_m, BM); g.tiles_n = mvm_div_up(max_n, BN);
+  const long long n_tiles = (long long)g.tiles_m * g.tiles_n * tab.n_pairs * batch;
+  const int grid = n_tiles < n_sm ? (int)n_tiles : n_sm;
+  gemm_tc_persist_kernel<true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA, *tWhi, *tWlo, *tA, *tA, g, st);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }

@@ -34,6 +34,10 @@ int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_
 // persistent 3xTF32 kernel (A operand in tensor memory, double-buffered accumulators, TMA-store epilogue)
 int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO,
                            cudaStream_t stream);
+// every (pair, tuple) score matrix in one launch of the persistent kernel (3xTF32); hi / lo: scratch [rows, 256]
+struct PairTable;
+int launch_score_gemm_tc(const float* mdesc, float* hi, float* lo, int n_pad, const PairTable& tab, int batch,
+                         float alpha, cudaStream_t stream);
 
 struct AttnSegs {
   int n_views;

@@ -69,6 +69,7 @@ GemmDesc make_gemm(const float* A, int lda, const float* W, int K, const float* 
 int g_math_mode = 3;
 
 long long g_hi_off = 0, g_lo_off = 0;   // set per forward from mvm_matcher_weights
+int g_score_tc = 1;                     // score GEMM on the tensor cores in mode 3 (mvm_debug_set_score_kernel)
 
 int run_gemm(const GemmDesc& g_in, cudaStream_t s) {
   GemmDesc g = g_in;
@@ -108,6 +109,8 @@ int fill_pair_table(PairTable& tab, const mvm_pair_io* pairs, int n_pairs, int n
 }  // namespace
 
 extern "C" {
+
+void mvm_debug_set_score_kernel(int tc) { g_score_tc = tc ? 1 : 0; }
 
 const char* mvm_version(void) { return "mvm_b200 0.1 sm_100a"; }
 
@@ -179,7 +182,10 @@ int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, in
 
   PairTable tab;
   MVM_TRY(fill_pair_table(tab, pairs, n_pairs, n_views, counts, batch));
-  MVM_TRY(launch_score_gemm_simt(ws.MD, n_pad, tab, batch, 1.0f / 16.0f, s));
+  // score matrices: tensor cores in the 3xTF32 mode (the K_lo / V^T_lo planes of the GNN are free again and
+  // hold the tf32 planes of the descriptors), fp32 CUDA cores otherwise
+  if (g_math_mode == 3 && g_score_tc) MVM_TRY(launch_score_gemm_tc(ws.MD, ws.KLO, ws.VTLO, n_pad, tab, batch, 1.0f / 16.0f, s));
+  else MVM_TRY(launch_score_gemm_simt(ws.MD, n_pad, tab, batch, 1.0f / 16.0f, s));
   MVM_TRY(launch_sinkhorn(tab, batch, w->bin_score, sinkhorn_iters, ws.sink_ws, s));
   MVM_TRY(launch_extract_matches(tab, batch, n_pad, match_threshold, ws.match_ws, s));
 

@@ -82,6 +82,7 @@ def test_gemm_kernel_variants_bit_identical():
     lib = _lib.lib()
     outs = []
     try:
+        lib.mvm_debug_set_score_kernel(0)       # same (fp32 CUDA-core) score GEMM for every variant
         for persist, tile in ((1, 256), (0, 128), (0, 256)):
             lib.mvm_debug_set_gemm_kernel(persist)
             lib.mvm_debug_set_gemm_tile(tile)
@@ -90,6 +91,7 @@ def test_gemm_kernel_variants_bit_identical():
     finally:
         lib.mvm_debug_set_gemm_kernel(1)
         lib.mvm_debug_set_gemm_tile(256)
+        lib.mvm_debug_set_score_kernel(1)
     for other in outs[1:]:
         for k in outs[0]:
             assert np.array_equal(outs[0][k], other[k]), k
@@ -124,3 +126,26 @@ def test_gemm_persistent_presplit(shape):
     assert torch.equal(out, old)
     if a2 is None:
         assert (plain.double() - a.double() @ w.double().T).abs().max().item() < 1e-4
+
+
+def test_score_gemm_tensor_cores_vs_cuda_cores():
+    """Score matrices of every pair from the persistent 3xTF32 kernel (SCORE mode, ragged views) against the fp32
+    CUDA-core kernel: the raw scores feed Sinkhorn, so compare the coupling matrices and the matches."""
+    import e2e_multi_view_matching_b200 as pkg
+    from e2e_multi_view_matching_b200 import _lib
+    from tests.test_matcher_gpu import run_ours
+    from tests.util import load_case, case_inputs, compare_matcher_outputs
+    lib = _lib.lib()
+    for name in ('mv4_ragged_sharp', 'pair_small_ragged', 'mv5_28l_96'):
+        meta, ref = load_case(name)
+        sd, data = case_inputs(meta)
+        pkg.set_math_mode(3)
+        try:
+            lib.mvm_debug_set_score_kernel(0)
+            simt = run_ours(meta, sd, data)
+            lib.mvm_debug_set_score_kernel(1)
+            tcs = run_ours(meta, sd, data)
+        finally:
+            lib.mvm_debug_set_score_kernel(1)
+        rep = compare_matcher_outputs(simt, tcs, tau=2e-3, score_tol=(1e-3 if 'sharp' in name else 3e-4, 3e-5))
+        print(name, rep)
