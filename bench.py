@@ -227,6 +227,7 @@ def main():
     from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
     from e2e_multi_view_matching_b200.pipeline import MultiViewPipeline, pose_auc
     from e2e_multi_view_matching_b200.synthetic import make_state_dict, make_scene_tuple_inputs
+    from e2e_multi_view_matching_b200 import sharding
 
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -245,7 +246,7 @@ def main():
     pipe = MultiViewPipeline(model)
 
     # tuples 1000 + (rank*B + k): every rank works on its own shard (weak scaling, no data-path collective)
-    data_np = make_scene_tuple_inputs(1000 + rank * B, T_VIEWS, N_KPTS, batch=B)
+    data_np = make_scene_tuple_inputs(sharding.tuple_shard(rank, world, B)[0], T_VIEWS, N_KPTS, batch=B)
     keys = [k for k, v in data_np.items() if isinstance(v, np.ndarray) and not k.startswith('image')
             and not k.startswith('landmark')]
     host = {k: torch.from_numpy(data_np[k]).pin_memory() for k in keys}
@@ -267,7 +268,7 @@ def main():
         last['res'] = res
         if world > 1:   # one scalar all-reduce per step (mirrors the val-loss all_reduce, train.py:104-106)
             loss.copy_(pose['ba_cost'][:, 1].sum().float().reshape(1))
-            dist.all_reduce(loss)
+            sharding.all_reduce_step_loss(loss)
         return pose
 
     # End-to-end step through the public API.  Every step's inputs come from pinned host memory: the copy of
@@ -298,7 +299,7 @@ def main():
         out_host['T_pair'].copy_(pose['T_pair'], non_blocking=True)
         if world > 1:
             loss.copy_(pose['ba_cost'][:, 1].sum().float().reshape(1))
-            dist.all_reduce(loss)
+            sharding.all_reduce_step_loss(loss)
         return pose
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -321,10 +322,7 @@ def main():
         per_step = [a.elapsed_time(b) for a, b in evs]
         last['per_step_ms'] = per_step
         ms = sum(per_step)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), wall
+        return sharding.max_over_ranks(ms, dev), wall
 
     for _ in range(args.warmup):
         step_device()
@@ -367,7 +365,7 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         total_tuples = B * args.steps * world
-        value = total_tuples / (ms_dev * 1e-3)
+        value = sharding.whole_job_throughput(B, args.steps, world, ms_dev)
         e2e = total_tuples / (ms_e2e * 1e-3)
         traffic_att, traffic_sink = load_traffic(B)
         att_ms, att_n = prof['attention']

@@ -1,0 +1,52 @@
+"""CPU, world_size 2 over gloo: the host logic of the multi-GPU path (tuple shards, the per-step scalar
+all-reduce, max-over-ranks timing) and bench.py's reference arm under a process group (rank 0 alone works)."""
+import os
+import subprocess
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from e2e_multi_view_matching_b200 import sharding
+    ids = sharding.tuple_shard(rank, world, 14)
+    loss = sharding.all_reduce_step_loss(torch.tensor([float(rank + 1)]))
+    mx = sharding.max_over_ranks(10.0 + rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, ids)
+    if rank == 0:
+        flat = [i for g in gathered for i in g]
+        assert flat == list(range(1000, 1000 + 14 * world)), flat          # disjoint, contiguous, complete
+        assert loss.item() == sum(range(1, world + 1))
+        assert mx == 10.0 + world - 1
+        assert sharding.whole_job_throughput(14, 10, world, 1000.0) == 14 * 10 * world
+        open(out, 'w').write('ok')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shards_and_collectives_world2(tmp_path):
+    out = str(tmp_path / 'ok.txt')
+    mp.spawn(_worker, args=(2, 29531, out), nprocs=2, join=True)
+    assert open(out).read() == 'ok'
+
+
+def test_no_process_group_is_a_noop():
+    from e2e_multi_view_matching_b200 import sharding
+    assert sharding.tuple_shard(0, 1, 3) == [1000, 1001, 1002]
+    assert sharding.all_reduce_step_loss(torch.tensor([2.0])).item() == 2.0
+    assert sharding.max_over_ranks(3.5) == 3.5
+
+
+def test_reference_arm_only_rank0_prints():
+    """bench.py --impl reference under torchrun-style env vars: ranks > 0 exit 0 without work or output."""
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1', MASTER_ADDR='127.0.0.1', MASTER_PORT='29532')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
+                        '--warmup', '0'], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == '', (r.returncode, r.stdout[-200:], r.stderr[-300:])
