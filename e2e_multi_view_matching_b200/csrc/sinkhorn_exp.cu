@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
           if (a > ABSORB_HI || a < ABSORB_LO) {
             float* kr = Ks + (size_t)r * n;
             for (int j = lane; j < n; j += 32) kr[j] *= a;
+            __syncwarp();        // every lane has read a_s[r] before lane 0 resets it (racecheck)
             if (lane == 0) { ut_s[r] += logf(a); e_s[r] *= a; a_s[r] = 1.f; }
           }
         }
