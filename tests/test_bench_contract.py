@@ -1,0 +1,51 @@
+"""CPU: the committed bench lines carry every key of the bench contract, and bench.py parses without a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+REQUIRED = ['metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+            'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline']
+
+
+def _load(name):
+    return json.load(open(os.path.join(ROOT, 'profiles', name)))
+
+
+def test_own_arm_line_has_the_contract_keys():
+    d = _load('bench_r01_v32.json')
+    for k in REQUIRED + ['cpu_baseline']:
+        assert k in d, k
+    base = json.load(open(os.path.join(ROOT, 'BASELINE.json')))
+    assert d['metric'] in base['metric'] and d['unit'] == 'tuples/s' and d['higher_is_better'] is True
+    assert d['scaling'] == 'weak' and d['vs_baseline'] is None and d['data'] == 'synthetic'
+    assert 'workload' in d['config'] and 'model' not in d['config']
+    assert d['warmup'] >= 3 and d['gpu_launches'] > 0
+    e = d['e2e']
+    assert e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] > 0 and e['value'] != d['value']
+    r = d['roofline']
+    for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+        assert k in r, k
+    assert r['bound'] in ('hbm', 'tensor') and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    c = d['cpu_baseline']
+    assert c['kind'] in ('reference', 'port') and c['cores'] >= 1 and c['sample']
+    assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+
+
+def test_reference_arm_line():
+    d = _load('bench_r01_v32_reference_arm.json')
+    assert d['impl'] == 'reference' and d['unit'] == 'tuples/s' and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def test_two_gpu_line_scales():
+    one, two = _load('bench_r01_v32.json'), _load('bench_r01_v31_2gpu.json')
+    assert two['n_gpus'] == 2 and two['config']['parallelism'] == 'dp2'
+    assert two['value'] > 1.7 * one['value'] * 0.95      # whole-job aggregate, weak scaling
+
+
+def test_bench_cli_parses_without_gpu():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--help'], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and '--impl' in r.stdout and '--gpus' in r.stdout
