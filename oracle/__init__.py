@@ -11,8 +11,11 @@ Parity pinning status:
   * two-view pose (oracle/pose.py): "parity unpinned" -- kornia 0.7.0 and
     pytorch3d 0.7.5 are pip-pinned third-party dependencies that are absent
     from /root/reference and from this image; their published algorithms are
-    restated, the reference's own call sites are followed line by line.
+    restated, the reference's own call sites are followed line by line;
+    cross-checked against OpenCV 4.13 (tests/test_pose_oracle_opencv.py).
   * multi-view BA (oracle/mvba.py): pinned on the reference's own gtest
     known-answer scenes (test_ba_problem.cpp:165-184); Ceres itself is absent
     ("parity unpinned" against Ceres' exact iterates).
+  * ba_initializer (oracle/ba_init.py): pinned on the reference's gtest scene
+    (test_ba_init.cpp:93-274); "parity unpinned" against Theia's exact iterates.
 """

@@ -5,7 +5,9 @@ pytorch3d==0.7.5 (requirements.txt:36) are pip-pinned dependencies that are abse
 /root/reference and from this image, so ``estimate_relative_pose.py`` and
 ``bundle_adjust_gauss_newton_2_view.py`` cannot be imported here.  Their published algorithms
 are restated below (function docstrings name the upstream function); the reference's OWN
-code (call sites, weighting, LM schedule) is followed line by line and cited.
+code (call sites, weighting, LM schedule) is followed line by line and cited.  The geometric
+primitives are cross-checked against OpenCV 4.13 (present in the image; cv2.triangulatePoints is
+also what the reference calls) by tests/test_pose_oracle_opencv.py.
 
 fp32 everywhere the reference is fp32 (``dtype=np.float32``); set ``dtype=np.float64`` to get
 the same algorithm in double (used to judge which of two fp32 answers is closer to the truth).
