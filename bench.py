@@ -166,6 +166,39 @@ def cpu_reference_tuple(sd, data_np, cap2=128, cap_ba=32):
     return t1 - t0, t2 - t1, n_ok
 
 
+def torch_gpu_port(sd, data_np, dev, B, stage_ms):
+    import torch
+    from oracle.matcher_torch import matcher_forward
+    nb = min(B, 4)                                      # the port materialises prob[B,4,N,4N]: keep the batch small
+    data = {k: (v[:nb] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == B else v) for k, v in data_np.items()
+            if not k.startswith('landmark') and not k.startswith('pose')}
+    data = {k: (torch.empty(v.shape, device='meta') if k.startswith('image') else torch.from_numpy(v).to(dev))
+            if isinstance(v, np.ndarray) else v for k, v in data.items()}
+    out = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for name, tf32 in (('tf32_allowed', True), ('fp32', False)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(2):
+                matcher_forward(sd, {'GNN_layers': LAYERS}, data, device=dev, to_numpy=False)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                matcher_forward(sd, {'GNN_layers': LAYERS}, data, device=dev, to_numpy=False)
+            e1.record()
+            torch.cuda.synchronize()
+            out['matcher_tuples_per_s_' + name] = 3 * nb / (e0.elapsed_time(e1) * 1e-3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    ours = sum(stage_ms.get(k, 0.0) for k in ('gemm', 'attention', 'sinkhorn', 'score_gemm', 'match', 'conf', 'kenc'))
+    out['ours_matcher_tuples_per_s'] = B / (ours * 1e-3)
+    out['note'] = ('torch port of the reference matcher (oracle/matcher_torch.py) in eager stock PyTorch on the same GPU, '
+                   'batch %d; matcher only; tf32_allowed = torch 1.10 defaults' % nb)
+    return out
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -207,6 +240,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--tuples', type=int, default=14, help='tuples per step per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-torch-gpu', action='store_true', help='skip the informational stock-PyTorch-on-GPU matcher line')
     ap.add_argument('--gemm-tile', type=int, default=256, choices=[128, 256])
     ap.add_argument('--gemm-kernel', default='persistent', choices=['persistent', 'tile'],
                     help='3xTF32 GEMM kernel: persistent (default) or the one-tile-per-CTA kernel (A/B comparison)')
@@ -421,6 +455,14 @@ def main():
                     v = m[i] >= 0
                     hits += int((la[i][v] == lb[i][m[i][v]]).sum()); tot += int(v.sum())
         line['match_precision'] = round(hits / max(tot, 1), 4)
+        if world == 1 and not args.no_torch_gpu:
+            # informational: the op-for-op torch port of the reference matcher run by stock PyTorch (cuBLAS / cuDNN
+            # eager) on the same GPU -- what a user of the reference gets by moving its model to the B200.  Matcher
+            # only (the reference's pose stage is CPU code); our matcher-only rate from the stage timers beside it.
+            try:
+                line['torch_gpu_port'] = torch_gpu_port(sd, data_np, dev, B, stage_ms)
+            except Exception as e:                                  # never let the extra line break the bench
+                line['torch_gpu_port'] = {'error': repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             t_m, t_p, n_ok = cpu_reference_tuple(sd, data_np)
             line['cpu_baseline'] = {

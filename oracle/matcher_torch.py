@@ -1,4 +1,5 @@
-"""torch-CPU restatement of the reference matcher forward (eval mode), op for op.
+"""torch restatement of the reference matcher forward (eval mode), op for op (CPU by default; `device=` runs the
+same stock-PyTorch ops on a GPU for bench.py's informational "torch_gpu_port" line).
 
 TEST INFRASTRUCTURE ONLY.  Same functions as oracle/matcher.py (numpy) but written with the torch
 ops the reference itself calls (F.conv1d, einsum, softmax, logsumexp), so that the CPU baseline of
@@ -69,13 +70,16 @@ def _log_optimal_transport(scores, alpha, iters):
     return Z + u.unsqueeze(2) + v.unsqueeze(1) - norm
 
 
-def matcher_forward(sd_np, config, data_np):
+def matcher_forward(sd_np, config, data_np, device=None, to_numpy=True):
     """MultiViewMatcher.forward (eval, multi_frame_matching=True branch or pairwise) -> numpy dict."""
-    sd = _t(sd_np)
+    dev = torch.device(device) if device is not None else torch.device('cpu')
+    sd = {k: v.to(dev) for k, v in _t(sd_np).items()}
+    out = (lambda t: t.cpu().numpy()) if to_numpy else (lambda t: t)
     names = config['GNN_layers']
     multi = config.get('multi_frame_matching', True)
     iters = config.get('sinkhorn_iterations', 100)
-    data = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
+    data = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else (v.to(dev) if torch.is_tensor(v) and not v.is_meta else v))
+            for k, v in data_np.items()}
     T = len(data['ids'])
     res = {}
     with torch.no_grad():
@@ -91,8 +95,8 @@ def matcher_forward(sd_np, config, data_np):
             sc = _log_optimal_transport(sc, sd['bin_score'], iters)
             max0, max1 = sc[:, :-1, :-1].max(2), sc[:, :-1, :-1].max(1)
             i0, i1 = max0.indices, max1.indices
-            ar0 = torch.arange(i0.shape[1])[None]
-            ar1 = torch.arange(i1.shape[1])[None]
+            ar0 = torch.arange(i0.shape[1], device=dev)[None]
+            ar1 = torch.arange(i1.shape[1], device=dev)[None]
             mut0 = ar0 == i1.gather(1, i0)
             mut1 = ar1 == i0.gather(1, i1)
             zero = sc.new_tensor(0)
@@ -102,18 +106,18 @@ def matcher_forward(sd_np, config, data_np):
             v1 = mut1 & v0.gather(1, i1)
             i0 = torch.where(v0, i0, i0.new_tensor(-1))
             i1 = torch.where(v1, i1, i1.new_tensor(-1))
-            bi = torch.arange(i0.shape[0]).unsqueeze(-1).repeat(1, i0.shape[-1])
-            add = sc[bi, torch.arange(i0.shape[-1]), i0].unsqueeze(-2)
+            bi = torch.arange(i0.shape[0], device=dev).unsqueeze(-1).repeat(1, i0.shape[-1])
+            add = sc[bi, torch.arange(i0.shape[-1], device=dev), i0].unsqueeze(-2)
             g1 = m1.transpose(-2, -1)[bi, i0].transpose(-2, -1)
             of = _mlp(sd, 'conf_mlp.layers_f', [512, 512, 256], torch.cat([m0, g1], -2), last_layer=False)
             oc = _mlp(sd, 'conf_mlp.layers_c', [1, 256, 256], add, last_layer=False)
             conf = torch.sigmoid(_mlp(sd, 'conf_mlp.layers', [256, 1], of + oc)).transpose(-2, -1)
-            res['matches%d_%d_%d' % (a, a, b)] = i0.numpy()
-            res['matches%d_%d_%d' % (b, a, b)] = i1.numpy()
-            res['matching_scores%d_%d_%d' % (a, a, b)] = ms0.numpy()
-            res['matching_scores%d_%d_%d' % (b, a, b)] = ms1.numpy()
-            res['scores_%d_%d' % (a, b)] = sc.numpy()
-            res['conf_scores_%d_%d' % (a, b)] = conf.numpy()
+            res['matches%d_%d_%d' % (a, a, b)] = out(i0)
+            res['matches%d_%d_%d' % (b, a, b)] = out(i1)
+            res['matching_scores%d_%d_%d' % (a, a, b)] = out(ms0)
+            res['matching_scores%d_%d_%d' % (b, a, b)] = out(ms1)
+            res['scores_%d_%d' % (a, b)] = out(sc)
+            res['conf_scores_%d_%d' % (a, b)] = out(conf)
 
         if multi:
             desc = [kenc(i, 'image0') for i in range(T)]
