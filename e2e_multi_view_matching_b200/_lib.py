@@ -91,6 +91,10 @@ def lib():
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp]
+    L.mvm_log_optimal_transport_ex.restype = C.c_int
+    L.mvm_log_optimal_transport_ex.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, C.c_int, _fp]
+    L.mvm_sinkhorn_max_active_clusters.restype = C.c_int
+    L.mvm_sinkhorn_max_active_clusters.argtypes = [C.c_int, C.c_int]
     L.mvm_extract_matches.restype = C.c_int
     L.mvm_extract_matches.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp,
                                       _fp, _fp, _fp]

@@ -150,13 +150,10 @@ int launch_attention_simt(const float* qkv, float* out, int batch, int n_pad, At
   MvmProfScope prof__(MVM_TAG_ATTN, stream);
   MVM_REQUIRE(n_pad % BQ == 0 && segs.n_views >= 1 && segs.n_views <= 8);
   MVM_REQUIRE(!is_cross || segs.n_views >= 2);
-  static bool attr_set = false;
   const int smem_bytes = SMEM_FLOATS * (int)sizeof(float);
-  if (!attr_set) {
-    cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         smem_bytes);
-    attr_set = true;
-  }
+  mvm_once_per_device(MVM_ONCE_ATTN_SIMT, [&] {
+    cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  });
   dim3 grid(n_pad / BQ, 4, batch * segs.n_views);
   attention_simt_kernel<<<grid, 256, smem_bytes, stream>>>(qkv, out, n_pad, segs, is_cross);
   MVM_CHECK_LAUNCH();

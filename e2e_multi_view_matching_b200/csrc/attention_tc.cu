@@ -462,11 +462,9 @@ template <int NPASS>
 int launch_attn(const float* qkv, const float* vt, const float* klo, const float* vtlo, float* out, int batch, int n_pad,
                 const AttnSegs& segs, int is_cross, cudaStream_t stream) {
   using C_ = ACfg<NPASS>;
-  static bool attr = false;
-  if (!attr) {
+  mvm_once_per_device(MVM_ONCE_ATTN_TC + 16 * (NPASS == 3), [&] {
     cudaFuncSetAttribute(attention_tc_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
-    attr = true;
-  }
+  });
   const int V = batch * segs.n_views;
   const long long rows = (long long)V * n_pad;
   const CUtensorMap* tK = mvm_get_tmap_2d(qkv, rows, 768, 768, BKV);

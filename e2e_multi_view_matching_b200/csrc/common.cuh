@@ -43,6 +43,25 @@ struct MvmProfScope {
 
 static inline int mvm_div_up(int a, int b) { return (a + b - 1) / b; }
 
+// ---- per-device state (profile.cu) -------------------------------------------------------
+// Function attributes (opt-in shared memory, cluster size) and the SM count are PER DEVICE: a process may
+// drive several GPUs (nn.DataParallel, model.to('cuda:1')) from several threads.  mvm_dev_info() describes
+// the CURRENT device; mvm_once_per_device(slot, f) runs f exactly once per (device, slot) under a mutex.
+#include <mutex>
+struct MvmDevInfo { int dev; int n_sm; size_t max_smem; };
+const MvmDevInfo& mvm_dev_info();
+std::mutex& mvm_attr_mutex();
+bool* mvm_attr_flag(int slot);   // flag of (current device, slot); call with mvm_attr_mutex() held
+enum MvmOnceSlot { MVM_ONCE_SINKHORN_CL = 0, MVM_ONCE_SINKHORN_EXP, MVM_ONCE_SINKHORN_LOG, MVM_ONCE_ATTN_TC,
+                   MVM_ONCE_ATTN_SIMT, MVM_ONCE_GEMM_TC, MVM_ONCE_GEMM_PERSIST, MVM_ONCE_GEMM_SCORE, MVM_ONCE_KENC,
+                   MVM_ONCE_MVBA, MVM_N_ONCE = 32 };
+template <class F>
+static inline void mvm_once_per_device(int slot, F&& f) {
+  std::lock_guard<std::mutex> g(mvm_attr_mutex());
+  bool* fl = mvm_attr_flag(slot);
+  if (!*fl) { f(); *fl = true; }
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -258,11 +258,8 @@ std::mutex g_tmap_mu;
 template <int BN, int NPASS, bool PRE>
 int launch_cfg(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO, cudaStream_t stream) {
   using C_ = Cfg<BN, NPASS>;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
-    attr = true;
-  }
+  // cheap and idempotent: set on every launch (per-device attribute; 12 template instances)
+  cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
   const CUtensorMap* tA = mvm_get_tmap_2d(d.A, d.M, d.K1, d.lda, BM);
   const CUtensorMap* tA2 = d.A2 ? mvm_get_tmap_2d(d.A2, d.M, d.K - d.K1, d.lda2, BM) : tA;
   const CUtensorMap* tW = mvm_get_tmap_2d(PRE ? d.Whi : d.W, d.N, d.K, d.ldw, BN);

@@ -348,15 +348,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 // K1 % 32 == 0, 16-byte aligned rows.
 int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO,
                            cudaStream_t stream) {
-  static bool attr = false;
-  static int n_sm = 0;
-  if (!attr) {
+  mvm_once_per_device(MVM_ONCE_GEMM_PERSIST, [&] {
     cudaFuncSetAttribute(gemm_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    attr = true;
-  }
+  });
+  const int n_sm = mvm_dev_info().n_sm;
   const CUtensorMap* tA = mvm_get_tmap_2d(d.A, d.M, d.K1, d.lda, BM);
   const CUtensorMap* tA2 = d.A2 ? mvm_get_tmap_2d(d.A2, d.M, d.K - d.K1, d.lda2, BM) : tA;
   const CUtensorMap* tWhi = mvm_get_tmap_2d(d.Whi, d.N, d.K, d.ldw, BN);
@@ -398,15 +393,10 @@ __global__ void split_planes_kernel(const float4* __restrict__ x, float4* __rest
 int launch_score_gemm_tc(const float* mdesc, float* hi, float* lo, int n_pad, const PairTable& tab, int batch,
                          float alpha, cudaStream_t stream) {
   MvmProfScope prof__(MVM_TAG_SCORE, stream);
-  static bool attr = false;
-  static int n_sm = 0;
-  if (!attr) {
+  mvm_once_per_device(MVM_ONCE_GEMM_SCORE, [&] {
     cudaFuncSetAttribute(gemm_tc_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    attr = true;
-  }
+  });
+  const int n_sm = mvm_dev_info().n_sm;
   const long long rows = (long long)batch * tab.n_views * n_pad;
   split_planes_kernel<<<n_sm * 4, 256, 0, stream>>>(reinterpret_cast<const float4*>(mdesc), reinterpret_cast<float4*>(hi),
                                                     reinterpret_cast<float4*>(lo), rows * 256 / 4);

@@ -133,11 +133,9 @@ int launch_kenc_front(const float* kpts, const float* kscores, const float* cons
                       cudaStream_t stream) {
   MvmProfScope prof__(MVM_TAG_KENC, stream);
   const float scale = 0.7f * fmaxf(img_w, img_h);
-  static bool attr = false;
-  if (!attr) {
+  mvm_once_per_device(MVM_ONCE_KENC, [&] {
     cudaFuncSetAttribute(kenc_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KENC_SMEM);
-    attr = true;
-  }
+  });
   kenc_front_kernel<<<mvm_div_up(n_points, PTS), 256, KENC_SMEM, stream>>>(
       kpts, kscores, w[0], b[0], w[1], b[1], w[2], b[2], h3, n_points, img_w * 0.5f, img_h * 0.5f,
       scale);

@@ -56,8 +56,17 @@ int launch_score_gemm_simt(const float* mdesc, int n_pad, const PairTable& tab, 
 
 int launch_sinkhorn_ref(const SinkhornTable& tab, int batch, float bin_score, int iters,
                         float* ws, cudaStream_t stream);
+// production dispatch (sinkhorn_exp.cu): cluster kernel up to 1024 x 1024, multi-CTA kernel beyond;
+// variant 0 = automatic, 1 = multi-CTA kernel, 2 = cluster kernel
 int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
-                    cudaStream_t stream);
+                    cudaStream_t stream, int variant = 0);
+int launch_sinkhorn_multicta(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
+                             cudaStream_t stream);
+// one thread-block cluster per problem (sinkhorn_cl.cu)
+int sinkhorn_cluster_size(int max_m, int max_n);
+int sinkhorn_cluster_max_active(int C, int n);
+int launch_sinkhorn_cluster(const SinkhornTable& tab, int batch, float bin_score, int iters, int C,
+                            cudaStream_t stream, int rr = 0);
 int launch_sinkhorn_log(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
                         cudaStream_t stream);
 size_t sinkhorn_ws_floats(int n_pairs, int batch, int n_pad);

@@ -164,10 +164,16 @@ int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, in
       MVM_TRY(run_gemm(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), s));
       MVM_TRY(launch_attention_simt(ws.QKV, ws.MSG, batch, n_pad, segs, L.is_cross, s));
     }
-    MVM_TRY(run_gemm(make_gemm(ws.MSG, 256, L.w_merge, 256, L.b_merge, ws.MRG, 256, rows, 256, 0), s));
+    // attn.merge (superglue.py:109) is linear and feeds mlp.0 directly (:121): packing.py folds it into the
+    // message half of mlp.0 (w_merge == NULL); an unfolded weight set still runs the separate GEMM
+    const float* msg = ws.MSG;
+    if (L.w_merge) {
+      MVM_TRY(run_gemm(make_gemm(ws.MSG, 256, L.w_merge, 256, L.b_merge, ws.MRG, 256, rows, 256, 0), s));
+      msg = ws.MRG;
+    }
     {
       GemmDesc g = make_gemm(ws.X, 256, L.w_mlp0, 512, L.b_mlp0, ws.H, 512, rows, 512, 1);
-      g.A2 = ws.MRG; g.lda2 = 256; g.K1 = 256;   // cat([x, message]) by K-split
+      g.A2 = msg; g.lda2 = 256; g.K1 = 256;      // cat([x, message]) by K-split
       MVM_TRY(run_gemm(g, s));
     }
     {
@@ -265,6 +271,20 @@ int mvm_log_optimal_transport(float* scores, int batch, int m, int n, float bin_
   tab.n_pairs = 1; tab.n_views = 2; tab.a[0] = 0; tab.b[0] = 1; tab.m[0] = m; tab.n[0] = n;
   tab.scores[0] = scores; tab.ws_off[0] = 0;
   return launch_sinkhorn(tab, batch, bin_score, iters, ws, (cudaStream_t)stream);
+}
+
+int mvm_log_optimal_transport_ex(float* scores, int batch, int m, int n, float bin_score, int iters, float* ws,
+                                 int variant, void* stream) {
+  MVM_REQUIRE(scores && ws && batch >= 1 && m >= 1 && n >= 1 && variant >= 0 && variant <= 3);
+  PairTable tab;
+  tab.n_pairs = 1; tab.n_views = 2; tab.a[0] = 0; tab.b[0] = 1; tab.m[0] = m; tab.n[0] = n;
+  tab.scores[0] = scores; tab.ws_off[0] = 0;
+  return launch_sinkhorn(tab, batch, bin_score, iters, ws, (cudaStream_t)stream, variant);
+}
+
+int mvm_sinkhorn_max_active_clusters(int m, int n) {
+  const int C = sinkhorn_cluster_size(m, n);
+  return C > 0 ? sinkhorn_cluster_max_active(C, n) : 0;
 }
 
 int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_views, int n_pad,

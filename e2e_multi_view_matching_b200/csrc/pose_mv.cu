@@ -890,12 +890,7 @@ int mvm_multi_view_ba_ex(const int* pair_a, const int* pair_b, int n_views, int 
   MVM_REQUIRE(n_views >= 2 && n_views <= MVM_MAX_VIEWS && n_pairs >= 1 && n_pairs <= MVM_MAX_PAIRS);
   if (workspace_bytes < mvm_mvba_workspace_bytes(n_views, n_pairs, batch, n_pad)) return MVM_ERR_WORKSPACE;
   MvmProfScope prof__(MVM_TAG_MVBA, stream);
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int n_sm = mvm_dev_info().n_sm;
   MvbaArgs g;
   g.n_views = n_views; g.n_pairs = n_pairs; g.batch = batch; g.n_pad = n_pad;
   for (int p = 0; p < n_pairs; ++p) { g.a[p] = pair_a[p]; g.b[p] = pair_b[p]; MVM_REQUIRE(pair_a[p] < pair_b[p]); }
@@ -913,7 +908,13 @@ int mvm_multi_view_ba_ex(const int* pair_a, const int* pair_b, int n_views, int 
   g.pscale = (double*)w; w += (size_t)batch * n_pairs * n_pad * 3 * sizeof(double);
   g.xch = (double*)w;
   cudaMemsetAsync(g.ctrs, 0, 1024, stream);
-  mvba_kernel<<<groups * n_pairs, NT, (size_t)n_pairs * NPART * sizeof(double), stream>>>(g);
+  // the CTAs of a group spin on a software barrier: launch cooperatively so that co-residency of the whole
+  // grid is guaranteed by the driver (fails with an error instead of deadlocking when it cannot be)
+  {
+    void* kargs[] = {(void*)&g};
+    cudaLaunchCooperativeKernel((const void*)mvba_kernel, dim3(groups * n_pairs), dim3(NT), kargs,
+                                (size_t)n_pairs * NPART * sizeof(double), stream);
+  }
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }

@@ -26,6 +26,41 @@ MvmProfScope::~MvmProfScope() {
   if (idx_ >= 0) cudaEventRecord(g_recs[idx_].b, s_);
 }
 
+// ---- per-device info / once-per-device function attributes (common.cuh) ------------------------
+namespace {
+constexpr int kMaxDev = 64;
+std::mutex g_attr_mutex;
+bool g_attr_done[kMaxDev][MVM_N_ONCE];
+MvmDevInfo g_dev[kMaxDev];
+bool g_dev_init[kMaxDev];
+}  // namespace
+
+std::mutex& mvm_attr_mutex() { return g_attr_mutex; }
+bool* mvm_attr_flag(int slot) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return &g_attr_done[dev % kMaxDev][slot];
+}
+const MvmDevInfo& mvm_dev_info() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev %= kMaxDev;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  if (!g_dev_init[dev]) {
+    MvmDevInfo d;
+    d.dev = dev;
+    d.n_sm = 0;
+    cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    d.max_smem = (size_t)optin;
+    g_dev[dev] = d;
+    g_dev_init[dev] = true;
+  }
+  return g_dev[dev];
+}
+
 extern "C" {
 
 unsigned long long mvm_launch_count(void) { return g_mvm_launches; }

@@ -245,17 +245,11 @@ int launch_sinkhorn_log(const SinkhornTable& tab, int batch, float bin_score, in
                         cudaStream_t stream) {
   MvmProfScope prof__(MVM_TAG_SINKHORN, stream);
   MVM_REQUIRE(tab.n_pairs >= 1 && tab.n_pairs <= MVM_MAX_PAIRS && batch >= 1);
-  static int n_sm = 0;
-  static size_t max_smem = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    int optin = 0;
-    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    max_smem = (size_t)optin;
-    cudaFuncSetAttribute(sinkhorn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  }
+  const int n_sm = mvm_dev_info().n_sm;
+  const size_t max_smem = mvm_dev_info().max_smem;
+  mvm_once_per_device(MVM_ONCE_SINKHORN_LOG, [&] {
+    cudaFuncSetAttribute(sinkhorn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+  });
   int max_m = 0, max_n = 0;
   size_t max_mn = 0;
   for (int p = 0; p < tab.n_pairs; ++p) {
@@ -277,7 +271,7 @@ int launch_sinkhorn_log(const SinkhornTable& tab, int batch, float bin_score, in
   };
   int g_min = 1;
   while (g_min <= n_sm && smem_need(g_min) > max_smem - 1024) ++g_min;
-  MVM_REQUIRE(g_min <= n_sm);
+  MVM_REQUIRE(g_min <= n_sm && n_sm <= 192);
   int NG = n_sm / g_min;
   if (NG > n_prob) NG = n_prob;
   const int rounds = (n_prob + NG - 1) / NG;
@@ -293,14 +287,19 @@ int launch_sinkhorn_log(const SinkhornTable& tab, int batch, float bin_score, in
   float* xch = ws + 256;
   cudaMemsetAsync(ctrs, 0, 256 * sizeof(float), stream);
   const size_t smem = smem_need(G);
-  sinkhorn_smem_kernel<<<G * NG, 1024, smem, stream>>>(tab, cfg, xch, ctrs);
+  {
+    // software group barriers inside: cooperative launch = co-residency guaranteed or an error, never a hang
+    void* kargs[] = {(void*)const_cast<SinkhornTable*>(&tab), (void*)&cfg, (void*)&xch, (void*)&ctrs};
+    cudaLaunchCooperativeKernel((const void*)sinkhorn_smem_kernel, dim3(G * NG), dim3(1024), kargs, smem, stream);
+  }
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }
 
 size_t sinkhorn_ws_floats(int n_pairs, int batch, int n_pad) {
   // counters + worst-case exchange ((2G+1)(n+1) per group, G*NG <= 148) and the v1 (u,v) scratch
-  const size_t xch = 256 + (size_t)(2 * 148 + 148) * (n_pad + 1) * 2;   // log-domain partials / 8-byte LL words
+  // (sized for up to 192 SMs; the launchers check the real SM count against this bound)
+  const size_t xch = 256 + (size_t)(2 * 192 + 192) * (n_pad + 1) * 2;   // log-domain partials / 8-byte LL words
   const size_t uv = (size_t)n_pairs * batch * (2 * (size_t)n_pad + 2);
   return xch > uv ? xch : uv;
 }

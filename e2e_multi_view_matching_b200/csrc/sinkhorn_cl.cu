@@ -1,0 +1,479 @@
+// Production Sinkhorn for problems up to 1024 x 1024: one thread-block CLUSTER per assignment problem.
+//
+// Same fixed point and the same 100 iterations as log_optimal_transport / log_sinkhorn_iterations
+// (superglue.py:143-172) in the stabilised scaling domain of sinkhorn_exp.cu:
+//
+//   K~_ij = exp(Z_ij + u~_i + v~_j)        evaluated once (and on the rare re-absorptions)
+//   row:  a_i = mu_i / sum_j K~_ij b_j     <=>  u_i = log_mu_i - LSE_j(Z_ij + v_j),  u = u~ + log a
+//   col:  b_j = nu_j / sum_i K~_ij a_i     <=>  v_j = log_nu_j - LSE_i(Z_ij + u_i),  v = v~ + log b
+//
+// What is different from sinkhorn_exp.cu (software group barrier through L2, 11 us per iteration):
+//   * the C CTAs of a problem are a hardware cluster (C = 16 for 513..1024 rows: non-portable size,
+//     gang-scheduled by the hardware, so there is no co-residency assumption and nothing to deadlock);
+//   * CTA c keeps rows [c*R, (c+1)*R), R <= 64, of K~ ON CHIP: every warp owns a 16 x 128 tile, RR rows of
+//     it in REGISTERS (float4 per lane) and 16 - RR rows in shared memory, so an iteration streams only
+//     (16-RR)/16 of the slab from shared memory, with 128-bit conflict-free accesses;
+//   * row sums: transposed 16-value warp reduction (16 shuffles) + 8 strip partials per row in shared memory;
+//     column sums: 4 row-group partials per column in shared memory, then the CTA's partial of column j is
+//     PUSHED into the shared memory of the CTA that owns column j (st.shared::cluster), one
+//     barrier.cluster, the owner adds the C partials in rank order (deterministic), divides, and pushes
+//     b_j into every CTA's copy of b, second barrier.cluster.  4 KB of DSMEM traffic per CTA and iteration.
+//   * dustbin row / column are rank-1 and never stored (as before).
+// The raw scores stay in the output buffer (L2) until the final pass rewrites them as Z + u + v - norm.
+// TMA is not applicable to the staging: the reference's [m+1, n+1] fp32 layout has a 4*(n+1)-byte row pitch,
+// which is not a multiple of 16 bytes for n = 1024 (tensor maps and bulk copies need 16-byte pitch/alignment).
+#include "common.cuh"
+#include "kernels.cuh"
+
+extern long long* g_sink_timing;   // sinkhorn_exp.cu (mvm_debug_set_sinkhorn_timing)
+
+namespace {
+
+constexpr float ABSORB_HI = 2980.958f;     // e^8
+constexpr float ABSORB_LO = 3.3546263e-4f; // e^-8
+constexpr int CL_ROWS = 64;                // rows of K~ per CTA
+constexpr int CL_MAXN = 1024;              // columns
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned saddr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(unsigned addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+struct OpSum { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
+struct OpMax { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+
+// 16 values per lane, reduced over the 32 lanes in 16 shuffles; afterwards every lane holds the total of
+// value index row16(lane) (lanes 2k and 2k+1 hold the same value).
+template <class Op>
+__device__ __forceinline__ float reduce16(float (&p)[16], int lane, Op op) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool hi = lane & 16;
+    const float send = hi ? p[k] : p[k + 8], keep = hi ? p[k + 8] : p[k];
+    p[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool hi = lane & 8;
+    const float send = hi ? p[k] : p[k + 4], keep = hi ? p[k + 4] : p[k];
+    p[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool hi = lane & 4;
+    const float send = hi ? p[k] : p[k + 2], keep = hi ? p[k + 2] : p[k];
+    p[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+  {
+    const bool hi = lane & 2;
+    const float send = hi ? p[0] : p[1], keep = hi ? p[1] : p[0];
+    p[0] = op(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+  }
+  return op(p[0], __shfl_xor_sync(0xffffffffu, p[0], 1));
+}
+__device__ __forceinline__ int row16(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+// b_j of the thread's four columns; 1 beyond the last column (K~ is 0 there)
+__device__ __forceinline__ float4 load_b4(const float* b_s, int col0, int n) {
+  float4 b4 = *reinterpret_cast<const float4*>(b_s + col0);
+  if (col0 + 0 >= n) b4.x = 1.f;
+  if (col0 + 1 >= n) b4.y = 1.f;
+  if (col0 + 2 >= n) b4.z = 1.f;
+  if (col0 + 3 >= n) b4.w = 1.f;
+  return b4;
+}
+
+struct SinkClCfg {
+  int C, batch, iters;
+  float alpha;
+  long long* timing;   // optional [6] cycle counters of thread 0 of CTA 0 (TIMING instance only), or null
+};
+
+// shared-memory carve (floats): fixed-size vectors at compile-time offsets (no registers spent on pointers),
+// the K~ rows last with the per-problem row stride LD = round_up(n, 128); identical in every CTA of a cluster
+constexpr int CL_VEC = CL_MAXN + 4;
+constexpr int OFF_B = 0;                              // [n+1]  column scalings b_j
+constexpr int OFF_KB = OFF_B + CL_VEC;                // [n+1]  exp(v~_j): dustbin row of K~ (u~_m = -alpha)
+constexpr int OFF_VT = OFF_KB + CL_VEC;               // [n+1]  absorbed column potentials v~_j
+constexpr int OFF_COLPART = OFF_VT + CL_VEC;          // [4][1024] column partials of the 4 row groups
+constexpr int OFF_CRECV = OFF_COLPART + 4 * CL_MAXN;  // [C][CS] partials pushed by the peers for my column slice
+constexpr int OFF_ROWPART = OFF_CRECV + CL_MAXN + 4 + 16;   // [8][64] row partials of the 8 column strips
+constexpr int OFF_A = OFF_ROWPART + 8 * CL_ROWS;      // [64] row scalings a_i, a[64] = dustbin row
+constexpr int OFF_UT = OFF_A + CL_ROWS + 4;           // [64] absorbed row potentials u~_i
+constexpr int OFF_E = OFF_UT + CL_ROWS;               // [64] exp(alpha + u~_i): dustbin column of K~ / kb_n
+constexpr int OFF_EA = OFF_E + CL_ROWS;               // [64] e_i a_i (dustbin column terms; 0 beyond the CTA's rows)
+constexpr int OFF_AW = OFF_EA + CL_ROWS;              // [32][16] per-warp copy of the row scalings of its row group
+constexpr int OFF_KS = OFF_AW + 32 * 16;              // [4][16-RR][LD]
+static_assert(OFF_KS % 4 == 0 && OFF_A % 4 == 0 && OFF_COLPART % 4 == 0, "16-byte alignment of the float4 regions");
+inline size_t cl_smem_bytes(int n, int RS) { return (size_t)(OFF_KS + 4 * RS * ((n + 127) & ~127)) * sizeof(float); }
+
+template <int RR, bool TIMING>
+__global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, SinkClCfg cfg) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int RS = 16 - RR;
+  const int C = cfg.C;
+  const unsigned c = cluster_ctarank();
+  const int prob = blockIdx.x / C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rg = warp >> 3, cw = warp & 7;
+  const float alpha = cfg.alpha;
+
+  const int p = prob / cfg.batch, bi = prob % cfg.batch;
+  const int m = tab.m[p], n = tab.n[p];
+  const int ld = n + 1;
+  float* Zg = tab.scores[p] + (long long)bi * (m + 1) * ld;
+  const int R = (m + C - 1) / C;
+  const int r0 = min(m, (int)c * R), nrows = min(m, r0 + R) - r0;
+  const int LD = (n + 127) & ~127, CS = (n + 1 + C - 1) / C;
+  const bool active = cw * 128 < n;
+  const int col0 = cw * 128 + lane * 4;
+
+  float* const b_s = smem + OFF_B;
+  float* const kb_s = smem + OFF_KB;
+  float* const vt_s = smem + OFF_VT;
+  float* const colpart = smem + OFF_COLPART;
+  float* const crecv = smem + OFF_CRECV;
+  float* const rowpart = smem + OFF_ROWPART;
+  float* const a_s = smem + OFF_A;
+  float* const ut_s = smem + OFF_UT;
+  float* const e_s = smem + OFF_E;
+  float* const ea_s = smem + OFF_EA;
+  float* const aw_s = smem + OFF_AW;
+  float* const ksm = smem + OFF_KS + (size_t)rg * RS * LD + col0;   // this thread's shared-memory rows (i >= RR)
+
+  const float mu = 1.0f / (float)(m + n), mu_bin = (float)n / (float)(m + n);
+  const float nu = mu, nu_bin = (float)m / (float)(m + n);
+  const float norm = -logf((float)(m + n));
+
+  float4 kreg[RR];
+#define K_GET(i) ((i) < RR ? kreg[(i) < RR ? (i) : 0] : *reinterpret_cast<const float4*>(ksm + ((i) - RR) * LD))
+#define K_PUT(i, v)                                                              \
+  do {                                                                           \
+    if ((i) < RR) kreg[(i) < RR ? (i) : 0] = (v);                                \
+    else *reinterpret_cast<float4*>(ksm + ((i) - RR) * LD) = (v);                \
+  } while (0)
+
+  // ---- init: u~_i = -max(rowmax_i, alpha), v~ = 0, b = 1; K~ = exp(Z + u~) <= 1 ----
+  {
+    float part[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int row = rg * 16 + i;
+      float mx = -3.0e38f;
+      if (active && row < nrows) {
+        const float* zr = Zg + (long long)(r0 + row) * ld + col0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (col0 + k < n) mx = fmaxf(mx, zr[k]);
+      }
+      part[i] = mx;
+    }
+    const float v = reduce16(part, lane, OpMax());
+    if (!(lane & 1)) rowpart[cw * CL_ROWS + rg * 16 + row16(lane)] = v;
+  }
+  for (int j = tid; j < CL_VEC; j += blockDim.x) { b_s[j] = 1.f; vt_s[j] = 0.f; kb_s[j] = 1.f; }
+  __syncthreads();
+  if (tid < CL_ROWS) {
+    float mx = alpha;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) mx = fmaxf(mx, rowpart[s * CL_ROWS + tid]);
+    ut_s[tid] = -mx;
+    e_s[tid] = tid < nrows ? __expf(alpha - mx) : 0.f;
+    a_s[tid] = tid < nrows ? 1.f : 0.f;
+    ea_s[tid] = 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int row = rg * 16 + i;
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && row < nrows) {
+      const float* zr = Zg + (long long)(r0 + row) * ld + col0;
+      const float ut = ut_s[row];
+      if (col0 + 0 < n) k4.x = __expf(zr[0] + ut);
+      if (col0 + 1 < n) k4.y = __expf(zr[1] + ut);
+      if (col0 + 2 < n) k4.z = __expf(zr[2] + ut);
+      if (col0 + 3 < n) k4.w = __expf(zr[3] + ut);
+    }
+    if (active) K_PUT(i, k4);
+  }
+  // peers' shared memory is about to be written: every CTA of the cluster must have started
+  cluster_sync_all();
+
+  const unsigned crecv_addr = smem_u32(crecv), b_addr = smem_u32(b_s);
+  unsigned tacc[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+  unsigned tprev = 0;
+  if (TIMING) tprev = (unsigned)clock();
+#define T_MARK(k)                                   \
+  do {                                              \
+    if (TIMING) {                                   \
+      const unsigned tn__ = (unsigned)clock();      \
+      tacc[k] += tn__ - tprev;                      \
+      tprev = tn__;                                 \
+    }                                               \
+  } while (0)
+
+  for (int it = 0; it < cfg.iters; ++it) {
+    // ---- row pass: partial sums of sum_j K~_ij b_j over this warp's 128-column strip ----
+    const float bin_col = kb_s[n] * b_s[n];
+    int cbad = 0;
+    if (active) {
+      const float4 b4 = load_b4(b_s, col0, n);
+      // column re-absorption is decided on the freshly merged b (identical in every CTA of the cluster)
+      cbad = (fmaxf(fmaxf(b4.x, b4.y), fmaxf(b4.z, b4.w)) > ABSORB_HI) | (fminf(fminf(b4.x, b4.y), fminf(b4.z, b4.w)) < ABSORB_LO);
+      float part[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 k = K_GET(i);
+        part[i] = fmaf(k.w, b4.w, fmaf(k.z, b4.z, fmaf(k.y, b4.y, k.x * b4.x)));
+      }
+      const float v = reduce16(part, lane, OpSum());
+      if (!(lane & 1)) rowpart[cw * CL_ROWS + rg * 16 + row16(lane)] = v;
+    }
+    if (warp == 31) {   // dustbin row (replicated in every CTA): a_m = mu_bin / sum_j kb_j b_j
+      float s = 0.f;
+      for (int j = lane; j <= n; j += 32) s = fmaf(kb_s[j], b_s[j], s);
+      s = warp_sum(s);
+      const float bn = b_s[n];
+      cbad |= (bn > ABSORB_HI) | (bn < ABSORB_LO);
+      if (lane == 0) a_s[CL_ROWS] = mu_bin / s;
+    }
+    T_MARK(0);
+    if (__syncthreads_or(cbad)) {
+      // v~_j += log b_j, K~_ij *= b_j, kb_j *= b_j, b_j = 1 (all columns); the row sums above are unchanged
+      if (active) {
+        const float4 b4 = load_b4(b_s, col0, n);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float4 k = K_GET(i);
+          k.x *= b4.x; k.y *= b4.y; k.z *= b4.z; k.w *= b4.w;
+          K_PUT(i, k);
+        }
+      }
+      for (int j = tid; j <= n; j += blockDim.x) {
+        const float bv = b_s[j];
+        vt_s[j] += logf(bv);
+        kb_s[j] *= bv;
+      }
+      __syncthreads();     // every b_s read of this iteration is done (bin_col, dustbin row, b4)
+      for (int j = tid; j <= n; j += blockDim.x) b_s[j] = 1.f;
+    }
+    T_MARK(1);
+    // ---- every warp: a_i = mu / (sum_j K~_ij b_j + e_i kb_n b_n) for the 16 rows of its row group ----
+    float a_abs = 1.f;         // scaling absorbed into u~ this iteration (book-keeping by the strip-0 warp)
+    if (active) {
+      const int rl = lane & 15, row = rg * 16 + rl;
+      float a_mine = 0.f, ea = 0.f;
+      if (row < nrows) {
+        float s = 0.f;
+        for (int q = 0; q * 128 < n; ++q) s += rowpart[q * CL_ROWS + row];
+        const float e = e_s[row];
+        a_mine = mu / (s + e * bin_col);
+        ea = e * a_mine;
+      }
+      const bool bad = row < nrows && (a_mine > ABSORB_HI || a_mine < ABSORB_LO);
+      if (__any_sync(0xffffffffu, bad)) {
+        // row re-absorption (every strip warp of the row group takes the same decision): K~ row *= a_i, a_i = 1
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float ai = __shfl_sync(0xffffffffu, a_mine, i);
+          if (__shfl_sync(0xffffffffu, (int)bad, i)) {
+            float4 k = K_GET(i);
+            k.x *= ai; k.y *= ai; k.z *= ai; k.w *= ai;
+            K_PUT(i, k);
+          }
+        }
+        if (bad) { a_abs = a_mine; a_mine = 1.f; }
+      }
+      float* aw = aw_s + warp * 16;
+      if (lane < 16) {
+        aw[lane] = a_mine;
+        if (cw == 0) { a_s[row] = a_mine; ea_s[row] = ea; }
+      }
+      __syncwarp();
+      // ---- column pass: partial c_j over this warp's 16 rows ----
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a4 = *reinterpret_cast<const float4*>(aw + q * 4);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 k = K_GET(q * 4 + t);
+          acc.x = fmaf(k.x, av[t], acc.x);
+          acc.y = fmaf(k.y, av[t], acc.y);
+          acc.z = fmaf(k.z, av[t], acc.z);
+          acc.w = fmaf(k.w, av[t], acc.w);
+        }
+      }
+      *reinterpret_cast<float4*>(colpart + rg * CL_MAXN + col0) = acc;
+    }
+    T_MARK(2);
+    __syncthreads();
+    if (cw == 0 && lane < 16 && a_abs != 1.f) {     // deferred: nobody reads e_s / ut_s before the next barrier
+      const int row = rg * 16 + lane;
+      ut_s[row] += logf(a_abs);
+      e_s[row] *= a_abs;
+    }
+    // ---- this CTA's partial of column j goes to the CTA that owns column j ----
+    for (int j = tid; j < n; j += blockDim.x) {
+      const float s = ((colpart[j] + colpart[CL_MAXN + j]) + colpart[2 * CL_MAXN + j]) + colpart[3 * CL_MAXN + j];
+      const int owner = j / CS, slot = j - owner * CS;
+      st_cluster_f32(mapa_u32(crecv_addr + (unsigned)(((int)c * CS + slot) * 4), (unsigned)owner), s);
+    }
+    if (warp == 31) {   // dustbin column: kb_n sum_i e_i a_i
+      float s = ea_s[lane] + ea_s[lane + 32];
+      s = warp_sum(s);
+      if (lane == 0) {
+        const int owner = n / CS, slot = n - owner * CS;
+        st_cluster_f32(mapa_u32(crecv_addr + (unsigned)(((int)c * CS + slot) * 4), (unsigned)owner), s * kb_s[n]);
+      }
+    }
+    T_MARK(3);
+    cluster_sync_all();
+    // ---- the owner of column j adds the C partials in rank order: b_j = nu_j / (sum_g c_j^g + kb_j a_m) ----
+    {
+      const float am = a_s[CL_ROWS];
+      for (int t = tid; t < CS; t += blockDim.x) {
+        const int j = (int)c * CS + t;
+        if (j <= n) {
+          float s = 0.f;
+          for (int g = 0; g < C; ++g) s += crecv[g * CS + t];
+          const float bj = (j < n ? nu : nu_bin) / (s + kb_s[j] * am);
+          for (int g = 0; g < C; ++g) st_cluster_f32(mapa_u32(b_addr + (unsigned)(j * 4), (unsigned)g), bj);
+        }
+      }
+    }
+    T_MARK(4);
+    cluster_sync_all();
+    T_MARK(5);
+  }
+  if (TIMING && cfg.timing && blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 6; ++i) cfg.timing[i] = (long long)tacc[i];
+#undef T_MARK
+
+  // ---- output: Z + u + v - norm with u = u~ + log a, v = v~ + log b ----
+  __syncthreads();
+  for (int j = tid; j <= n; j += blockDim.x) vt_s[j] += logf(b_s[j]);
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int row = rg * 16 + i;
+      if (row < nrows) {
+        const float u = ut_s[row] + logf(a_s[row]) - norm;
+        float* zr = Zg + (long long)(r0 + row) * ld + col0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (col0 + k < n) zr[k] = zr[k] + u + vt_s[col0 + k];
+      }
+    }
+  }
+  if (tid < nrows) Zg[(long long)(r0 + tid) * ld + n] = alpha + ut_s[tid] + logf(a_s[tid]) + vt_s[n] - norm;
+  if (c == (unsigned)(C - 1)) {
+    const float um = -alpha + logf(a_s[CL_ROWS]);     // u~_m = -alpha
+    for (int j = tid; j <= n; j += blockDim.x) Zg[(long long)m * ld + j] = alpha + um + vt_s[j] - norm;
+  }
+#undef K_GET
+#undef K_PUT
+}
+
+constexpr int CL_RR = 8;   // rows of every 16-row warp tile held in registers (default)
+
+void cl_set_attrs() {
+  mvm_once_per_device(MVM_ONCE_SINKHORN_CL, [&] {
+    const int smem = (int)mvm_dev_info().max_smem;
+    cudaFuncSetAttribute(sinkhorn_cl_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(sinkhorn_cl_kernel<8, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(sinkhorn_cl_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(sinkhorn_cl_kernel<6, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(sinkhorn_cl_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(sinkhorn_cl_kernel<6, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  });
+}
+
+}  // namespace
+
+// Smallest cluster size whose CTAs hold <= 64 rows each; 0 when the problem does not fit a cluster
+// (more than 1024 rows or columns): the caller then uses the multi-CTA kernel of sinkhorn_exp.cu.
+int sinkhorn_cluster_size(int max_m, int max_n) {
+  if (max_n > CL_MAXN || max_m > 16 * CL_ROWS) return 0;
+  int C = 1;
+  while (C * CL_ROWS < max_m) C *= 2;
+  return C;
+}
+
+int launch_sinkhorn_cluster(const SinkhornTable& tab, int batch, float bin_score, int iters, int C,
+                            cudaStream_t stream, int rr) {
+  MVM_REQUIRE(tab.n_pairs >= 1 && tab.n_pairs <= MVM_MAX_PAIRS && batch >= 1);
+  MVM_REQUIRE(C == 1 || C == 2 || C == 4 || C == 8 || C == 16);
+  int max_n = 0;
+  for (int p = 0; p < tab.n_pairs; ++p) {
+    MVM_REQUIRE(tab.m[p] >= 1 && tab.n[p] >= 1 && tab.n[p] <= CL_MAXN && tab.m[p] <= C * CL_ROWS);
+    max_n = tab.n[p] > max_n ? tab.n[p] : max_n;
+  }
+  if (rr == 0) rr = CL_RR;
+  MVM_REQUIRE(rr == 6 || rr == 8);
+  const size_t smem = cl_smem_bytes(max_n, 16 - rr);
+  auto kern = rr == 8 ? sinkhorn_cl_kernel<8, false> : (g_sink_timing ? sinkhorn_cl_kernel<6, true> : sinkhorn_cl_kernel<6, false>);
+  cl_set_attrs();
+  MVM_REQUIRE(smem <= mvm_dev_info().max_smem);
+  SinkClCfg cfg;
+  cfg.C = C; cfg.batch = batch; cfg.iters = iters; cfg.alpha = bin_score; cfg.timing = g_sink_timing;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)(tab.n_pairs * batch * C));
+  lc.blockDim = dim3(1024);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  MvmProfScope prof__(MVM_TAG_SINKHORN, stream);
+  cudaLaunchKernelEx(&lc, kern, tab, cfg);
+  MVM_CHECK_LAUNCH();
+  return MVM_OK;
+}
+
+// Clusters of size C that can be co-resident on the current device with this kernel's footprint
+// (0: the size is not launchable here).  Used to pick the kernel and reported by bench.py.
+int sinkhorn_cluster_max_active(int C, int n) {
+  auto kern = sinkhorn_cl_kernel<CL_RR, false>;
+  cl_set_attrs();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)(C * 64));
+  lc.blockDim = dim3(1024);
+  lc.dynamicSmemBytes = cl_smem_bytes(n, 16 - CL_RR);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  int num = 0;
+  if (cudaOccupancyMaxActiveClusters(&num, kern, &lc) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return num;
+}

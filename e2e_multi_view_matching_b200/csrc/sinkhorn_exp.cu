@@ -223,21 +223,36 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_exp_kernel(PairTable tab, Si
 long long* g_sink_timing = nullptr;
 extern "C" void mvm_debug_set_sinkhorn_timing(long long* p) { g_sink_timing = p; }
 
+// Production dispatch: problems of up to 1024 x 1024 run on one hardware cluster each (sinkhorn_cl.cu);
+// larger ones (cfg4: 2048 keypoints, 16.8 MB per matrix) on the multi-CTA kernel below.
+// variant: 0 = automatic, 1 = force the multi-CTA kernel, 2 / 3 = force the cluster kernel (8 / 6 register rows).
 int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, int variant) {
+  MVM_REQUIRE(tab.n_pairs >= 1 && tab.n_pairs <= MVM_MAX_PAIRS && batch >= 1);
+  int mm = 0, mn = 0;
+  for (int p = 0; p < tab.n_pairs; ++p) {
+    mm = tab.m[p] > mm ? tab.m[p] : mm;
+    mn = tab.n[p] > mn ? tab.n[p] : mn;
+  }
+  if (variant != 1) {
+    const int C = sinkhorn_cluster_size(mm, mn);
+    if (C > 0 && sinkhorn_cluster_max_active(C, mn) > 0)
+      return launch_sinkhorn_cluster(tab, batch, bin_score, iters, C, stream, variant == 3 ? 6 : 0);
+    MVM_REQUIRE(variant == 0);
+  }
+  return launch_sinkhorn_multicta(tab, batch, bin_score, iters, ws, stream);
+}
+
+int launch_sinkhorn_multicta(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
+                             cudaStream_t stream) {
   MVM_REQUIRE(tab.n_pairs >= 1 && tab.n_pairs <= MVM_MAX_PAIRS && batch >= 1);
   MvmProfScope prof__(MVM_TAG_SINKHORN, stream);
-  static int n_sm = 0;
-  static size_t max_smem = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    int optin = 0;
-    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    max_smem = (size_t)optin;
-    cudaFuncSetAttribute(sinkhorn_exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  }
+  const int n_sm = mvm_dev_info().n_sm;
+  const size_t max_smem = mvm_dev_info().max_smem;
+  MVM_REQUIRE(n_sm <= 192);   // sinkhorn_ws_floats sizes the exchange buffer for at most 192 SMs
+  mvm_once_per_device(MVM_ONCE_SINKHORN_EXP, [&] {
+    cudaFuncSetAttribute(sinkhorn_exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+  });
   int max_m = 0, max_n = 0;
   for (int p = 0; p < tab.n_pairs; ++p) {
     max_m = tab.m[p] > max_m ? tab.m[p] : max_m;
@@ -272,7 +287,11 @@ int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int it
   float* xch = ws + 256;
   cudaMemsetAsync(ctrs, 0, 256 * sizeof(float), stream);
   const size_t smem = smem_need(G);
-  sinkhorn_exp_kernel<<<G * NG, 1024, smem, stream>>>(tab, cfg, xch, ctrs);
+  {
+    // software group barriers inside: cooperative launch = co-residency guaranteed or an error, never a hang
+    void* kargs[] = {(void*)const_cast<SinkhornTable*>(&tab), (void*)&cfg, (void*)&xch, (void*)&ctrs};
+    cudaLaunchCooperativeKernel((const void*)sinkhorn_exp_kernel, dim3(G * NG), dim3(1024), kargs, smem, stream);
+  }
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }

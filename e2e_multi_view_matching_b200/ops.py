@@ -89,6 +89,12 @@ def log_optimal_transport(scores, alpha, iters, ref_kernel=False, kernel=None):
     Z[:, :m, :n] = scores
     nws = lib.mvm_sinkhorn_workspace_floats(1, B, max(m, n))
     ws = torch.empty(nws, dtype=torch.float32, device=scores.device)
+    variants = {'multicta': 1, 'cluster': 2, 'cluster6': 3}
+    if kernel in variants:
+        rc = lib.mvm_log_optimal_transport_ex(_lib.ptr(Z), B, m, n, float(alpha), int(iters), _lib.ptr(ws),
+                                              variants[kernel], _lib.stream_ptr())
+        _lib.check(rc, 'mvm_log_optimal_transport_ex')
+        return Z
     fn = {None: lib.mvm_log_optimal_transport, 'ref': lib.mvm_log_optimal_transport_ref,
           'log': lib.mvm_log_optimal_transport_logdomain}['ref' if ref_kernel else kernel]
     rc = fn(_lib.ptr(Z), B, m, n, float(alpha), int(iters), _lib.ptr(ws), _lib.stream_ptr())

@@ -50,7 +50,7 @@ def head_permutation(d_model=256, heads=4):
 class PackedMatcher:
     """Flat device buffer + the mvm_matcher_weights struct pointing into it."""
 
-    def __init__(self, state_dict, layer_names, conf_mlp=True, device='cuda'):
+    def __init__(self, state_dict, layer_names, conf_mlp=True, device='cuda', fold_merge=True):
         sd = _strip(state_dict)
         tensors = []   # (name, cpu double tensor)
 
@@ -76,10 +76,19 @@ class PackedMatcher:
                 bs.append(b[src])
             add('l%d_w_qkv' % l, torch.cat(ws, 0))
             add('l%d_b_qkv' % l, torch.cat(bs, 0))
-            w, b = _conv(sd, p + 'attn.merge')
-            add('l%d_w_merge' % l, w[:, src])
-            add('l%d_b_merge' % l, b)
+            wm, bm = _conv(sd, p + 'attn.merge')
+            wm = wm[:, src]
             w, b = _fold(sd, p + 'mlp.0', p + 'mlp.1')
+            if fold_merge:
+                # mlp.0(cat[x, merge(a)]) = W0x x + (W0m Wm) a + (b0 + W0m bm): merge is linear and has no other
+                # consumer (superglue.py:109,121), so it is folded offline in fp64: -10 % GEMM FLOPs, one launch
+                # and one [rows,256] round trip less per layer
+                d = wm.shape[0]
+                b = b + w[:, d:] @ bm
+                w = torch.cat([w[:, :d], w[:, d:] @ wm], 1)
+            else:
+                add('l%d_w_merge' % l, wm)
+                add('l%d_b_merge' % l, bm)
             add('l%d_w_mlp0' % l, w)
             add('l%d_b_mlp0' % l, b)
             w, b = _conv(sd, p + 'mlp.3')
@@ -131,7 +140,7 @@ class PackedMatcher:
         for l, name in enumerate(layer_names):
             L = W.layers[l]
             for f in ('w_qkv', 'b_qkv', 'w_merge', 'b_merge', 'w_mlp0', 'b_mlp0', 'w_mlp1', 'b_mlp1'):
-                setattr(L, f, P('l%d_%s' % (l, f)))
+                setattr(L, f, P('l%d_%s' % (l, f)) if 'l%d_%s' % (l, f) in offsets else None)
             L.is_cross = 1 if name == 'cross' else 0
         W.w_final = P('w_final')
         W.b_final = P('b_final')
@@ -145,3 +154,4 @@ class PackedMatcher:
         self.struct = W
         self.n_layers = len(layer_names)
         self.has_conf = bool(conf_mlp)
+        self.fold_merge = bool(fold_merge)

@@ -33,8 +33,8 @@ extern "C" {
 typedef struct mvm_layer_weights {
   const float* w_qkv;   /* [768,256] */
   const float* b_qkv;   /* [768]     */
-  const float* w_merge; /* [256,256] */
-  const float* b_merge; /* [256]     */
+  const float* w_merge; /* [256,256]; NULL = folded into w_mlp0 (what packing.py does by default):      */
+  const float* b_merge; /* [256]      w_mlp0[:,256:] <- w_mlp0[:,256:] @ w_merge, b_mlp0 += w_mlp0[:,256:] @ b_merge */
   const float* w_mlp0;  /* [512,512]  mlp.0 with mlp.1 (BN) folded */
   const float* b_mlp0;  /* [512]     */
   const float* w_mlp1;  /* [256,512]  mlp.3 */
@@ -148,6 +148,13 @@ int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, i
 size_t mvm_sinkhorn_workspace_floats(int n_pairs, int batch, int n_max);
 int mvm_log_optimal_transport(float* scores, int batch, int m, int n, float bin_score,
                               int iters, float* ws, void* stream);
+/* variant 0 = what mvm_log_optimal_transport picks (one thread-block cluster per problem when m, n <= 1024 and
+ * the device can co-schedule the cluster, else the multi-CTA kernel, launched cooperatively); 1 = multi-CTA
+ * kernel; 2 / 3 = cluster kernel with 8 / 6 of every 16 rows in registers (fails when the problem does not fit). */
+int mvm_log_optimal_transport_ex(float* scores, int batch, int m, int n, float bin_score, int iters,
+                                 float* ws, int variant, void* stream);
+/* co-resident clusters the device offers for an m x n problem (0: the cluster kernel is not used) */
+int mvm_sinkhorn_max_active_clusters(int m, int n);
 int mvm_log_optimal_transport_ref(float* scores, int batch, int m, int n, float bin_score,
                                   int iters, float* ws, void* stream);
 int mvm_log_optimal_transport_logdomain(float* scores, int batch, int m, int n, float bin_score,

@@ -4,7 +4,10 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import MATCHER_CASES, load_case, case_inputs, compare_matcher_outputs
+import json
+import os
+
+from tests.util import GOLDEN, MATCHER_CASES, load_case, case_inputs, compare_matcher_outputs, score_tol_for
 
 pytestmark = pytest.mark.gpu
 
@@ -32,9 +35,14 @@ def test_matcher_matches_reference_golden(name, mode):
     pkg.set_math_mode(mode)
     got = run_ours(meta, sd, data)
     assert set(ref.keys()) == set(got.keys())
-    tol = dict(tau=2e-4, score_tol=(2e-4, 1e-5)) if mode == 0 else dict(tau=2e-3, score_tol=(1e-3 if 'sharp' in name else 3e-4, 3e-5))
-    rep = compare_matcher_outputs(ref, got, min_stable=0.9 if 'sharp' in name else 0.0, **tol)
-    print(name, mode, rep)
+    # score tolerance: the reference's own fp32 arithmetic sits up to 2.9e-4 from its double-precision run on
+    # these cases (tests/golden/matcher_report.json: max_abs_ref32_vs_ref64), so 3e-4 abs (+3e-5 rel) is the
+    # resolution of the fixture itself; matches are compared exactly on every row whose top-2 margin exceeds
+    # tau, and >= 90 % of the rows of every case (but the deliberately flat one) must be such rows
+    noise = json.load(open(os.path.join(GOLDEN, 'matcher_report.json')))[name]['max_abs_ref32_vs_ref64']
+    tol = dict(tau=2e-4, score_tol=(max(2e-4, 2.5 * noise), 1e-5)) if mode == 0 else dict(tau=2e-3, score_tol=score_tol_for(name))
+    rep = compare_matcher_outputs(ref, got, min_stable=0.0 if name == 'pair_flat' else 0.9, **tol)
+    print(name, mode, rep, 'reference fp32 noise', noise)
 
 
 def test_matcher_batched_equals_single():

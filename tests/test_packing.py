@@ -9,9 +9,9 @@ from e2e_multi_view_matching_b200.synthetic import make_state_dict
 LAYERS = ['self', 'cross', 'self']
 
 
-def _packed():
+def _packed(fold_merge=False):
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in make_state_dict(len(LAYERS), seed=3).items()}
-    return sd, packing.PackedMatcher(sd, LAYERS, conf_mlp=True, device='cpu')
+    return sd, packing.PackedMatcher(sd, LAYERS, conf_mlp=True, device='cpu', fold_merge=fold_merge)
 
 
 def _get(pm, name, shape):
@@ -51,6 +51,26 @@ def test_head_permutation_reproduces_the_reference_view():
     # merge consumes the head-major channels: its columns carry the same permutation
     wm, _, _ = _get(pm, 'l1_w_merge', (256, 256))
     torch.testing.assert_close(wm, sd['gnn.layers.1.attn.merge.weight'][:, :, 0][:, src])
+
+
+def test_merge_folded_into_mlp0():
+    """Default packing: attn.merge (linear, single consumer) is folded into the message half of mlp.0 --
+    mlp.0+BN(cat[x, merge(a)]) evaluated with the reference's layers == folded matrix applied to cat[x, a]."""
+    sd, pm = _packed(fold_merge=True)
+    assert pm.struct.layers[1].w_merge is None and 'l1_w_merge' not in pm.offsets
+    src = packing.head_permutation()
+    x = torch.randn(3, 256, 11, dtype=torch.float64)
+    a_ref = torch.randn(3, 256, 11, dtype=torch.float64)          # attention output in the reference's channel order
+    p = 'gnn.layers.1.'
+    msg = torch.nn.functional.conv1d(a_ref, sd[p + 'attn.merge.weight'].double(), sd[p + 'attn.merge.bias'].double())
+    ref = torch.nn.functional.conv1d(torch.cat([x, msg], 1), sd[p + 'mlp.0.weight'].double(), sd[p + 'mlp.0.bias'].double())
+    ref = torch.nn.functional.batch_norm(ref, sd[p + 'mlp.1.running_mean'].double(), sd[p + 'mlp.1.running_var'].double(),
+                                         sd[p + 'mlp.1.weight'].double(), sd[p + 'mlp.1.bias'].double(), False, 0.0, 1e-5)
+    wf, _, _ = _get(pm, 'l1_w_mlp0', (512, 512))
+    bf, _, _ = _get(pm, 'l1_b_mlp0', (512,))
+    a_packed = a_ref[:, src]                                      # the kernels' head-contiguous channel order
+    got = torch.einsum('oc,bcn->bon', wf.double(), torch.cat([x, a_packed], 1)) + bf.double()[None, :, None]
+    assert (got - ref).abs().max() < 2e-5
 
 
 def test_tf32_planes():

@@ -36,7 +36,7 @@ def test_matcher_tensor_core_modes(name, mode):
     """Whole matcher with the GEMMs (and attention, once enabled) on tcgen05: 3xTF32 keeps the fp32
     parity contract; single-pass TF32 (torch 1.10's Ampere default) is compared at TF32 accuracy."""
     import e2e_multi_view_matching_b200 as pkg
-    from tests.util import load_case, case_inputs, compare_matcher_outputs
+    from tests.util import load_case, case_inputs, compare_matcher_outputs, score_tol_for
     from tests.test_matcher_gpu import run_ours
     meta, ref = load_case(name)
     sd, data = case_inputs(meta)
@@ -45,7 +45,7 @@ def test_matcher_tensor_core_modes(name, mode):
     if mode == 3:
         # 'sharp' cases scale the raw scores by gain^2 = 256: the ~1e-5 relative 3xTF32 error of the raw
         # score shows up as an absolute error of the (O(1)) log-coupling entries
-        rep = compare_matcher_outputs(ref, got, tau=2e-3, score_tol=(1e-3 if 'sharp' in name else 3e-4, 3e-5))
+        rep = compare_matcher_outputs(ref, got, tau=2e-3, score_tol=score_tol_for(name))
     else:
         rep = compare_matcher_outputs(ref, got, tau=0.3, score_tol=(0.3, 3e-2), conf_tol=5e-2)   # single-pass TF32: ~1e-3 relative per GEMM
     print(name, mode, rep)
@@ -134,7 +134,7 @@ def test_score_gemm_tensor_cores_vs_cuda_cores():
     import e2e_multi_view_matching_b200 as pkg
     from e2e_multi_view_matching_b200 import _lib
     from tests.test_matcher_gpu import run_ours
-    from tests.util import load_case, case_inputs, compare_matcher_outputs
+    from tests.util import load_case, case_inputs, compare_matcher_outputs, score_tol_for
     lib = _lib.lib()
     for name in ('mv4_ragged_sharp', 'pair_small_ragged', 'mv5_28l_96'):
         meta, ref = load_case(name)
@@ -147,5 +147,5 @@ def test_score_gemm_tensor_cores_vs_cuda_cores():
             tcs = run_ours(meta, sd, data)
         finally:
             lib.mvm_debug_set_score_kernel(1)
-        rep = compare_matcher_outputs(simt, tcs, tau=2e-3, score_tol=(1e-3 if 'sharp' in name else 3e-4, 3e-5))
+        rep = compare_matcher_outputs(simt, tcs, tau=2e-3, score_tol=score_tol_for(name))
         print(name, rep)

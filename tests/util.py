@@ -7,7 +7,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
-MATCHER_CASES = ['pair_small_ragged', 'pair_18l_128', 'mv3_ragged', 'mv5_28l_96', 'pair3_mv_false',
+MATCHER_CASES = ['pair_small_ragged', 'pair_18l_128', 'mv3_ragged', 'mv5_28l_96', 'pair3_mv_false', 'pair_flat',
                  'pair_18l_128_sharp', 'mv5_28l_96_sharp', 'mv4_ragged_sharp']
 
 
@@ -26,6 +26,14 @@ def case_inputs(meta):
     else:
         data = make_view_inputs(meta['iseed'], meta['counts'])
     return sd, data
+
+
+def score_tol_for(name):
+    """(abs, rel) tolerance on the log-couplings of a golden case in the default 3xTF32 mode.  The reference's own
+    fp32 run sits `noise` away from its double-precision run (matcher_report.json, measured by the generator), so two
+    equally accurate fp32-class implementations may differ by up to ~2x that; never below 3e-4."""
+    noise = json.load(open(os.path.join(GOLDEN, 'matcher_report.json')))[name]['max_abs_ref32_vs_ref64']
+    return (max(3e-4, 2.5 * noise), 3e-5)
 
 
 def stable_rows(Z, tau):
@@ -48,7 +56,8 @@ def compare_matcher_outputs(ref, got, tau=2e-4, score_tol=(2e-4, 1e-5), min_stab
     - coupling matrices / confidences: allclose with abs + rel tolerance
     - matches: bit-exact on every keypoint whose decision margin exceeds tau
     Returns a small report dict."""
-    report = {'n_pairs': 0, 'unstable': 0, 'rows': 0, 'max_score_err': 0.0, 'max_conf_err': 0.0}
+    report = {'n_pairs': 0, 'unstable': 0, 'rows': 0, 'max_score_err': 0.0, 'max_conf_err': 0.0,
+              'mismatch_at_margin_0': 0}
     for k in ref:
         if not k.startswith('scores_'):
             continue
@@ -66,6 +75,7 @@ def compare_matcher_outputs(ref, got, tau=2e-4, score_tol=(2e-4, 1e-5), min_stab
             assert got[mk].dtype == np.int64 and got[mk].shape == ref[mk].shape
             assert np.array_equal(ref[mk][st], got[mk][st]), (mk, int((ref[mk][st] != got[mk][st]).sum()))
             same = ref[mk] == got[mk]
+            report['mismatch_at_margin_0'] += int((~same).sum())    # measured, incl. the near-ties (informational)
             np.testing.assert_allclose(got[sk][same], ref[sk][same], rtol=max(2e-3, 2 * score_tol[0]), atol=1e-6)
             report['unstable'] += int((~st).sum())
             report['rows'] += int(st.size)
