@@ -43,6 +43,15 @@ class PairIO(C.Structure):
                 ('scores', _fp), ('conf', _fp)]
 
 
+class MatcherOptions(C.Structure):
+    _fields_ = [('math_mode', C.c_int), ('score_kernel', C.c_int), ('gemm_tile', C.c_int), ('gemm_kernel', C.c_int),
+                ('sinkhorn_variant', C.c_int), ('attention_split', C.c_int)]
+
+
+class SuperPointWeights(C.Structure):
+    _fields_ = [('w', _fp * 10), ('b', _fp * 10), ('w_pb', _fp), ('b_pb', _fp), ('w_db', _fp), ('b_db', _fp)]
+
+
 class MvmError(RuntimeError):
     pass
 
@@ -68,6 +77,20 @@ def lib():
     L.mvm_matcher_forward.argtypes = [
         C.POINTER(MatcherWeights), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _fp, _fp, _fp,
         C.c_float, C.c_float, C.c_int, C.c_float, C.POINTER(PairIO), C.c_int, _fp, C.c_size_t, _fp]
+    L.mvm_matcher_options_default.restype = None
+    L.mvm_matcher_options_default.argtypes = [C.POINTER(MatcherOptions)]
+    L.mvm_matcher_forward_ex.restype = C.c_int
+    L.mvm_matcher_forward_ex.argtypes = [
+        C.POINTER(MatcherWeights), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _fp, _fp, _fp,
+        C.c_float, C.c_float, C.c_int, C.c_float, C.POINTER(PairIO), C.c_int, _fp, C.c_size_t,
+        C.POINTER(MatcherOptions), _fp]
+    for name in ('mvm_debug_set_score_kernel', 'mvm_debug_set_gemm_tile', 'mvm_debug_set_gemm_kernel',
+                 'mvm_debug_set_attention_split'):
+        getattr(L, name).restype = None
+        getattr(L, name).argtypes = [C.c_int]
+    for name in ('mvm_debug_set_attention_timing', 'mvm_debug_set_sinkhorn_timing', 'mvm_debug_set_mvba_timing'):
+        getattr(L, name).restype = None
+        getattr(L, name).argtypes = [_fp]
     L.mvm_linear.restype = C.c_int
     L.mvm_linear.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int,
                              _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp]
@@ -83,6 +106,8 @@ def lib():
     L.mvm_attention_tc.restype = C.c_int
     L.mvm_attention_tc.argtypes = [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, _fp,
                                    _fp, _fp]
+    L.mvm_attention_h3.restype = C.c_int
+    L.mvm_attention_h3.argtypes = [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, _fp]
     L.mvm_attention.restype = C.c_int
     L.mvm_attention.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, _fp]
     L.mvm_sinkhorn_workspace_floats.restype = C.c_size_t
@@ -121,9 +146,24 @@ def lib():
     L.mvm_multi_view_ba_ex.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
                                        _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,
                                        C.c_size_t, _fp]
+    L.mvm_multi_view_ba_obs.restype = C.c_int
+    L.mvm_multi_view_ba_obs.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
+                                        _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _fp, _fp,
+                                        C.c_size_t, _fp]
     L.mvm_triangulate_pairs.restype = C.c_int
     L.mvm_triangulate_pairs.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
                                         _fp, _fp, _fp, _fp, _fp, _fp]
+    L.mvm_superpoint_workspace_bytes.restype = C.c_size_t
+    L.mvm_superpoint_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.mvm_superpoint_dense.restype = C.c_int
+    L.mvm_superpoint_dense.argtypes = [C.POINTER(SuperPointWeights), _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp,
+                                       C.c_size_t, _fp]
+    L.mvm_superpoint_sample.restype = C.c_int
+    L.mvm_superpoint_sample.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]
+    L.mvm_match_loss_forward.restype = C.c_int
+    L.mvm_match_loss_forward.argtypes = [_fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp]
+    L.mvm_match_loss_backward.restype = C.c_int
+    L.mvm_match_loss_backward.argtypes = [_fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp]
     L.mvm_launch_count.restype = C.c_ulonglong
     L.mvm_profile_enable.argtypes = [C.c_int]
     L.mvm_profile_collect.restype = C.c_int

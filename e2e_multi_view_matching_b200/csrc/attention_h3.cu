@@ -1,58 +1,47 @@
-// Flash-style multi-head attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) with
-// multi-view key/value segments.  Reference semantics: attention() superglue.py:87-91,
-// MultiHeadedAttention :94-109, cross source = concatenation of the other views
-// (multi_view_matcher.py:76-78,92-95).  prob[B,4,N,M] is never materialised.
+// Flash-style multi-head attention on the 5th-gen tensor cores, fp32-faithful with HALF-PRECISION operand planes
+// ("fp16x3"): every product is A_hi.B_hi + A_hi.B_lo + A_lo.B_hi with hi = fp16(x), lo = fp16(x - hi), fp32
+// accumulation in tensor memory.  hi + lo carries 22 mantissa bits -- the same as the tf32 hi/lo pair of
+// attention_tc.cu (measured: identical error on the same operands) -- but tcgen05.mma kind::f16 moves
+// K = 16 per instruction where kind::tf32 moves K = 8, so the three passes cost 1.5 tf32 passes: 768 tensor
+// cycles per 64-key tile instead of 1536.  (fp16 subnormals keep lo exact to 2^-24 absolute; operands of this
+// path -- projected descriptors, softmax numerators <= 2^8 -- are far inside the fp16 range.)
+// Reference semantics: attention() superglue.py:87-91, MultiHeadedAttention :94-109, cross source = concatenation
+// of the other views (multi_view_matcher.py:76-78,92-95).  prob[B,4,N,M] is never materialised.
 //
-// One CTA = 128 queries of one (view, head); keys/values stream through in tiles of 64.
-//   warp 0      TMA producer   per tile K [64x64] (from QKV) and V^T [64 d x 64 keys], 3-deep rings
-//   warp 1      tcgen05.mma issuer for S = Q K^T  (M128 N64 K64, kind::tf32) into one of two TMEM S buffers
-//   warp 2      tcgen05.mma issuer for O_g += P V (M128 N64 K64) into the TMEM accumulator of the tile's
-//               softmax group; BOTH A operands (Q and P) live in tensor memory, so shared-memory bandwidth
-//               only carries the K / V^T tiles
-//   warps 3-6   softmax group 0 (even key tiles), warps 7-10 softmax group 1 (odd key tiles): thread r of a
-//               group owns query row r (TMEM lane r): tcgen05.ld S row, row max / sum in registers (no
-//               shuffles), exp2, P written back to TENSOR MEMORY (tcgen05.st) and consumed as the A operand
-//               of P.V straight from TMEM.  Each group has its own S/P buffer, its own output accumulator in
-//               TMEM (O_g += P(j) V(j) over its tiles) and its own softmax reference (m_g, l_g); the two
-//               partial softmaxes are merged once at the end (exact: softmax is invariant to the reference).
-//               Two groups so that a tile's S -> softmax -> P latency (wake-up, TMEM load, 64 exp2, split, TMEM
-//               store: ~1.2 k cycles) overlaps the other group's tile instead of idling the tensor pipe
-//   (NPASS == 3) every product is A.B + A.B_lo + A_lo.B (fp32-faithful "3xTF32"): the tf32 hi/lo planes of
-//               K and V^T are produced by the QKV GEMM epilogue and arrive by TMA; Q and P are split in
-//               registers by the softmax threads before they are stored to tensor memory
-// All operands are K-major: Q, K rows of the fused QKV projection [rows, 768]; V^T [view*256 + h*64 + d, key]
-// is written by the QKV GEMM epilogue (gemm_tc.cu).
+// Same structure as attention_tc.cu: one CTA = 128 queries of one (view, head), key tiles of 64;
+//   warp 0      TMA producer: K_hi | K_lo [64 keys x 64 d] and V^T_hi | V^T_lo [64 d x 64 keys] fp16 tiles (8 KB each,
+//               one 128-byte swizzle row per matrix row), 3-deep rings; the planes are written by the QKV GEMM epilogue
+//   warp 1      tcgen05.mma issuer S = Q K^T   (M128 N64 K16 kind::f16, A = Q_hi / Q_lo from tensor memory)
+//   warp 2      tcgen05.mma issuer O_g += P V  (A = P_hi / P_lo from tensor memory)
+//   warps 3-6 / 7-10   softmax groups 0 / 1 (even / odd key tiles): thread r owns query row r; S row -> registers,
+//               exp2, P split into packed half2 hi / lo planes written OVER S in tensor memory (32 + 32 columns),
+//               per-group output accumulator resident in TMEM with lazy rescaling, merged once at the end.
+// TMEM columns: S0/P0 [0,64)  S1/P1 [64,128)  O0 [128,192)  O1 [192,256)  Q_hi [256,288)  Q_lo [288,320).
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
-long long* g_attn_dbg = nullptr;   // optional clock64 trace buffer (mvm_debug_set_attention_timing); shared with attention_h3.cu
+extern long long* g_attn_dbg;   // attention_tc.cu (mvm_debug_set_attention_timing)
 
 namespace {
 
 constexpr int BQ = 128, BKV = 64, HD = 64;
-constexpr int SUB = 32;                       // fp32 elements per 128-byte swizzle row
-constexpr int KV_SUB_BYTES = BKV * SUB * 4;   //  8 KB  [64 rows x 128 B]
-constexpr int K_BYTES = 2 * KV_SUB_BYTES;     // d 0-31 | d 32-63      (rows = keys)
-constexpr int V_BYTES = 2 * KV_SUB_BYTES;     // keys 0-31 | keys 32-63 (rows = d)
+constexpr int K_BYTES = BKV * HD * 2;         //  8 KB  [64 keys x 64 d] fp16, 128-byte rows
+constexpr int V_BYTES = HD * BKV * 2;         //  8 KB  [64 d x 64 keys] fp16
 
-template <int NPASS>
-struct ACfg {
+struct HCfg {
   static constexpr int ST = 3;                          // K and V^T ring depth
-  static constexpr int PL = NPASS == 3 ? 2 : 1;         // planes (hi [, lo])
-  static constexpr int OFF_K = 0;
-  static constexpr int OFF_V = OFF_K + ST * K_BYTES * PL;
-  static constexpr int OFF_BAR = OFF_V + ST * V_BYTES * PL;
+  static constexpr int OFF_K = 0;                       // per stage: hi | lo
+  static constexpr int OFF_V = OFF_K + ST * K_BYTES * 2;
+  static constexpr int OFF_BAR = OFF_V + ST * V_BYTES * 2;
   static constexpr int OFF_ML = OFF_BAR + 512;          // (m, l) of both softmax groups: float [2][2][128]
   static constexpr int SMEM_BYTES = OFF_ML + 2048 + 1024;
   static constexpr int NTHREADS = 352;
-  static constexpr int MIN_CTAS = 1;
-  // TMEM columns: S0/P0 [0,64) S1/P1 [64,128) O0 [128,192) Q_hi [192,256)
-  //               Q_lo [256,320) P0_lo [320,384) P1_lo [384,448) O1 [448,512)
-  static constexpr int TMEM_COLS = 512;
+  static constexpr int TMEM_COLS = 512;                 // 320 used (allocation sizes are powers of two)
 };
 
-struct AttnTcArgs {
+struct AttnH3Args {
   const float* qkv;    // [V, n_pad, 768]
   float* out;          // [V, n_pad, 256]
   int n_pad;
@@ -61,24 +50,49 @@ struct AttnTcArgs {
   long long* dbg;      // optional clock64 trace of CTA (0,0,0): [tile][16] (tools/attn_timing.py)
 };
 
-using tc::tf32_rn;
 
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// rn_tf32 of a finite value with two integer instructions (round to nearest, ties away -- what cvt.rna does,
-// which the compiler expands to four instructions with the Inf/NaN guard)
-__device__ __forceinline__ float tf32_hi(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+// x -> (hi, lo) half-precision planes of two consecutive elements, packed the way the tensor core reads a 16-bit A
+// operand from tensor memory (element k in the low half of 32-bit column k / 2)
+__device__ __forceinline__ void split_pack(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {   // D = F32, A = B = F16, both K-major
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 columns store
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
 
-template <int NPASS>
-__global__ void __launch_bounds__(ACfg<NPASS>::NTHREADS, ACfg<NPASS>::MIN_CTAS)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                    const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo, AttnTcArgs g) {
-  using C_ = ACfg<NPASS>;
+__global__ void __launch_bounds__(HCfg::NTHREADS, 1)
+attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo, AttnH3Args g) {
+  using C_ = HCfg;
   constexpr int ST = C_::ST;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -151,8 +165,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     seg = 0; k0 = 0; cnt = 0;
   };
 
-  auto sK = [&](int s) { return smem + C_::OFF_K + s * K_BYTES * C_::PL; };
-  auto sV = [&](int s) { return smem + C_::OFF_V + s * V_BYTES * C_::PL; };
+  auto sK = [&](int s) { return smem + C_::OFF_K + s * K_BYTES * 2; };
+  auto sV = [&](int s) { return smem + C_::OFF_V + s * V_BYTES * 2; };
 
   if (threadIdx.x == 0) {
     tc::mbar_init(q_ready, 128);
@@ -166,7 +180,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   }
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
-    if (NPASS == 3) { tc::prefetch_tmap(&tmKlo); tc::prefetch_tmap(&tmVlo); }
+    tc::prefetch_tmap(&tmKlo); tc::prefetch_tmap(&tmVlo);
   }
   if (warp == 1) tc::tmem_alloc<C_::TMEM_COLS>(tmem_slot);
   tc::tc_fence_before();
@@ -174,8 +188,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   tc::tc_fence_after();
   if (threadIdx.x == 0) cmark(2);
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 128, tmem_Q = tmem_base + 192;
-  const uint32_t tmem_Qlo = tmem_base + 256, tmem_Plo0 = tmem_base + 320, tmem_O1 = tmem_base + 448;
+  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 128, tmem_O1 = tmem_base + 192;
+  const uint32_t tmem_Q = tmem_base + 256, tmem_Qlo = tmem_base + 288;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -185,14 +199,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       const int s = j % ST;
       tc::mbar_wait(k_empty + s, ((j / ST) & 1) ^ 1);
       if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(k_full + s, K_BYTES * C_::PL);
+        tc::mbar_arrive_expect_tx(k_full + s, K_BYTES * 2);
         const int krow = (b * T + seg) * g.n_pad + k0;
-        tc::tma_load_2d(sK(s), &tmK, k_full + s, 256 + h * HD, krow);
-        tc::tma_load_2d(sK(s) + KV_SUB_BYTES, &tmK, k_full + s, 256 + h * HD + SUB, krow);
-        if (NPASS == 3) {
-          tc::tma_load_2d(sK(s) + K_BYTES, &tmKlo, k_full + s, h * HD, krow);
-          tc::tma_load_2d(sK(s) + K_BYTES + KV_SUB_BYTES, &tmKlo, k_full + s, h * HD + SUB, krow);
-        }
+        tc::tma_load_2d(sK(s), &tmK, k_full + s, h * HD, krow);
+        tc::tma_load_2d(sK(s) + K_BYTES, &tmKlo, k_full + s, h * HD, krow);
       }
       __syncwarp();
     };
@@ -202,14 +212,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       const int s = j % ST;
       tc::mbar_wait(v_empty + s, ((j / ST) & 1) ^ 1);
       if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(v_full + s, V_BYTES * C_::PL);
+        tc::mbar_arrive_expect_tx(v_full + s, V_BYTES * 2);
         const int vrow = (b * T + seg) * 256 + h * HD;
         tc::tma_load_2d(sV(s), &tmV, v_full + s, k0, vrow);
-        tc::tma_load_2d(sV(s) + KV_SUB_BYTES, &tmV, v_full + s, k0 + SUB, vrow);
-        if (NPASS == 3) {
-          tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, k0, vrow);
-          tc::tma_load_2d(sV(s) + V_BYTES + KV_SUB_BYTES, &tmVlo, v_full + s, k0 + SUB, vrow);
-        }
+        tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, k0, vrow);
       }
       __syncwarp();
     };
@@ -227,7 +233,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     // queued MMAs.  The ordering a single in-order stream gave for free is now explicit: S(j) overwrites the
     // buffer P(j-2) was read from, so it waits for P.V(j-2) to complete (o_full[j & 1]).
     // Whole warp converged, one elected lane issues (see tc::elect_one).
-    constexpr uint32_t idesc = tc::make_idesc_tf32(BQ, BKV);   // M=128, N=64
+    constexpr uint32_t idesc = make_idesc_f16(BQ, BKV);        // M=128, N=64
     tc::mbar_wait(q_ready, 0);
     tc::tc_fence_after();
     for (int j = 0; j < nt; ++j) {
@@ -243,14 +249,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       const uint32_t d = tmem_S0 + sb * 64;
       if (tc::elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < HD / 8; ++kk) {
-          const uint32_t offk = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
-          const uint64_t dk = tc::make_kmajor_sw128_desc(k_hi + offk);
-          tc::umma_tf32_ts(d, tmem_Q + kk * 8, dk, idesc, kk != 0);           // A = Q from tensor memory
-          if (NPASS == 3) {
-            tc::umma_tf32_ts(d, tmem_Q + kk * 8, tc::make_kmajor_sw128_desc(k_lo + offk), idesc, 1);
-            tc::umma_tf32_ts(d, tmem_Qlo + kk * 8, dk, idesc, 1);
-          }
+        for (int kk = 0; kk < HD / 16; ++kk) {                  // K = 16 halves = 32 bytes = 8 TMEM columns per MMA
+          const uint64_t dk = tc::make_kmajor_sw128_desc(k_hi + kk * 32);
+          umma_f16_ts(d, tmem_Q + kk * 8, dk, idesc, kk != 0);                // A = Q from tensor memory
+          umma_f16_ts(d, tmem_Q + kk * 8, tc::make_kmajor_sw128_desc(k_lo + kk * 32), idesc, 1);
+          umma_f16_ts(d, tmem_Qlo + kk * 8, dk, idesc, 1);
         }
         mark(j, 6);
         tc::umma_commit(s_full + sb);
@@ -261,7 +264,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     }
   } else if (warp == 2) {
     // =========================== MMA issuer 2: O_g += P V ===========================
-    constexpr uint32_t idesc = tc::make_idesc_tf32(BQ, HD);    // M=128, N=64
+    constexpr uint32_t idesc = make_idesc_f16(BQ, HD);         // M=128, N=64
     for (int j = 0; j < nt; ++j) {
       const int s = j % ST, sb = j & 1;
       // P(j) arrives in two halves (keys 0-31, 32-63): the first 12 MMAs start while the softmax threads are
@@ -271,18 +274,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc::tc_fence_after();
       mark(j, 10);
       const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
-      const uint32_t p_hi = tmem_S0 + sb * 64, p_lo = tmem_Plo0 + sb * 64;
+      const uint32_t p_hi = tmem_S0 + sb * 64, p_lo = p_hi + 32;          // P planes over S: hi [0,32) lo [32,64)
       const uint32_t o_acc = sb ? tmem_O1 : tmem_O;
-      auto issue_PV = [&](int kk0) {
+      auto issue_PV = [&](int kk0) {                                       // two K = 16 steps = 32 keys
 #pragma unroll
-        for (int kk = kk0; kk < kk0 + BKV / 16; ++kk) {
-          const uint32_t offv = (kk >> 2) * KV_SUB_BYTES + (kk & 3) * 32;
-          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + offv);
-          tc::umma_tf32_ts(o_acc, p_hi + kk * 8, dv, idesc, ((j >> 1) | kk) != 0);  // A = P from tensor memory; O_g accumulates over the group's tiles
-          if (NPASS == 3) {
-            tc::umma_tf32_ts(o_acc, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + offv), idesc, 1);
-            tc::umma_tf32_ts(o_acc, p_lo + kk * 8, dv, idesc, 1);
-          }
+        for (int kk = kk0; kk < kk0 + 2; ++kk) {
+          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + kk * 32);
+          umma_f16_ts(o_acc, p_hi + kk * 8, dv, idesc, ((j >> 1) | kk) != 0);  // A = P from tensor memory; O_g accumulates over the group's tiles
+          umma_f16_ts(o_acc, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + kk * 32), idesc, 1);
+          umma_f16_ts(o_acc, p_lo + kk * 8, dv, idesc, 1);
         }
       };
       if (tc::elect_one()) issue_PV(0);
@@ -292,7 +292,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc::tc_fence_after();
       mark(j, 12);
       if (tc::elect_one()) {
-        issue_PV(BKV / 16);
+        issue_PV(2);
         mark(j, 13);
         tc::umma_commit(o_full + (j & 1));
         mark(j, 14);
@@ -309,21 +309,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     // group 0: Q row -> tensor memory (A operand of S = Q K^T); rows past the view are read but never written back
     if (grp == 0) {
-      if (NPASS == 3) {
-        float lo[32];
+      uint32_t qh[32], ql[32];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float hi = tf32_rn(qr[c * 32 + i]);
-            lo[i] = tf32_rn(qr[c * 32 + i] - hi);
-            qr[c * 32 + i] = hi;
-          }
-          tc::tmem_st32(tmem_Qlo + lane_addr + c * 32, lo);
-        }
-      }
-      tc::tmem_st32(tmem_Q + lane_addr, qr);
-      tc::tmem_st32(tmem_Q + lane_addr + 32, qr + 32);
+      for (int i = 0; i < 32; ++i) split_pack(qr[2 * i], qr[2 * i + 1], qh[i], ql[i]);
+      tmem_st16(tmem_Q + lane_addr, qh);
+      tmem_st16(tmem_Q + lane_addr + 16, qh + 16);
+      tmem_st16(tmem_Qlo + lane_addr, ql);
+      tmem_st16(tmem_Qlo + lane_addr + 16, ql + 16);
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(q_ready);
@@ -333,7 +325,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     // TENSOR MEMORY.  The reference m_ref of a row is only raised (and O_g, l rescaled) when the row maximum
     // outgrows it by more than 2^8: softmax is invariant to the reference, P stays <= 2^8, and the common tile
     // costs no TMEM read of O at all.  Log2 units throughout (scores * log2(e) / sqrt(d)).
-    const uint32_t tm_S = tmem_S0 + grp * 64, tm_Plo = tmem_Plo0 + grp * 64, tm_O = grp ? tmem_O1 : tmem_O;
+    const uint32_t tm_S = tmem_S0 + grp * 64, tm_O = grp ? tmem_O1 : tmem_O;
     uint64_t* my_o_full = o_full + grp;
     float m_ref = -INFINITY, l_run = 0.f;
     const float scale_l2e = 0.125f * 1.4426950408889634f;
@@ -389,22 +381,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         // P(j) overwrites S(j) in tensor memory (row r = lane r, keys along columns): A operand of P.V,
         // handed over in two halves
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float lo[32];
+        for (int c = 0; c < 2; ++c) {                        // keys [32 c, 32 c + 32): 16 packed columns per plane
+          uint32_t ph[16], pl[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float pv = ex2_ftz(fmaf(s[c * 32 + i], scale_l2e, nm));
-            rs4[i & 3] += pv;
-            if (NPASS == 3) {
-              const float hi = tf32_hi(pv);
-              lo[i] = pv - hi;          // the tensor core reads the top 19 bits: truncation of lo costs 2^-21 |p|
-              s[c * 32 + i] = hi;
-            } else {
-              s[c * 32 + i] = pv;
-            }
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_ftz(fmaf(s[c * 32 + 2 * i], scale_l2e, nm));
+            const float p1 = ex2_ftz(fmaf(s[c * 32 + 2 * i + 1], scale_l2e, nm));
+            rs4[i & 1] += p0;
+            rs4[2 + (i & 1)] += p1;
+            split_pack(p0, p1, ph[i], pl[i]);
           }
-          if (NPASS == 3) tc::tmem_st32(tm_Plo + lane_addr + c * 32, lo);
-          tc::tmem_st32(tm_S + lane_addr + c * 32, s + c * 32);
+          tmem_st16(tm_S + lane_addr + c * 16, ph);            // P_hi over S columns [0,32)
+          tmem_st16(tm_S + lane_addr + 32 + c * 16, pl);       // P_lo over S columns [32,64)
           tc::tmem_st_wait();
           tc::tc_fence_before();
           tc::mbar_arrive((c == 0 ? p_ready : p_ready_b) + grp);
@@ -459,41 +447,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   if (threadIdx.x == 32) cmark(7);
 }
 
-template <int NPASS>
-int launch_attn(const float* qkv, const float* vt, const float* klo, const float* vtlo, float* out, int batch, int n_pad,
-                const AttnSegs& segs, int is_cross, cudaStream_t stream) {
-  using C_ = ACfg<NPASS>;
-  mvm_once_per_device(MVM_ONCE_ATTN_TC + 16 * (NPASS == 3), [&] {
-    cudaFuncSetAttribute(attention_tc_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
-  });
-  const int V = batch * segs.n_views;
-  const long long rows = (long long)V * n_pad;
-  const CUtensorMap* tK = mvm_get_tmap_2d(qkv, rows, 768, 768, BKV);
-  const CUtensorMap* tV = mvm_get_tmap_2d(vt, (long long)V * 256, n_pad, n_pad, BKV);
-  const CUtensorMap* tKlo = klo ? mvm_get_tmap_2d(klo, rows, 256, 256, BKV) : tK;
-  const CUtensorMap* tVlo = vtlo ? mvm_get_tmap_2d(vtlo, (long long)V * 256, n_pad, n_pad, BKV) : tV;
-  if (!tK || !tV || !tKlo || !tVlo) return MVM_ERR_LAUNCH;
-  AttnTcArgs g;
-  g.qkv = qkv; g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross; g.dbg = g_attn_dbg;
-  dim3 grid(mvm_div_up(n_pad, BQ), 4, V);
-  attention_tc_kernel<NPASS><<<grid, C_::NTHREADS, C_::SMEM_BYTES, stream>>>(*tK, *tV, *tKlo, *tVlo, g);
-  MVM_CHECK_LAUNCH();
-  return MVM_OK;
-}
-
 }  // namespace
 
-extern "C" void mvm_debug_set_attention_timing(long long* buf) { g_attn_dbg = buf; }
-
-// qkv [V, n_pad, 768] (q | k | unused-v), vt [V, 256, n_pad] = V^T per head; out [V, n_pad, 256]
-int launch_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_pad, AttnSegs segs,
-                        int is_cross, int n_pass, cudaStream_t stream, const float* klo, const float* vtlo) {
+// K / V^T planes in half precision: kh, kl [rows, 256]; vth, vtl [V * 256, n_pad] (written by the QKV GEMM epilogue)
+int launch_attention_h3(const float* qkv, const __half* kh, const __half* kl, const __half* vth, const __half* vtl,
+                        float* out, int batch, int n_pad, AttnSegs segs, int is_cross, cudaStream_t stream) {
+  MVM_REQUIRE(qkv && kh && kl && vth && vtl && out);
   MVM_REQUIRE(n_pad % 64 == 0 && segs.n_views >= 1 && segs.n_views <= 8);
   MVM_REQUIRE(!is_cross || segs.n_views >= 2);
   MvmProfScope prof__(MVM_TAG_ATTN, stream);
-  if (n_pass == 3) {
-    MVM_REQUIRE(klo && vtlo);
-    return launch_attn<3>(qkv, vt, klo, vtlo, out, batch, n_pad, segs, is_cross, stream);
-  }
-  return launch_attn<1>(qkv, vt, nullptr, nullptr, out, batch, n_pad, segs, is_cross, stream);
+  using C_ = HCfg;
+  mvm_once_per_device(MVM_ONCE_ATTN_H3, [&] {
+    cudaFuncSetAttribute(attention_h3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
+  });
+  const int V = batch * segs.n_views;
+  const long long rows = (long long)V * n_pad;
+  const CUtensorMap* tK = mvm_get_tmap_2d_f16(kh, rows, 256, 256, BKV);
+  const CUtensorMap* tKlo = mvm_get_tmap_2d_f16(kl, rows, 256, 256, BKV);
+  const CUtensorMap* tV = mvm_get_tmap_2d_f16(vth, (long long)V * 256, n_pad, n_pad, HD);
+  const CUtensorMap* tVlo = mvm_get_tmap_2d_f16(vtl, (long long)V * 256, n_pad, n_pad, HD);
+  if (!tK || !tV || !tKlo || !tVlo) return MVM_ERR_LAUNCH;
+  AttnH3Args g;
+  g.qkv = qkv; g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross; g.dbg = g_attn_dbg;
+  dim3 grid(mvm_div_up(n_pad, BQ), 4, V);
+  attention_h3_kernel<<<grid, C_::NTHREADS, C_::SMEM_BYTES, stream>>>(*tK, *tV, *tKlo, *tVlo, g);
+  MVM_CHECK_LAUNCH();
+  return MVM_OK;
 }

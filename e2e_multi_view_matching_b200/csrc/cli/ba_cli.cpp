@@ -11,7 +11,7 @@
 //
 // Built twice from this file (-DMVM_CLI_BA_INIT selects ba_initializer).  The problems accepted are the ones
 // the reference's writer emits (bundle_adjust_io.py:193-259): every 3-D point is observed exactly twice, by two
-// different cameras, with one weight per point, fx == fy, at most 8 cameras.  Anything else is refused with a
+// different cameras (one weight per observation, equal in x and y), fx == fy, at most 8 cameras.  Anything else is refused with a
 // message and a non-zero exit code -- there is no CPU fallback solver in here.
 #include <cuda_runtime.h>
 
@@ -151,7 +151,6 @@ int run_bundle_adjuster(const std::string& dir) {
     if (first[k] < 0 || second[k] < 0) die("ba_in.csv: a point with fewer than two observations is not supported");
     int ca = relabel(obs[first[k]].cam), cb = relabel(obs[second[k]].cam);
     if (ca == cb) die("ba_in.csv: both observations of a point in one camera");
-    if (obs[first[k]].wx != obs[second[k]].wx) die("ba_in.csv: different weights on the two observations of a point are not supported");
     if (ca > cb) { std::swap(ca, cb); flip[k] = 1; }
     members[pidx[{ca, cb}]].push_back(k);
   }
@@ -159,7 +158,8 @@ int run_bundle_adjuster(const std::string& dir) {
   for (auto& m : members) n_max = std::max(n_max, m.size());
   const int n_pad = (int)((n_max + 63) / 64 * 64);
 
-  std::vector<float> xa((size_t)P * n_pad * 2, 0.f), xb((size_t)P * n_pad * 2, 0.f), w((size_t)P * n_pad, 0.f);
+  std::vector<float> xa((size_t)P * n_pad * 2, 0.f), xb((size_t)P * n_pad * 2, 0.f), w((size_t)P * n_pad, 0.f),
+      wb((size_t)P * n_pad, 0.f);
   std::vector<double> p0((size_t)P * n_pad * 3, 0.0);
   std::vector<int> n_valid(P, 0);
   for (int p = 0; p < P; ++p) {
@@ -172,7 +172,8 @@ int run_bundle_adjuster(const std::string& dir) {
       // residual w (f X/Z + c - x) = (w f) (X/Z - (x - c)/f)
       xa[2 * o] = (float)((oa.x - cx) / fx); xa[2 * o + 1] = (float)((oa.y - cy) / fy);
       xb[2 * o] = (float)((ob.x - cx) / fx); xb[2 * o + 1] = (float)((ob.y - cy) / fy);
-      w[o] = (float)(oa.wx * fx);
+      w[o] = (float)(oa.wx * fx);      // one weight per observation (ba_problem.h:60-151)
+      wb[o] = (float)(ob.wx * fx);
       for (int c = 0; c < 3; ++c) p0[3 * o + c] = pts[(size_t)3 * k + c];
     }
   }
@@ -186,15 +187,15 @@ int run_bundle_adjuster(const std::string& dir) {
   }
 
   need_gpu();
-  DevBuf<float> d_xa(xa), d_xb(xb), d_w(w), d_out((size_t)T * 16);
+  DevBuf<float> d_xa(xa), d_xb(xb), d_w(w), d_wb(wb), d_out((size_t)T * 16);
   DevBuf<double> d_p0(p0), d_extr(extr), d_out64((size_t)T * 16), d_cost(2);
   DevBuf<int> d_nv(n_valid), d_it(1);
   const size_t ws_bytes = mvm_mvba_workspace_bytes(T, P, 1, n_pad);
   DevBuf<unsigned char> d_ws(ws_bytes);
-  const int rc = mvm_multi_view_ba_ex(pa.data(), pb.data(), T, P, 1, n_pad, d_xa.p, d_xb.p, d_w.p, d_nv.p, d_extr.p, d_p0.p,
+  const int rc = mvm_multi_view_ba_obs(pa.data(), pb.data(), T, P, 1, n_pad, d_xa.p, d_xb.p, d_w.p, d_wb.p, d_nv.p, d_extr.p, d_p0.p,
                                       /*weights_prenormalized=*/1, d_out.p, d_out64.p, /*max_iterations=*/50, d_it.p,
                                       d_cost.p, d_ws.p, ws_bytes, nullptr);
-  if (rc != 0) die("mvm_multi_view_ba_ex failed with status " + std::to_string(rc), 3);
+  if (rc != 0) die("mvm_multi_view_ba_obs failed with status " + std::to_string(rc), 3);
   cuda_ok(cudaDeviceSynchronize(), "bundle adjustment kernel");
   const auto res = d_out64.download();
   const auto cost = d_cost.download();

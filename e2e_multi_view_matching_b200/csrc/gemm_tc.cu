@@ -306,6 +306,31 @@ const CUtensorMap* mvm_get_tmap_2d(const float* base, long long rows, long long 
   return mvm_get_tmap_3d(base, 0, rows, cols, ld, 0, box_rows);
 }
 
+// 2-D fp16 row-major [rows, cols] with row stride ld (elements), box = [box_rows, 64 cols = 128 B], 128B swizzle
+const CUtensorMap* mvm_get_tmap_2d_f16(const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  TmKey key(base, -16, rows, cols, ld, 0, box_rows);      // slabs = -16 marks the half-precision maps
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) return it->second;
+  EncodeFn enc = get_encode();
+  if (!enc) return nullptr;
+  CUtensorMap* tm = new CUtensorMap;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[mvm_b200] cuTensorMapEncodeTiled (f16) failed (%d) rows=%lld cols=%lld ld=%lld\n", (int)r, rows, cols, ld);
+    delete tm;
+    return nullptr;
+  }
+  g_tmaps[key] = tm;
+  return tm;
+}
+
 int g_gemm_bn = 256;   // output tile width of the one-tile-per-CTA tcgen05 GEMM (128 or 256), see mvm_debug_set_gemm_tile
 extern "C" void mvm_debug_set_gemm_tile(int bn) { g_gemm_bn = bn == 256 ? 256 : 128; }
 int g_gemm_persist = 1;   // 1: the persistent kernel of gemm_tc_persist.cu serves the 3xTF32 path (default)
@@ -313,14 +338,19 @@ extern "C" void mvm_debug_set_gemm_kernel(int persistent) { g_gemm_persist = per
 
 // GEMM on the tensor cores.  Requirements: K, K1 multiples of 32, N multiple of 128, 16-byte aligned
 // rows (lda/ldw/ldc/ldr multiples of 4).  n_pass: 3 = fp32-faithful 3xTF32, 1 = single-pass TF32.
+int mvm_default_gemm_tile() { return g_gemm_bn; }
+int mvm_default_gemm_persistent() { return g_gemm_persist; }
+
 int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_pad, cudaStream_t stream,
-                   float* KLO, float* VTLO) {
+                   float* KLO, float* VTLO, int gemm_tile, int gemm_persist) {
+  if (gemm_tile < 0) gemm_tile = g_gemm_bn;            // stage-level callers: the process defaults
+  if (gemm_persist < 0) gemm_persist = g_gemm_persist;
   MVM_REQUIRE(d.batch == 1 && d.K % BK == 0 && d.K1 % BK == 0 && d.N % 128 == 0);
   MVM_REQUIRE(d.lda % 4 == 0 && d.ldw % 4 == 0 && d.ldc % 4 == 0 && (d.R == nullptr || d.ldr % 4 == 0));
   MVM_REQUIRE(d.A2 == nullptr || d.lda2 % 4 == 0);
   MvmProfScope prof__(MVM_TAG_GEMM, stream);
-  if (g_gemm_persist && n_pass == 3 && d.Whi && d.Wlo) return launch_gemm_tc_persist(d, VT, vt_col0, n_pad, KLO, VTLO, stream);
-  if (g_gemm_bn == 256 && d.N % 256 == 0) {
+  if (gemm_persist && n_pass == 3 && d.Whi && d.Wlo) return launch_gemm_tc_persist(d, VT, vt_col0, n_pad, KLO, VTLO, stream);
+  if (gemm_tile == 256 && d.N % 256 == 0) {
     if (n_pass == 3 && d.Whi && d.Wlo) return launch_cfg<256, 3, true>(d, VT, vt_col0, n_pad, KLO, VTLO, stream);
     if (n_pass == 1) return launch_cfg<256, 1, false>(d, VT, vt_col0, n_pad, nullptr, nullptr, stream);
   }

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -52,6 +53,9 @@ struct PArgs {
   int relu;
   float* VT; int vt_col0; int n_pad;   // transposed output for columns >= vt_col0 (see gemm_tc.cu)
   float* KLO; float* VTLO;             // tf32 lo planes of the K / V^T attention operands
+  // half-precision operand planes for attention_h3.cu (fp16x3): K hi / lo [rows, 256], V^T hi / lo [V*256, n_pad];
+  // when set they replace the fp32 K third of C, KLO, VT and VTLO
+  __half* KH16; __half* KL16; __half* VTH16; __half* VTL16;
   int tiles_m, tiles_n;
 };
 
@@ -279,12 +283,19 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (has_r) x += r[j];
           v[j] = x;
         }
-        if (g.VT && nb >= g.vt_col0) {
+        if ((g.VT || g.VTH16) && nb >= g.vt_col0) {
           // V^T (and its lo plane) for the attention kernel: lanes = consecutive keypoints -> coalesced
           if (m < g.M) {
             const int slab = m / g.n_pad, ii = m % g.n_pad;
             const long long off = ((long long)slab * (g.N - g.vt_col0) + (nb - g.vt_col0)) * g.n_pad + ii;
-            if (g.VTLO) {
+            if (g.VTH16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const __half h = __float2half_rn(v[j]);
+                g.VTH16[off + (long long)j * g.n_pad] = h;
+                g.VTL16[off + (long long)j * g.n_pad] = __float2half_rn(v[j] - __half2float(h));
+              }
+            } else if (g.VTLO) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float h = tf32_hi(v[j]);
@@ -294,6 +305,28 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) g.VT[off + (long long)j * g.n_pad] = v[j];
+            }
+          }
+          continue;
+        }
+        if (g.KH16 && nb >= 256 && nb < 512) {
+          // K hi / lo planes in half precision: 64 contiguous bytes per row and plane
+          if (m < g.M) {
+            uint32_t hp[16], lp[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+              hp[j] = *reinterpret_cast<const uint32_t*>(&h);
+              lp[j] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            uint4* dh = reinterpret_cast<uint4*>(g.KH16 + (long long)m * 256 + (nb - 256));
+            uint4* dl = reinterpret_cast<uint4*>(g.KL16 + (long long)m * 256 + (nb - 256));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dh[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+              dl[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
             }
           }
           continue;
@@ -347,7 +380,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 // Requirements (checked by the dispatcher in gemm_tc.cu): pre-split W planes, N % 128 == 0, K % 32 == 0,
 // K1 % 32 == 0, 16-byte aligned rows.
 int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const HalfPlanes* hp) {
   mvm_once_per_device(MVM_ONCE_GEMM_PERSIST, [&] {
     cudaFuncSetAttribute(gemm_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
@@ -363,6 +396,8 @@ int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad,
   g.bias = d.bias; g.R = d.R; g.ldr = d.ldr; g.C = d.C; g.ldc = d.ldc; g.M = d.M; g.N = d.N; g.K = d.K;
   g.K1 = d.K1; g.alpha = d.alpha; g.relu = d.relu; g.VT = VT; g.vt_col0 = vt_col0; g.n_pad = n_pad;
   g.KLO = KLO; g.VTLO = VTLO;
+  g.KH16 = hp ? (__half*)hp->kh : nullptr; g.KL16 = hp ? (__half*)hp->kl : nullptr;
+  g.VTH16 = hp ? (__half*)hp->vth : nullptr; g.VTL16 = hp ? (__half*)hp->vtl : nullptr;
   g.tiles_m = mvm_div_up(d.M, BM); g.tiles_n = d.N / BN;
   const int n_tiles = g.tiles_m * g.tiles_n;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;

@@ -29,11 +29,17 @@ int launch_transpose_cn(const float* in, float* out, int n_views_total, int C, i
                         cudaStream_t stream);
 
 // tcgen05 GEMM (gemm_tc.cu): n_pass 3 = fp32-faithful 3xTF32, 1 = single-pass TF32
+// gemm_tile (128 / 256) and gemm_persist (0 / 1) select the kernel; -1 = the process defaults
 int launch_gemm_tc(const GemmDesc& d, int n_pass, float* VT, int vt_col0, int n_pad, cudaStream_t stream,
-                   float* KLO = nullptr, float* VTLO = nullptr);
+                   float* KLO = nullptr, float* VTLO = nullptr, int gemm_tile = -1, int gemm_persist = -1);
+int mvm_default_gemm_tile();
+int mvm_default_gemm_persistent();
 // persistent 3xTF32 kernel (A operand in tensor memory, double-buffered accumulators, TMA-store epilogue)
+// hp != nullptr (QKV projection, vt_col0 = 512): the K third and V^T leave as half-precision hi / lo planes for
+// launch_attention_h3 instead of the fp32 / tf32 buffers (kh, kl [rows, 256]; vth, vtl [V*256, n_pad], as __half)
+struct HalfPlanes { void* kh; void* kl; void* vth; void* vtl; };
 int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const HalfPlanes* hp = nullptr);
 // every (pair, tuple) score matrix in one launch of the persistent kernel (3xTF32); hi / lo: scratch [rows, 256]
 struct PairTable;
 int launch_score_gemm_tc(const float* mdesc, float* hi, float* lo, int n_pad, const PairTable& tab, int batch,
@@ -49,6 +55,10 @@ int launch_attention_tc(const float* qkv, const float* vt, float* out, int batch
                         const float* vtlo = nullptr);
 int launch_attention_simt(const float* qkv, float* out, int batch, int n_pad, AttnSegs segs,
                           int is_cross, cudaStream_t stream);
+// fp32-faithful attention with half-precision operand planes (fp16x3, attention_h3.cu); planes as in HalfPlanes
+struct __half;
+int launch_attention_h3(const float* qkv, const __half* kh, const __half* kl, const __half* vth, const __half* vtl,
+                        float* out, int batch, int n_pad, AttnSegs segs, int is_cross, cudaStream_t stream);
 
 // scores[p][bi] inner block = mdesc[a] . mdesc[b]^T * alpha   (mdesc: [views, n_pad, 256])
 int launch_score_gemm_simt(const float* mdesc, int n_pad, const PairTable& tab, int batch,

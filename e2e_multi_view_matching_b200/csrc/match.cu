@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(256) rowcol_argmax_kernel(PairTable tab, int b
       ArgMax other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
       best = better(best, other);
     }
-    if (lane == 0) { idx0[i] = best.i; max0[i] = best.v; }
+    // an all-NaN row never replaces the sentinel: clamp so that the index stays usable (the reference returns
+    // garbage for NaN inputs; an out-of-range index here would be an illegal address in mutual_kernel / conf_gather)
+    if (lane == 0) { idx0[i] = best.i == 0x7fffffff ? 0 : best.i; max0[i] = best.v; }
   } else {
     __shared__ float sv[8][32];
     __shared__ int si[8][32];
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256) rowcol_argmax_kernel(PairTable tab, int b
     __syncthreads();
     if (warp == 0 && j < n) {
       for (int w = 1; w < 8; ++w) best = better(best, ArgMax{sv[w][lane], si[w][lane]});
-      idx1[j] = best.i;
+      idx1[j] = best.i == 0x7fffffff ? 0 : best.i;
     }
   }
 }

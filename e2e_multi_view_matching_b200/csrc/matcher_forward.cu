@@ -6,6 +6,7 @@
 #include "../../include/mvm_b200.h"
 #include "common.cuh"
 #include "kernels.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -64,18 +65,25 @@ GemmDesc make_gemm(const float* A, int lda, const float* W, int K, const float* 
   return g;
 }
 
-// math mode of the 1x1-conv GEMMs and attention: 3 = tcgen05 3xTF32 (fp32-faithful, DEFAULT),
-// 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA cores (cross-check path)
+// PROCESS DEFAULTS of the per-call options (mvm_matcher_options).  They are read once, at the top of
+// mvm_matcher_forward, to fill the options of that call; nothing below this point reads or writes a global,
+// so two models / two streams / two threads may run forwards concurrently (each with its own workspace).
+// math mode: 3 = tcgen05 3xTF32 (fp32-faithful, DEFAULT), 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA cores
 int g_math_mode = 3;
-
-long long g_hi_off = 0, g_lo_off = 0;   // set per forward from mvm_matcher_weights
 int g_score_tc = 1;                     // score GEMM on the tensor cores in mode 3 (mvm_debug_set_score_kernel)
+int g_attn_split = 1;                   // operand planes of the mode-3 attention: 1 = fp16 hi/lo (default), 0 = tf32 hi/lo
 
-int run_gemm(const GemmDesc& g_in, cudaStream_t s) {
+// everything a forward needs to know beyond its arguments, by value
+struct Ctx {
+  int math_mode, score_tc, gemm_tile, gemm_persist, sinkhorn_variant, attn_split;
+  long long hi_off, lo_off;             // tf32 planes of the weights (mvm_matcher_weights)
+};
+
+int run_gemm(const Ctx& cx, const GemmDesc& g_in, cudaStream_t s) {
   GemmDesc g = g_in;
-  if (g_math_mode == 3 && g_lo_off != 0) { g.Whi = g.W + g_hi_off; g.Wlo = g.W + g_lo_off; }
-  if (g_math_mode != 0 && g.batch == 1 && g.N % 128 == 0 && g.K % 32 == 0 && g.K1 % 32 == 0 && g.ldc % 4 == 0)
-    return launch_gemm_tc(g, g_math_mode, nullptr, 0, 0, s);
+  if (cx.math_mode == 3 && cx.lo_off != 0) { g.Whi = g.W + cx.hi_off; g.Wlo = g.W + cx.lo_off; }
+  if (cx.math_mode != 0 && g.batch == 1 && g.N % 128 == 0 && g.K % 32 == 0 && g.K1 % 32 == 0 && g.ldc % 4 == 0)
+    return launch_gemm_tc(g, cx.math_mode, nullptr, 0, 0, s, nullptr, nullptr, cx.gemm_tile, cx.gemm_persist);
   return launch_gemm_simt(g, s);
 }
 
@@ -111,6 +119,7 @@ int fill_pair_table(PairTable& tab, const mvm_pair_io* pairs, int n_pairs, int n
 extern "C" {
 
 void mvm_debug_set_score_kernel(int tc) { g_score_tc = tc ? 1 : 0; }
+void mvm_debug_set_attention_split(int fp16) { g_attn_split = fp16 ? 1 : 0; }
 
 const char* mvm_version(void) { return "mvm_b200 0.1 sm_100a"; }
 
@@ -118,12 +127,35 @@ size_t mvm_matcher_workspace_bytes(int batch, int n_views, int n_pad, int n_pair
   return carve(nullptr, batch, n_views, n_pad, n_pairs, has_conf).total;
 }
 
+void mvm_matcher_options_default(mvm_matcher_options* o) {
+  if (!o) return;
+  o->math_mode = g_math_mode;
+  o->score_kernel = g_score_tc;
+  o->gemm_tile = mvm_default_gemm_tile();
+  o->gemm_kernel = mvm_default_gemm_persistent();
+  o->sinkhorn_variant = 0;
+  o->attention_split = g_attn_split;
+}
+
 int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, int n_pad,
                         const int* counts, const float* kpts, const float* kscores,
                         const float* desc, float img_w, float img_h, int sinkhorn_iters,
                         float match_threshold, const mvm_pair_io* pairs, int n_pairs,
                         void* workspace, size_t workspace_bytes, void* stream_) {
+  return mvm_matcher_forward_ex(w, batch, n_views, n_pad, counts, kpts, kscores, desc, img_w, img_h, sinkhorn_iters,
+                                match_threshold, pairs, n_pairs, workspace, workspace_bytes, nullptr, stream_);
+}
+
+int mvm_matcher_forward_ex(const mvm_matcher_weights* w, int batch, int n_views, int n_pad,
+                           const int* counts, const float* kpts, const float* kscores,
+                           const float* desc, float img_w, float img_h, int sinkhorn_iters,
+                           float match_threshold, const mvm_pair_io* pairs, int n_pairs,
+                           void* workspace, size_t workspace_bytes, const mvm_matcher_options* opt, void* stream_) {
   cudaStream_t s = (cudaStream_t)stream_;
+  mvm_matcher_options o;
+  if (opt) o = *opt; else mvm_matcher_options_default(&o);
+  MVM_REQUIRE(o.math_mode == 0 || o.math_mode == 1 || o.math_mode == 3);
+  MVM_REQUIRE(o.sinkhorn_variant >= 0 && o.sinkhorn_variant <= 3);
   MVM_REQUIRE(w && counts && kpts && kscores && desc && pairs && workspace);
   MVM_REQUIRE(batch >= 1 && n_views >= 2 && n_views <= MVM_MAX_VIEWS);
   MVM_REQUIRE(n_pad >= 64 && n_pad % 64 == 0);
@@ -132,7 +164,12 @@ int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, in
   Workspace ws = carve((char*)workspace, batch, n_views, n_pad, n_pairs, w->has_conf);
   if (ws.total > workspace_bytes) return MVM_ERR_WORKSPACE;
 
-  g_hi_off = w->hi_offset; g_lo_off = w->lo_offset;
+  Ctx cx;
+  cx.math_mode = o.math_mode; cx.score_tc = o.score_kernel ? 1 : 0; cx.gemm_tile = o.gemm_tile == 128 ? 128 : 256;
+  cx.gemm_persist = o.gemm_kernel ? 1 : 0; cx.sinkhorn_variant = o.sinkhorn_variant;
+  cx.hi_off = w->hi_offset; cx.lo_off = w->lo_offset;
+  // the fp16x3 attention needs the persistent GEMM (its epilogue writes the half-precision planes) and pre-split weights
+  cx.attn_split = (o.attention_split == 1 && cx.math_mode == 3 && cx.lo_off != 0) ? 1 : 0;
   const int V = batch * n_views;
   const int rows = V * n_pad;
   AttnSegs segs;
@@ -142,69 +179,80 @@ int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, in
   // keypoint encoder + descriptor add (multi_view_matcher.py:265-269)
   MVM_TRY(launch_transpose_cn(desc, ws.DT, V, 256, n_pad, s));
   MVM_TRY(launch_kenc_front(kpts, kscores, w->kenc_w, w->kenc_b, ws.H3, rows, img_w, img_h, s));
-  MVM_TRY(run_gemm(make_gemm(ws.H3, 128, w->kenc_w[3], 128, w->kenc_b[3], ws.H4, 256, rows, 256, 1), s));
+  MVM_TRY(run_gemm(cx, make_gemm(ws.H3, 128, w->kenc_w[3], 128, w->kenc_b[3], ws.H4, 256, rows, 256, 1), s));
   {
     GemmDesc g = make_gemm(ws.H4, 256, w->kenc_w[4], 256, w->kenc_b[4], ws.X, 256, rows, 256, 0);
     g.R = ws.DT; g.ldr = 256;
-    MVM_TRY(run_gemm(g, s));
+    MVM_TRY(run_gemm(cx, g, s));
   }
 
   // attentional GNN (multi_view_matcher.py:87-100 / superglue.py:131-140)
   for (int l = 0; l < w->n_layers; ++l) {
     const mvm_layer_weights& L = w->layers[l];
-    if (g_math_mode != 0) {
-      // tensor-core path: the QKV GEMM epilogue also writes V^T [view, 256, n_pad] for the P.V product
-      float* klo = g_math_mode == 3 ? ws.KLO : nullptr;
-      float* vtlo = g_math_mode == 3 ? ws.VTLO : nullptr;
+    if (cx.attn_split == 1) {
+      // fp16x3: K and V^T leave the QKV GEMM as half-precision hi / lo planes (carved out of the tf32 lo-plane
+      // buffers: two fp16 planes fill one fp32 plane exactly)
+      __half* kh = reinterpret_cast<__half*>(ws.KLO);
+      __half* vth = reinterpret_cast<__half*>(ws.VTLO);
+      HalfPlanes hp = {kh, kh + (size_t)rows * 256, vth, vth + (size_t)rows * 256};
       GemmDesc gq = make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0);
-      if (g_math_mode == 3 && g_lo_off != 0) { gq.Whi = gq.W + g_hi_off; gq.Wlo = gq.W + g_lo_off; }
-      MVM_TRY(launch_gemm_tc(gq, g_math_mode, ws.VT, 512, n_pad, s, klo, vtlo));
-      MVM_TRY(launch_attention_tc(ws.QKV, ws.VT, ws.MSG, batch, n_pad, segs, L.is_cross, g_math_mode, s, klo, vtlo));
+      gq.Whi = gq.W + cx.hi_off; gq.Wlo = gq.W + cx.lo_off;
+      MVM_TRY(launch_gemm_tc_persist(gq, nullptr, 512, n_pad, nullptr, nullptr, s, &hp));
+      MVM_TRY(launch_attention_h3(ws.QKV, (const __half*)hp.kh, (const __half*)hp.kl, (const __half*)hp.vth,
+                                  (const __half*)hp.vtl, ws.MSG, batch, n_pad, segs, L.is_cross, s));
+    } else if (cx.math_mode != 0) {
+      // tensor-core path: the QKV GEMM epilogue also writes V^T [view, 256, n_pad] for the P.V product
+      float* klo = cx.math_mode == 3 ? ws.KLO : nullptr;
+      float* vtlo = cx.math_mode == 3 ? ws.VTLO : nullptr;
+      GemmDesc gq = make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0);
+      if (cx.math_mode == 3 && cx.lo_off != 0) { gq.Whi = gq.W + cx.hi_off; gq.Wlo = gq.W + cx.lo_off; }
+      MVM_TRY(launch_gemm_tc(gq, cx.math_mode, ws.VT, 512, n_pad, s, klo, vtlo, cx.gemm_tile, cx.gemm_persist));
+      MVM_TRY(launch_attention_tc(ws.QKV, ws.VT, ws.MSG, batch, n_pad, segs, L.is_cross, cx.math_mode, s, klo, vtlo));
     } else {
-      MVM_TRY(run_gemm(make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), s));
+      MVM_TRY(run_gemm(cx, make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0), s));
       MVM_TRY(launch_attention_simt(ws.QKV, ws.MSG, batch, n_pad, segs, L.is_cross, s));
     }
     // attn.merge (superglue.py:109) is linear and feeds mlp.0 directly (:121): packing.py folds it into the
     // message half of mlp.0 (w_merge == NULL); an unfolded weight set still runs the separate GEMM
     const float* msg = ws.MSG;
     if (L.w_merge) {
-      MVM_TRY(run_gemm(make_gemm(ws.MSG, 256, L.w_merge, 256, L.b_merge, ws.MRG, 256, rows, 256, 0), s));
+      MVM_TRY(run_gemm(cx, make_gemm(ws.MSG, 256, L.w_merge, 256, L.b_merge, ws.MRG, 256, rows, 256, 0), s));
       msg = ws.MRG;
     }
     {
       GemmDesc g = make_gemm(ws.X, 256, L.w_mlp0, 512, L.b_mlp0, ws.H, 512, rows, 512, 1);
       g.A2 = msg; g.lda2 = 256; g.K1 = 256;      // cat([x, message]) by K-split
-      MVM_TRY(run_gemm(g, s));
+      MVM_TRY(run_gemm(cx, g, s));
     }
     {
       GemmDesc g = make_gemm(ws.H, 512, L.w_mlp1, 512, L.b_mlp1, ws.X, 256, rows, 256, 0);
       g.R = ws.X; g.ldr = 256;                   // desc = desc + delta
-      MVM_TRY(run_gemm(g, s));
+      MVM_TRY(run_gemm(cx, g, s));
     }
   }
 
   // final projection once per view (the reference redoes it per pair, :276)
-  MVM_TRY(run_gemm(make_gemm(ws.X, 256, w->w_final, 256, w->b_final, ws.MD, 256, rows, 256, 0), s));
+  MVM_TRY(run_gemm(cx, make_gemm(ws.X, 256, w->w_final, 256, w->b_final, ws.MD, 256, rows, 256, 0), s));
 
   PairTable tab;
   MVM_TRY(fill_pair_table(tab, pairs, n_pairs, n_views, counts, batch));
   // score matrices: tensor cores in the 3xTF32 mode (the K_lo / V^T_lo planes of the GNN are free again and
   // hold the tf32 planes of the descriptors), fp32 CUDA cores otherwise
-  if (g_math_mode == 3 && g_score_tc) MVM_TRY(launch_score_gemm_tc(ws.MD, ws.KLO, ws.VTLO, n_pad, tab, batch, 1.0f / 16.0f, s));
+  if (cx.math_mode == 3 && cx.score_tc) MVM_TRY(launch_score_gemm_tc(ws.MD, ws.KLO, ws.VTLO, n_pad, tab, batch, 1.0f / 16.0f, s));
   else MVM_TRY(launch_score_gemm_simt(ws.MD, n_pad, tab, batch, 1.0f / 16.0f, s));
-  MVM_TRY(launch_sinkhorn(tab, batch, w->bin_score, sinkhorn_iters, ws.sink_ws, s));
+  MVM_TRY(launch_sinkhorn(tab, batch, w->bin_score, sinkhorn_iters, ws.sink_ws, s, cx.sinkhorn_variant));
   MVM_TRY(launch_extract_matches(tab, batch, n_pad, match_threshold, ws.match_ws, s));
 
   if (w->has_conf) {
     const long long crow = (long long)n_pairs * batch * n_pad;
     MVM_TRY(launch_conf_gather(ws.MD, tab, batch, n_pad, ws.FEAT, ws.SC, s));
-    MVM_TRY(run_gemm(make_gemm(ws.FEAT, 512, w->conf_wf0, 512, w->conf_bf0, ws.CF1, 512, (int)crow, 512, 1), s));
-    MVM_TRY(run_gemm(make_gemm(ws.CF1, 512, w->conf_wf1, 512, w->conf_bf1, ws.CF2, 256, (int)crow, 256, 1), s));
+    MVM_TRY(run_gemm(cx, make_gemm(ws.FEAT, 512, w->conf_wf0, 512, w->conf_bf0, ws.CF1, 512, (int)crow, 512, 1), s));
+    MVM_TRY(run_gemm(cx, make_gemm(ws.CF1, 512, w->conf_wf1, 512, w->conf_bf1, ws.CF2, 256, (int)crow, 256, 1), s));
     MVM_TRY(launch_conf_c0(ws.SC, w->conf_wc0, w->conf_bc0, ws.CC0, crow, s));
     {
       GemmDesc g = make_gemm(ws.CC0, 256, w->conf_wc1, 256, w->conf_bc1, ws.CC1, 256, (int)crow, 256, 1);
       g.R = ws.CF2; g.ldr = 256;                 // out_f + out_c
-      MVM_TRY(run_gemm(g, s));
+      MVM_TRY(run_gemm(cx, g, s));
     }
     MVM_TRY(launch_conf_final(ws.CC1, w->conf_wl, w->conf_bl, tab, batch, n_pad, s));
   }
@@ -295,6 +343,16 @@ int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, i
   for (int t = 0; t < 8; ++t) segs.counts[t] = t < n_views ? counts[t] : 0;
   MVM_REQUIRE(n_pass == 1 || (klo && vtlo));
   return launch_attention_tc(qkv, vt, out, batch, n_pad, segs, is_cross, n_pass, (cudaStream_t)stream, klo, vtlo);
+}
+
+int mvm_attention_h3(const float* qkv, const void* kh, const void* kl, const void* vth, const void* vtl, float* out,
+                     int batch, int n_views, int n_pad, const int* counts, int is_cross, void* stream) {
+  MVM_REQUIRE(qkv && kh && kl && vth && vtl && out && counts && n_views >= 1 && n_views <= 8);
+  AttnSegs segs;
+  segs.n_views = n_views;
+  for (int t = 0; t < 8; ++t) segs.counts[t] = t < n_views ? counts[t] : 0;
+  return launch_attention_h3(qkv, (const __half*)kh, (const __half*)kl, (const __half*)vth, (const __half*)vtl, out, batch,
+                             n_pad, segs, is_cross, (cudaStream_t)stream);
 }
 
 int mvm_log_optimal_transport_logdomain(float* scores, int batch, int m, int n, float bin_score, int iters,

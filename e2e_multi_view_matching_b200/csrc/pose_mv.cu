@@ -190,7 +190,8 @@ struct MvbaArgs {
   int n_views, n_pairs, batch, n_pad, n_groups;
   int a[MVM_MAX_PAIRS], b[MVM_MAX_PAIRS];
   const float* xa; const float* xb;     // [B,P,n_pad,2] normalised observations in views a, b
-  const float* conf;                    // [B,P,n_pad]
+  const float* conf;                    // [B,P,n_pad] weight of a match (both observations), or of its view-a observation
+  const float* conf_b;                  // [B,P,n_pad] weight of the view-b observation (per-observation weights), or null
   const int* n_valid;                   // [B,P]
   const double* extr_init;              // [B,T,16]
   const double* pts_init;               // [B,P,n_pad,3] given initial points, or null: DLT from extr_init
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
     const float* xa = g.xa + prob * g.n_pad * 2;
     const float* xb = g.xb + prob * g.n_pad * 2;
     const float* cf = g.conf + prob * g.n_pad;
+    const float* cfb = g.conf_b ? g.conf_b + prob * g.n_pad : cf;     // BaProblem weights are per OBSERVATION (ba_problem.h:60-151)
     double* pcur = g.pts + prob * 2 * g.n_pad * 3;
     double* pnew = pcur + (long long)g.n_pad * 3;
     double* psc = g.pscale + prob * g.n_pad * 3;
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
     // ---- confidence normalisation over all observations of the tuple (:56-60) ----
     {
       double c = 0.0;
-      for (int i = tid; i < n; i += NT) c += 2.0 * (double)cf[i];
+      for (int i = tid; i < n; i += NT) c += (double)cf[i] + (double)cfb[i];
       wacc(&s_acc[warp][0], c, lane);
       exchange(1);
     }
@@ -466,10 +468,10 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         double na[6] = {0, 0, 0, 0, 0, 0}, nb[6] = {0, 0, 0, 0, 0, 0};
         if (i < n) {
           const double pt[3] = {pcur[3 * i], pcur[3 * i + 1], pcur[3 * i + 2]};
-          const double w = (double)cf[i] * wscale;
+          const double w = (double)cf[i] * wscale, wB = (double)cfb[i] * wscale;
           Obs oa, ob;
           eval_obs(fix_a, s_cam[va], s_Ra, one6, pt, one3, xa[2 * i], xa[2 * i + 1], w, true, oa);
-          eval_obs(fix_b, s_cam[vb], s_Rb, one6, pt, one3, xb[2 * i], xb[2 * i + 1], w, true, ob);
+          eval_obs(fix_b, s_cam[vb], s_Rb, one6, pt, one3, xb[2 * i], xb[2 * i + 1], wB, true, ob);
           for (int c = 0; c < 3; ++c) {
             const double s = oa.Jp[0][c] * oa.Jp[0][c] + oa.Jp[1][c] * oa.Jp[1][c] +
                              ob.Jp[0][c] * ob.Jp[0][c] + ob.Jp[1][c] * ob.Jp[1][c];
@@ -514,9 +516,9 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
         if (act) {
           const double pt[3] = {pcur[3 * i], pcur[3 * i + 1], pcur[3 * i + 2]};
           const double sp[3] = {psc[3 * i], psc[3 * i + 1], psc[3 * i + 2]};
-          const double w = (double)cf[i] * wscale;
+          const double w = (double)cf[i] * wscale, wB = (double)cfb[i] * wscale;
           eval_obs(fix_a, s_cam[va], s_Ra, s_sc[va], pt, sp, xa[2 * i], xa[2 * i + 1], w, true, oa);
-          eval_obs(fix_b, s_cam[vb], s_Rb, s_sc[vb], pt, sp, xb[2 * i], xb[2 * i + 1], w, true, ob);
+          eval_obs(fix_b, s_cam[vb], s_Rb, s_sc[vb], pt, sp, xb[2 * i], xb[2 * i + 1], wB, true, ob);
           cost = 0.5 * (oa.r[0] * oa.r[0] + oa.r[1] * oa.r[1] + ob.r[0] * ob.r[0] + ob.r[1] * ob.r[1]);
           // point block M = Hpp + clamp(diag)/radius
           double H[6];
@@ -678,10 +680,10 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
           if (i < n && solved) {
             const double pt[3] = {pcur[3 * i], pcur[3 * i + 1], pcur[3 * i + 2]};
             const double sp[3] = {psc[3 * i], psc[3 * i + 1], psc[3 * i + 2]};
-            const double w = (double)cf[i] * wscale;
+            const double w = (double)cf[i] * wscale, wB = (double)cfb[i] * wscale;
             Obs oa, ob;
             eval_obs(fix_a, s_cam[va], Rca, s_sc[va], pt, sp, xa[2 * i], xa[2 * i + 1], w, true, oa);
-            eval_obs(fix_b, s_cam[vb], Rcb, s_sc[vb], pt, sp, xb[2 * i], xb[2 * i + 1], w, true, ob);
+            eval_obs(fix_b, s_cam[vb], Rcb, s_sc[vb], pt, sp, xb[2 * i], xb[2 * i + 1], wB, true, ob);
             double H[6];
             int e = 0;
             for (int r = 0; r < 3; ++r)
@@ -721,7 +723,7 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
             Obs na, nb;
             const double one6[6] = {1, 1, 1, 1, 1, 1}, one3[3] = {1, 1, 1};
             eval_obs(fix_a, s_camn[va], s_Ra, one6, pn, one3, xa[2 * i], xa[2 * i + 1], w, false, na);
-            eval_obs(fix_b, s_camn[vb], s_Rb, one6, pn, one3, xb[2 * i], xb[2 * i + 1], w, false, nb);
+            eval_obs(fix_b, s_camn[vb], s_Rb, one6, pn, one3, xb[2 * i], xb[2 * i + 1], wB, false, nb);
             cnew = 0.5 * (na.r[0] * na.r[0] + na.r[1] * na.r[1] + nb.r[0] * nb.r[0] + nb.r[1] * nb.r[1]);
           }
           wacc(&s_acc[warp][0], cnew, lane);
@@ -885,6 +887,17 @@ int mvm_multi_view_ba_ex(const int* pair_a, const int* pair_b, int n_views, int 
                          int weights_prenormalized, float* extr_out, double* extr_out_f64, int max_iterations,
                          int* iterations_out, double* cost_out, void* workspace, size_t workspace_bytes,
                          void* stream_) {
+  return mvm_multi_view_ba_obs(pair_a, pair_b, n_views, n_pairs, batch, n_pad, xn_a, xn_b, conf, nullptr, n_valid, extr_init,
+                               points_init, weights_prenormalized, extr_out, extr_out_f64, max_iterations, iterations_out,
+                               cost_out, workspace, workspace_bytes, stream_);
+}
+
+int mvm_multi_view_ba_obs(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch,
+                         int n_pad, const float* xn_a, const float* xn_b, const float* conf, const float* conf_b,
+                         const int* n_valid, const double* extr_init, const double* points_init,
+                         int weights_prenormalized, float* extr_out, double* extr_out_f64, int max_iterations,
+                         int* iterations_out, double* cost_out, void* workspace, size_t workspace_bytes,
+                         void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MVM_REQUIRE(pair_a && pair_b && xn_a && xn_b && conf && n_valid && extr_init && extr_out && workspace);
   MVM_REQUIRE(n_views >= 2 && n_views <= MVM_MAX_VIEWS && n_pairs >= 1 && n_pairs <= MVM_MAX_PAIRS);
@@ -898,7 +911,7 @@ int mvm_multi_view_ba_ex(const int* pair_a, const int* pair_b, int n_views, int 
   if (groups < 1) return MVM_ERR_INVALID;
   if (groups > batch) groups = batch;
   g.n_groups = groups;
-  g.xa = xn_a; g.xb = xn_b; g.conf = conf; g.n_valid = n_valid; g.extr_init = extr_init;
+  g.xa = xn_a; g.xb = xn_b; g.conf = conf; g.conf_b = conf_b; g.n_valid = n_valid; g.extr_init = extr_init;
   g.pts_init = points_init; g.prenorm = weights_prenormalized ? 1 : 0; g.extr_out64 = extr_out_f64;
   g.extr_out = extr_out; g.max_iter = max_iterations; g.iters_out = iterations_out; g.cost_out = cost_out;
   g.timing = g_mvba_timing;

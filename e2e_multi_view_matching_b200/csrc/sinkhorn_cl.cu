@@ -49,12 +49,61 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned saddr, unsigned rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f32(unsigned addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+
+// remote shared-memory store that reports its 4 bytes to an mbarrier of the destination CTA
+__device__ __forceinline__ void st_async_f32(unsigned addr, float v, unsigned mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr),
+               "r"(__float_as_uint(v)), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
 }
 
 struct OpSum { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
 struct OpMax { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+
+// 8 values per lane, reduced over the 32 lanes in 9 shuffles; afterwards every lane holds the total of value index
+// row8(lane) (the four lanes that differ in bits 0-1 hold the same value).
+template <class Op>
+__device__ __forceinline__ float reduce8(float (&p)[8], int lane, Op op) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool hi = lane & 16;
+    const float send = hi ? p[k] : p[k + 4], keep = hi ? p[k + 4] : p[k];
+    p[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool hi = lane & 8;
+    const float send = hi ? p[k] : p[k + 2], keep = hi ? p[k + 2] : p[k];
+    p[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+  {
+    const bool hi = lane & 4;
+    const float send = hi ? p[0] : p[1], keep = hi ? p[1] : p[0];
+    p[0] = op(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+  p[0] = op(p[0], __shfl_xor_sync(0xffffffffu, p[0], 2));
+  return op(p[0], __shfl_xor_sync(0xffffffffu, p[0], 1));
+}
+__device__ __forceinline__ int row8(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
 
 // 16 values per lane, reduced over the 32 lanes in 16 shuffles; afterwards every lane holds the total of
 // value index row16(lane) (lanes 2k and 2k+1 hold the same value).
@@ -119,9 +168,13 @@ constexpr int OFF_UT = OFF_A + CL_ROWS + 4;           // [64] absorbed row poten
 constexpr int OFF_E = OFF_UT + CL_ROWS;               // [64] exp(alpha + u~_i): dustbin column of K~ / kb_n
 constexpr int OFF_EA = OFF_E + CL_ROWS;               // [64] e_i a_i (dustbin column terms; 0 beyond the CTA's rows)
 constexpr int OFF_AW = OFF_EA + CL_ROWS;              // [32][16] per-warp copy of the row scalings of its row group
-constexpr int OFF_KS = OFF_AW + 32 * 16;              // [4][16-RR][LD]
-static_assert(OFF_KS % 4 == 0 && OFF_A % 4 == 0 && OFF_COLPART % 4 == 0, "16-byte alignment of the float4 regions");
-inline size_t cl_smem_bytes(int n, int RS) { return (size_t)(OFF_KS + 4 * RS * ((n + 127) & ~127)) * sizeof(float); }
+constexpr int OFF_DUST = OFF_AW + 32 * 16;            // [8] strip partials of the dustbin row sum
+constexpr int OFF_MBAR = OFF_DUST + 8;                // 2 x 8-byte mbarriers (A: partials landed, B: b landed)
+constexpr int OFF_KS = OFF_MBAR + 4;                  // [4][16-RR][1024]  (compile-time row stride: immediate offsets)
+static_assert(OFF_KS % 4 == 0 && OFF_A % 4 == 0 && OFF_COLPART % 4 == 0 && OFF_AW % 4 == 0 && OFF_KB % 4 == 0,
+              "16-byte alignment of the float4 regions");
+static_assert(OFF_MBAR % 2 == 0, "8-byte alignment of the mbarriers");
+inline size_t cl_smem_bytes(int n, int RS) { (void)n; return (size_t)(OFF_KS + 4 * RS * CL_MAXN) * sizeof(float); }
 
 template <int RR, bool TIMING>
 __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, SinkClCfg cfg) {
@@ -140,7 +193,8 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
   float* Zg = tab.scores[p] + (long long)bi * (m + 1) * ld;
   const int R = (m + C - 1) / C;
   const int r0 = min(m, (int)c * R), nrows = min(m, r0 + R) - r0;
-  const int LD = (n + 127) & ~127, CS = (n + 1 + C - 1) / C;
+  constexpr int LD = CL_MAXN;
+  const int CS = (n + 1 + C - 1) / C;
   const bool active = cw * 128 < n;
   const int col0 = cw * 128 + lane * 4;
 
@@ -155,6 +209,7 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
   float* const e_s = smem + OFF_E;
   float* const ea_s = smem + OFF_EA;
   float* const aw_s = smem + OFF_AW;
+  float* const dust_s = smem + OFF_DUST;
   float* const ksm = smem + OFF_KS + (size_t)rg * RS * LD + col0;   // this thread's shared-memory rows (i >= RR)
 
   const float mu = 1.0f / (float)(m + n), mu_bin = (float)n / (float)(m + n);
@@ -213,10 +268,33 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
     }
     if (active) K_PUT(i, k4);
   }
+  // ---- exchange machinery: two transaction mbarriers per CTA.  mbar A completes when the C partials of every
+  // column this CTA owns have landed in crecv; mbar B when all n+1 merged b_j have landed in b_s.  The values
+  // travel by st.async (remote shared-memory store that reports its bytes to the destination's mbarrier), so an
+  // iteration has no cluster-wide barrier: a CTA only ever waits for the data it needs. ----
+  const unsigned mbarA = smem_u32(smem + OFF_MBAR), mbarB = mbarA + 8;
+  const int owned = max(0, min(n + 1, ((int)c + 1) * CS) - (int)c * CS);
+  if (tid == 0) {
+    mbar_init(mbarA, 1);
+    mbar_init(mbarB, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 8) dust_s[tid] = 0.f;
+  // the row-max scratch of the strips beyond the last column becomes the (never written) zero partial of those strips
+  for (int j = tid; j < 8 * CL_ROWS; j += blockDim.x)
+    if ((j / CL_ROWS) * 128 >= n) rowpart[j] = 0.f;
   // peers' shared memory is about to be written: every CTA of the cluster must have started
   cluster_sync_all();
 
   const unsigned crecv_addr = smem_u32(crecv), b_addr = smem_u32(b_s);
+  // column j = tid of this CTA's partial sums goes to slot (c, j - owner CS) of its owner (n <= 1024: one column per
+  // thread; the dustbin column n is pushed by warp 31)
+  unsigned push_addr = 0, push_mbar = 0;
+  if (tid < n) {
+    const int owner = tid / CS, slot = tid - owner * CS;
+    push_addr = mapa_u32(crecv_addr + (unsigned)(((int)c * CS + slot) * 4), (unsigned)owner);
+    push_mbar = mapa_u32(mbarA, (unsigned)owner);
+  }
   unsigned tacc[6] = {0u, 0u, 0u, 0u, 0u, 0u};
   unsigned tprev = 0;
   if (TIMING) tprev = (unsigned)clock();
@@ -230,6 +308,11 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
   } while (0)
 
   for (int it = 0; it < cfg.iters; ++it) {
+    const unsigned ph = (unsigned)it & 1u;
+    if (tid == 0) {   // arm this iteration's phase (transactions that arrive earlier are accounted for)
+      mbar_expect_tx(mbarA, (unsigned)(owned * C * 4));
+      mbar_expect_tx(mbarB, (unsigned)((n + 1) * 4));
+    }
     // ---- row pass: partial sums of sum_j K~_ij b_j over this warp's 128-column strip ----
     const float bin_col = kb_s[n] * b_s[n];
     int cbad = 0;
@@ -237,22 +320,31 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
       const float4 b4 = load_b4(b_s, col0, n);
       // column re-absorption is decided on the freshly merged b (identical in every CTA of the cluster)
       cbad = (fmaxf(fmaxf(b4.x, b4.y), fmaxf(b4.z, b4.w)) > ABSORB_HI) | (fminf(fminf(b4.x, b4.y), fminf(b4.z, b4.w)) < ABSORB_LO);
-      float part[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 k = K_GET(i);
-        part[i] = fmaf(k.w, b4.w, fmaf(k.z, b4.z, fmaf(k.y, b4.y, k.x * b4.x)));
+      for (int h8 = 0; h8 < 2; ++h8) {           // two groups of 8 rows: 8 partials live instead of 16
+        float part[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 k = K_GET(h8 * 8 + i);
+          part[i] = fmaf(k.w, b4.w, fmaf(k.z, b4.z, fmaf(k.y, b4.y, k.x * b4.x)));
+        }
+        const float v = reduce8(part, lane, OpSum());
+        if (!(lane & 3)) rowpart[cw * CL_ROWS + rg * 16 + h8 * 8 + row8(lane)] = v;
       }
-      const float v = reduce16(part, lane, OpSum());
-      if (!(lane & 1)) rowpart[cw * CL_ROWS + rg * 16 + row16(lane)] = v;
+      if (rg == 0) {   // dustbin row (replicated in every CTA): strip partial of sum_{j<n} kb_j b_j
+        const float4 kb4 = *reinterpret_cast<const float4*>(kb_s + col0);
+        float d = 0.f;
+        if (col0 + 0 < n) d = kb4.x * b4.x;
+        if (col0 + 1 < n) d = fmaf(kb4.y, b4.y, d);
+        if (col0 + 2 < n) d = fmaf(kb4.z, b4.z, d);
+        if (col0 + 3 < n) d = fmaf(kb4.w, b4.w, d);
+        d = warp_sum(d);
+        if (lane == 0) dust_s[cw] = d;
+      }
     }
-    if (warp == 31) {   // dustbin row (replicated in every CTA): a_m = mu_bin / sum_j kb_j b_j
-      float s = 0.f;
-      for (int j = lane; j <= n; j += 32) s = fmaf(kb_s[j], b_s[j], s);
-      s = warp_sum(s);
+    if (tid == 0) {
       const float bn = b_s[n];
       cbad |= (bn > ABSORB_HI) | (bn < ABSORB_LO);
-      if (lane == 0) a_s[CL_ROWS] = mu_bin / s;
     }
     T_MARK(0);
     if (__syncthreads_or(cbad)) {
@@ -275,17 +367,26 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
       for (int j = tid; j <= n; j += blockDim.x) b_s[j] = 1.f;
     }
     T_MARK(1);
+    if (tid == 0) {      // a_m = mu_bin / sum_{j<=n} kb_j b_j  (strip partials in a fixed order + the corner term)
+      float sd = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sd += dust_s[q];
+      a_s[CL_ROWS] = mu_bin / (sd + bin_col);
+    }
     // ---- every warp: a_i = mu / (sum_j K~_ij b_j + e_i kb_n b_n) for the 16 rows of its row group ----
     float a_abs = 1.f;         // scaling absorbed into u~ this iteration (book-keeping by the strip-0 warp)
     if (active) {
       const int rl = lane & 15, row = rg * 16 + rl;
       float a_mine = 0.f, ea = 0.f;
-      if (row < nrows) {
+      {
         float s = 0.f;
-        for (int q = 0; q * 128 < n; ++q) s += rowpart[q * CL_ROWS + row];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += rowpart[q * CL_ROWS + row];      // strips beyond n hold 0
         const float e = e_s[row];
-        a_mine = mu / (s + e * bin_col);
-        ea = e * a_mine;
+        if (row < nrows) {
+          a_mine = mu / (s + e * bin_col);
+          ea = e * a_mine;
+        }
       }
       const bool bad = row < nrows && (a_mine > ABSORB_HI || a_mine < ABSORB_LO);
       if (__any_sync(0xffffffffu, bad)) {
@@ -332,41 +433,42 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
       e_s[row] *= a_abs;
     }
     // ---- this CTA's partial of column j goes to the CTA that owns column j ----
-    for (int j = tid; j < n; j += blockDim.x) {
-      const float s = ((colpart[j] + colpart[CL_MAXN + j]) + colpart[2 * CL_MAXN + j]) + colpart[3 * CL_MAXN + j];
-      const int owner = j / CS, slot = j - owner * CS;
-      st_cluster_f32(mapa_u32(crecv_addr + (unsigned)(((int)c * CS + slot) * 4), (unsigned)owner), s);
+    if (tid < n) {
+      const float s = ((colpart[tid] + colpart[CL_MAXN + tid]) + colpart[2 * CL_MAXN + tid]) + colpart[3 * CL_MAXN + tid];
+      st_async_f32(push_addr, s, push_mbar);
     }
     if (warp == 31) {   // dustbin column: kb_n sum_i e_i a_i
       float s = ea_s[lane] + ea_s[lane + 32];
       s = warp_sum(s);
       if (lane == 0) {
         const int owner = n / CS, slot = n - owner * CS;
-        st_cluster_f32(mapa_u32(crecv_addr + (unsigned)(((int)c * CS + slot) * 4), (unsigned)owner), s * kb_s[n]);
+        st_async_f32(mapa_u32(crecv_addr + (unsigned)(((int)c * CS + slot) * 4), (unsigned)owner), s * kb_s[n],
+                     mapa_u32(mbarA, (unsigned)owner));
       }
     }
     T_MARK(3);
-    cluster_sync_all();
     // ---- the owner of column j adds the C partials in rank order: b_j = nu_j / (sum_g c_j^g + kb_j a_m) ----
-    {
+    if (tid < owned) {       // CS <= 1024: one column per thread
+      mbar_wait(mbarA, ph);
+      const int t = tid, j = (int)c * CS + t;
       const float am = a_s[CL_ROWS];
-      for (int t = tid; t < CS; t += blockDim.x) {
-        const int j = (int)c * CS + t;
-        if (j <= n) {
-          float s = 0.f;
-          for (int g = 0; g < C; ++g) s += crecv[g * CS + t];
-          const float bj = (j < n ? nu : nu_bin) / (s + kb_s[j] * am);
-          for (int g = 0; g < C; ++g) st_cluster_f32(mapa_u32(b_addr + (unsigned)(j * 4), (unsigned)g), bj);
-        }
-      }
+      float s = 0.f;
+      for (int g = 0; g < C; ++g) s += crecv[g * CS + t];
+      const float bj = (j < n ? nu : nu_bin) / (s + kb_s[j] * am);
+      for (int g = 0; g < C; ++g)
+        st_async_f32(mapa_u32(b_addr + (unsigned)(j * 4), (unsigned)g), bj, mapa_u32(mbarB, (unsigned)g));
     }
     T_MARK(4);
-    cluster_sync_all();
+    // all n+1 scalings of this iteration have landed in b_s.  One warp polls, the others sleep in the barrier: 32
+    // polling warps cost 34 instruction issues per warp and iteration (ncu source view, r02)
+    if (warp == 0) mbar_wait(mbarB, ph);
+    __syncthreads();
     T_MARK(5);
   }
   if (TIMING && cfg.timing && blockIdx.x == 0 && tid == 0)
     for (int i = 0; i < 6; ++i) cfg.timing[i] = (long long)tacc[i];
 #undef T_MARK
+  cluster_sync_all();          // nobody leaves while a peer may still have traffic in flight
 
   // ---- output: Z + u + v - norm with u = u~ + log a, v = v~ + log b ----
   __syncthreads();

@@ -196,6 +196,8 @@ __device__ __forceinline__ float tf32_rn(float x) {
 // 2-D fp32 row-major [rows, cols] with row stride ld (elements), box = [box_rows, 32 cols = 128 B],
 // 128B swizzle, zero fill out of bounds.  Cached per (pointer, shape) -- workspaces are stable.
 const CUtensorMap* mvm_get_tmap_2d(const float* base, long long rows, long long cols, long long ld, int box_rows);
+// 2-D fp16 [rows, cols]: box = [box_rows, 64 cols = 128 B]
+const CUtensorMap* mvm_get_tmap_2d_f16(const void* base, long long rows, long long cols, long long ld, int box_rows);
 // 3-D [slabs, rows, cols]: box = [1, box_rows, 32]
 const CUtensorMap* mvm_get_tmap_3d(const float* base, long long slabs, long long rows, long long cols,
                                    long long ld_row, long long ld_slab, int box_rows);

@@ -50,9 +50,16 @@ def main(argv=None):
     if opt.ckpt:
         sd = torch.load(opt.ckpt, map_location='cpu')
         sd = sd.get('model', sd)
-        matcher.load_state_dict({k[7:] if k.startswith('module.') else k: v for k, v in sd.items()}, strict=False)
+        # the reference loads with strict=False (helpers.py:48), which hides key mismatches: load the same way,
+        # but say what did not line up
+        missing, unexpected = matcher.load_state_dict({k[7:] if k.startswith('module.') else k: v for k, v in sd.items()},
+                                                      strict=False)
+        if missing or unexpected:
+            import logging
+            logging.warning('checkpoint keys: %d missing (%s...), %d unexpected (%s...)', len(missing),
+                            ', '.join(missing[:3]), len(unexpected), ', '.join(unexpected[:3]))
     else:
-        sd = make_state_dict(len(layers), seed=opt.seed, final_proj_gain=12.0)
+        sd = make_state_dict(len(layers), seed=opt.seed, final_proj_gain=12.0, conf_head='score')
         matcher.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
     matcher = matcher.cuda()
     pipe = MultiViewPipeline(matcher)

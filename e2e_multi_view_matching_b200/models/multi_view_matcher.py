@@ -178,8 +178,10 @@ class MultiViewMatcher(nn.Module):
         key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
             tuple((b.data_ptr(), b._version) for b in self.buffers())
         if self._packed is None or key != self._packed_key:
+            # 'fold_merge' is not a reference key: False keeps attn.merge as its own GEMM (A/B of the offline fold)
             self._packed = PackedMatcher(self.state_dict(), self.config['GNN_layers'],
-                                         conf_mlp=self.config['conf_mlp'], device=device)
+                                         conf_mlp=self.config['conf_mlp'], device=device,
+                                         fold_merge=self.config.get('fold_merge', True))
             self._packed_key = key
         return self._packed
 
@@ -216,6 +218,7 @@ class MultiViewMatcher(nn.Module):
         packed = self._pack(dev)
         result = {}
         iters = self.config['sinkhorn_iterations']
+        self._engine.last = None        # the pose stage must never continue from a previous call's state
         with torch.no_grad():
             if not self.config['multi_frame_matching']:
                 # pairwise `match` for every id0 < id1 (multi_view_matcher.py:325-329)
@@ -230,6 +233,7 @@ class MultiViewMatcher(nn.Module):
                         assert (h, w) == (h1, w1), 'pair with different image sizes: not supported'
                         outs = self._engine.run(packed, [self._view(data, id0), self._view(data, id1)],
                                                 (w, h), [(0, 1)], iters, self.match_threshold)
+                        self._engine.last['view_ids'] = [id0, id1]
                         self._publish(result, outs, {0: id0, 1: id1})
                 return result
             # multi_match (multi_view_matcher.py:217-320), eval branch
@@ -245,5 +249,6 @@ class MultiViewMatcher(nn.Module):
                 pair_ids = [(slot[i0], slot[i1]) for i1 in with_kpts for i0 in with_kpts if i0 < i1]
                 outs = self._engine.run(packed, [self._view(data, i) for i in with_kpts], (w, h),
                                         pair_ids, iters, self.match_threshold)
+                self._engine.last['view_ids'] = list(with_kpts)     # slot -> view id of the caller's data dict
                 self._publish(result, outs, {s: i for i, s in slot.items()})
         return result

@@ -57,6 +57,18 @@ def attention(qkv, batch, n_views, counts, is_cross, tc_passes=0):
     V, n_pad, _ = qkv.shape
     out = torch.zeros(V, n_pad, 256, dtype=torch.float32, device=qkv.device)
     cnt = (C.c_int * n_views)(*counts)
+    if tc_passes == 'h3':     # fp16x3: the planes the QKV GEMM epilogue writes in the matcher
+        k = qkv[:, :, 256:512].contiguous()
+        kh = k.half()
+        kl = (k - kh.float()).half().reshape(-1, 256).contiguous()
+        kh = kh.reshape(-1, 256).contiguous()
+        vt = qkv[:, :, 512:].transpose(1, 2).contiguous()      # [V, 256, n_pad]
+        vth = vt.half()
+        vtl = (vt - vth.float()).half().contiguous()
+        rc = lib.mvm_attention_h3(_lib.ptr(qkv), _lib.ptr(kh), _lib.ptr(kl), _lib.ptr(vth.contiguous()), _lib.ptr(vtl),
+                                  _lib.ptr(out), batch, n_views, n_pad, cnt, int(is_cross), _lib.stream_ptr())
+        _lib.check(rc, 'mvm_attention_h3')
+        return out
     if tc_passes:
         vt = qkv[:, :, 512:].transpose(1, 2).contiguous()      # [V, 256, n_pad]
         klo = vtlo = None

@@ -49,24 +49,40 @@ class MultiViewPipeline:
         self.pose = MultiViewPoseEngine(conf_thresh=conf_thresh)
 
     def __call__(self, data, global_ba=True):
+        """-> (matcher result, pose).  Views without keypoints are skipped by the matcher (multi_view_matcher.py:
+        155-162), so the pose stage works on view SLOTS: pose['view_ids'][s] is the id (in `data`) of slot s, the
+        extrinsics / pair tensors are indexed by slot.  pose is None when fewer than two views have keypoints
+        (nothing to estimate: the reference's "cannot compute pose" case)."""
         result = self.matcher(data)
-        T = len(data['ids'])
-        intr = [data['intr%d' % i] for i in range(T)]
-        pose = self.pose.run(self.matcher._engine.last, intr, global_ba=global_ba)
+        state = self.matcher._engine.last
+        if state is None:
+            return result, None
+        view_ids = state['view_ids']
+        intr = [data['intr%d' % i] for i in view_ids]
+        pose = self.pose.run(state, intr, global_ba=global_ba)
+        pose['view_ids'] = list(view_ids)
         return result, pose
 
     @staticmethod
     def pair_errors(data, pose, tuple_size):
-        """Pose errors of every pair from the absolute extrinsics (eval_multi_view.py:53-66)."""
+        """Pose errors of every pair id0 < id1 from the absolute extrinsics (eval_multi_view.py:53-66); pairs with
+        a view that has no keypoints (or pose None) count as failures (inf), like eval_pairs.py:258-260."""
+        n_batch = data['pose0'].shape[0]
+        if pose is None:
+            return [(np.inf, np.inf, np.inf)] * (n_batch * tuple_size * (tuple_size - 1) // 2)
         extr = pose['extrinsics'].double().cpu().numpy()
+        slot = {v: s for s, v in enumerate(pose.get('view_ids', range(tuple_size)))}
         errs = []
         for b in range(extr.shape[0]):
             for id1 in range(tuple_size):
                 for id0 in range(id1):
+                    if id0 not in slot or id1 not in slot:
+                        errs.append((np.inf, np.inf, np.inf))
+                        continue
                     p0 = data['pose%d' % id0][b].double().cpu().numpy()
                     p1 = data['pose%d' % id1][b].double().cpu().numpy()
-                    T_gt = p1 @ np.linalg.inv(p0)            # world->cam poses: x1 = p1 p0^-1 x0
-                    T_pr = extr[b, id1] @ np.linalg.inv(extr[b, id0])
+                    T_gt = np.linalg.inv(p1) @ p0            # cam->world poses, as the reference (eval_multi_view.py:59)
+                    T_pr = extr[b, slot[id1]] @ np.linalg.inv(extr[b, slot[id0]])
                     et, er = compute_pose_error_np(T_gt, T_pr[:3, :3], T_pr[:3, 3])
                     errs.append((max(et, er), et, er))
         return errs
@@ -83,7 +99,10 @@ class PairPipeline:
 
     def __call__(self, data):
         result = self.matcher(data)
+        state = self.matcher._engine.last
+        if state is None:            # a view without keypoints: "cannot compute pose" (eval_pairs.py:258-260)
+            return result, None
         intr = [data['intr0'], data['intr1']]
-        pose = self.pose.run(self.matcher._engine.last, intr, global_ba=False)
+        pose = self.pose.run(state, intr, global_ba=False)
         T = pose['T_pair'] if self.eval_mode == 'w8pt_ba' else pose['T_w8pt']
         return result, {'T_021': T[:, 0], 'success': pose['success'][:, 0], **pose}

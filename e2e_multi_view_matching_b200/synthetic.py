@@ -43,8 +43,14 @@ def _put_bn(sd, key, bn):
 
 
 def make_state_dict(n_layers, seed=0, conf_mlp=True, desc_dim=256,
-                    kenc_layers=(32, 64, 128, 256), bin_score=1.0, final_proj_gain=1.0, residual_gain=1.0):
-    """Deterministic random state dict (numpy arrays) with the reference's keys."""
+                    kenc_layers=(32, 64, 128, 256), bin_score=1.0, final_proj_gain=1.0, residual_gain=1.0,
+                    conf_head='random'):
+    """Deterministic random state dict (numpy arrays) with the reference's keys.
+    conf_head='score': instead of a random confidence head (whose output is noise, so the weighted eight-point
+    sees every wrong match at full weight and the pose AUC is ~0), a 'trained-like' one: channel 0 of the
+    layers_c path carries relu(s + 4) of the assignment log-score s of the match (multi_view_matcher.py:303-305)
+    to the output, conf ~ sigmoid(2 relu(s + 4) - 6) -- 0.88 for a certain match, 0.5 at s = -1, ~0 below -3 --
+    on top of a small random contribution of every other weight (all kernels stay exercised)."""
     rng = np.random.default_rng(seed)
     sd = {}
     sd['bin_score'] = np.array(bin_score, dtype=np.float32)
@@ -87,6 +93,24 @@ def make_state_dict(n_layers, seed=0, conf_mlp=True, desc_dim=256,
         _put_bn(sd, 'conf_mlp.layers_c.4', _bn(rng, d))
         w, b = _conv(rng, 1, d, zero_bias=True)
         _put_conv(sd, 'conf_mlp.layers.0', w, b)
+        if conf_head == 'score':
+            ident = {'weight': np.ones, 'bias': np.zeros, 'running_mean': np.zeros, 'running_var': np.ones}
+            for key in ('layers_f.1', 'layers_f.4', 'layers_c.1', 'layers_c.4'):
+                c = sd['conf_mlp.%s.weight' % key].shape[0]
+                for name, fn in ident.items():
+                    sd['conf_mlp.%s.%s' % (key, name)] = fn(c, np.float32)
+            for key in ('layers_f.0', 'layers_f.3', 'layers_c.0', 'layers_c.3', 'layers.0'):
+                sd['conf_mlp.%s.weight' % key] = sd['conf_mlp.%s.weight' % key] * np.float32(0.02)
+                sd['conf_mlp.%s.bias' % key] = sd['conf_mlp.%s.bias' % key] * np.float32(0.02)
+            sd['conf_mlp.layers_c.0.weight'][0, 0, 0] = 1.0
+            sd['conf_mlp.layers_c.0.bias'][0] = 4.0
+            sd['conf_mlp.layers_c.3.weight'][0, :, 0] = 0.0
+            sd['conf_mlp.layers_c.3.weight'][0, 0, 0] = 1.0
+            sd['conf_mlp.layers_c.3.bias'][0] = 0.0
+            sd['conf_mlp.layers_f.3.weight'][0, :, 0] = 0.0
+            sd['conf_mlp.layers_f.3.bias'][0] = 0.0
+            sd['conf_mlp.layers.0.weight'][0, 0, 0] = 2.0
+            sd['conf_mlp.layers.0.bias'][0] = -6.0
     return sd
 
 
@@ -144,7 +168,8 @@ def make_scene_tuple_inputs(seed, n_views=5, n_kpts=1024, batch=1, width=640, he
     2..6 m) seen by `n_views` cameras (view 0 identity, others rotated <= 12 deg, baseline <= 0.6 m),
     pixel keypoints with `noise_px` noise, descriptors = landmark descriptor + noise (unit norm),
     scores U(0,1), K = [[f,0,(w-1)/2],[0,f,(h-1)/2],[0,0,1]].  Returns the matcher `data` dict
-    (numpy) with intr{i} [B,3,3] and pose{i} [B,4,4] (world->cam ground truth)."""
+    (numpy) with intr{i} [B,3,3], pose{i} [B,4,4] (cam->world ground truth, the reference's convention) and
+    extr{i} (its inverse, world->cam)."""
     rng = np.random.default_rng(seed)
     K = np.array([[f, 0, (width - 1) / 2], [0, f, (height - 1) / 2], [0, 0, 1.0]])
     Kinv = np.linalg.inv(K)
@@ -189,8 +214,10 @@ def make_scene_tuple_inputs(seed, n_views=5, n_kpts=1024, batch=1, width=640, he
             de = land_desc[sel] + desc_noise * rng.standard_normal((n_kpts, desc_dim))
             de /= np.linalg.norm(de, axis=1, keepdims=True)
             sc = rng.uniform(0, 1, n_kpts)
+            # pose{i} follows the reference's data dicts: CAMERA-TO-WORLD (T_021 = inv(pose1) @ pose0,
+            # eval_multi_view.py:58-59, helpers.py:255); extr{i} is the world-to-camera matrix used above
             for key, val in (('keypoints%d' % i, px), ('scores%d' % i, sc), ('descriptors%d' % i, de.T),
-                             ('intr%d' % i, K), ('pose%d' % i, T)):
+                             ('intr%d' % i, K), ('pose%d' % i, np.linalg.inv(T)), ('extr%d' % i, T)):
                 out.setdefault(key, []).append(val.astype(np.float32))
             out.setdefault('landmark%d' % i, []).append(sel.astype(np.int64))
     for k in list(out.keys()):
@@ -199,3 +226,39 @@ def make_scene_tuple_inputs(seed, n_views=5, n_kpts=1024, batch=1, width=640, he
         out['image%d' % i] = np.zeros((batch, 1, height, width), np.float32)
     out['ids'] = list(range(n_views))
     return out
+
+
+def make_superpoint_state_dict(seed=0, logit_gain=3.0):
+    """Seeded SuperPoint weights with the reference's keys/shapes (models/models/superpoint.py:120-137): He-uniform
+    convolutions; the detector logits are scaled by `logit_gain` so that the 65-way softmax has peaks."""
+    rng = np.random.default_rng(seed)
+    shapes = [('conv1a', 1, 64, 3), ('conv1b', 64, 64, 3), ('conv2a', 64, 64, 3), ('conv2b', 64, 64, 3),
+              ('conv3a', 64, 128, 3), ('conv3b', 128, 128, 3), ('conv4a', 128, 128, 3), ('conv4b', 128, 128, 3),
+              ('convPa', 128, 256, 3), ('convPb', 256, 65, 1), ('convDa', 128, 256, 3), ('convDb', 256, 256, 1)]
+    sd = {}
+    for name, cin, cout, k in shapes:
+        bound = np.sqrt(6.0 / (cin * k * k))
+        g = logit_gain if name == 'convPb' else 1.0
+        sd[name + '.weight'] = (rng.uniform(-bound, bound, size=(cout, cin, k, k)) * g).astype(np.float32)
+        sd[name + '.bias'] = (rng.uniform(-0.1, 0.1, size=(cout,)) * g).astype(np.float32)
+    return sd
+
+
+def make_image(seed, height, width, batch=1):
+    """Seeded grayscale test image in [0,1]: smooth blobs + oriented edges + fine texture.  [batch,1,H,W] float32."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float64)
+    out = []
+    for _ in range(batch):
+        img = np.zeros((height, width))
+        for _ in range(24):
+            cx, cy = rng.uniform(0, width), rng.uniform(0, height)
+            s = rng.uniform(4, 30)
+            img += rng.uniform(-1, 1) * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+        for _ in range(8):
+            th = rng.uniform(0, np.pi)
+            img += 0.3 * np.sign(np.sin((xx * np.cos(th) + yy * np.sin(th)) / rng.uniform(6, 25) + rng.uniform(0, 6)))
+        img += 0.15 * rng.standard_normal((height, width))
+        img = (img - img.min()) / (img.max() - img.min())
+        out.append(img[None])
+    return np.stack(out, 0).astype(np.float32)

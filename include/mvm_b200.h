@@ -6,7 +6,9 @@
  * stubs).  Conventions: plain device pointers + sizes, an explicit CUDA stream (passed as
  * void* == cudaStream_t), int status return (0 ok, 1 invalid argument, 2 launch failure,
  * 3 workspace too small).  Nothing throws across the ABI, every call is stream-ordered and
- * re-entrant per stream; the only state is the caller-provided workspace.
+ * re-entrant per stream; the only state on the call path is the caller-provided workspace (process-wide
+ * defaults exist for the options struct, see mvm_matcher_options; per-device function attributes and
+ * tensor-map descriptors are cached under a mutex).
  *
  * Activation layout inside the library is point-major [view, keypoint, channel]; the
  * reference's channel-first [B, C, N] tensors are accepted at the boundary.
@@ -96,6 +98,28 @@ int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, in
                         float match_threshold, const mvm_pair_io* pairs, int n_pairs,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-call options: the forward reads its configuration from this struct only (no process-global state on the
+ * call path), so concurrent forwards on different streams / threads with different options are safe as long as
+ * each has its own workspace.  mvm_matcher_options_default fills in the process defaults (math mode 3, tensor-core
+ * score kernel, 256-wide persistent GEMM, automatic Sinkhorn kernel), which mvm_set_math_mode / the mvm_debug_*
+ * hooks below change for callers of the plain mvm_matcher_forward. */
+typedef struct mvm_matcher_options {
+  int math_mode;        /* 3 = tcgen05 3xTF32 (fp32-faithful), 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA cores */
+  int score_kernel;     /* 1 = score matrices on the tensor cores (math mode 3), 0 = fp32 CUDA cores */
+  int gemm_tile;        /* 128 | 256: tile width of the one-tile-per-CTA GEMM (when gemm_kernel == 0) */
+  int gemm_kernel;      /* 1 = persistent 3xTF32 GEMM, 0 = one tile per CTA */
+  int sinkhorn_variant; /* 0 = automatic (see mvm_log_optimal_transport_ex) */
+  int attention_split;  /* math mode 3: operand planes of attention, 0 = tf32 hi/lo (3 x kind::tf32), 1 = fp16 hi/lo
+                         * (3 x kind::f16: same 22-bit operands, half the tensor-pipe time) */
+} mvm_matcher_options;
+void mvm_matcher_options_default(mvm_matcher_options* opt);
+int mvm_matcher_forward_ex(const mvm_matcher_weights* w, int batch, int n_views, int n_pad,
+                           const int* counts, const float* kpts, const float* kscores,
+                           const float* desc, float img_w, float img_h, int sinkhorn_iters,
+                           float match_threshold, const mvm_pair_io* pairs, int n_pairs,
+                           void* workspace, size_t workspace_bytes, const mvm_matcher_options* opt /* NULL = defaults */,
+                           void* stream);
+
 /* ---- individual stages (exported for stage-parity tests and for callers that only need
  * one stage; same semantics as the fused forward) -------------------------------------- */
 
@@ -137,6 +161,13 @@ int mvm_attention(const float* qkv, float* out, int batch, int n_views, int n_pa
 int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, int n_views, int n_pad,
                      const int* counts, int is_cross, int n_pass, const float* klo, const float* vtlo,
                      void* stream);
+
+/* fp32-faithful attention with HALF-PRECISION operand planes (fp16x3: hi = fp16(x), lo = fp16(x - hi); three
+ * kind::f16 MMAs per product, half the tensor-pipe time of the tf32 variant at the same 22-bit operand precision).
+ * kh, kl [n_views_total * n_pad, 256] and vth, vtl [n_views_total * 256, n_pad] are fp16 buffers (the QKV GEMM
+ * epilogue writes them inside mvm_matcher_forward); the q third of qkv is read as fp32. */
+int mvm_attention_h3(const float* qkv, const void* kh, const void* kl, const void* vth, const void* vtl, float* out,
+                     int batch, int n_views, int n_pad, const int* counts, int is_cross, void* stream);
 
 /* log_optimal_transport (superglue.py:143-172).  scores: [batch, m+1, n+1] buffers whose
  * inner [m,n] block holds the raw scores on entry; on exit the full coupling matrix
@@ -248,12 +279,60 @@ int mvm_multi_view_ba_ex(const int* pair_a, const int* pair_b, int n_views, int 
                          int* iterations_out, double* cost_out, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* The general form of the reference's BaProblem for pairwise tracks (ba_problem.h:60-151): one weight per
+ * OBSERVATION.  conf [B,P,n_pad] weighs the view-a observation of a point, conf_b the view-b observation
+ * (NULL = the same weight, i.e. mvm_multi_view_ba_ex).  With weights_prenormalized != 0 and points_init given this
+ * is exactly the problem `ba_in.csv` states -- the reference's own gtest scenes (test_ba_problem.cpp:40-67, weight =
+ * depth in each camera) run through it (tests/test_mv_gpu.py). */
+int mvm_multi_view_ba_obs(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch,
+                          int n_pad, const float* xn_a, const float* xn_b, const float* conf, const float* conf_b,
+                          const int* n_valid, const double* extr_init, const double* points_init,
+                          int weights_prenormalized, float* extr_out, double* extr_out_f64, int max_iterations,
+                          int* iterations_out, double* cost_out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
 /* Two-view DLT of every match of every (tuple, pair) with the given world->cam extrinsics
  * (cv2.triangulatePoints in write_bundle_adjust_problem, bundle_adjust_io.py:219-225).
  * points_out [B,P,n_pad,3] doubles (zero beyond n_valid). */
 int mvm_triangulate_pairs(const int* pair_a, const int* pair_b, int n_views, int n_pairs, int batch, int n_pad,
                           const float* xn_a, const float* xn_b, const int* n_valid, const double* extr,
                           double* points_out, void* stream);
+
+/* ---- SuperPoint front-end (models/models/superpoint.py:147-229) --------------------------- */
+
+/* Device pointers.  3x3 convolutions conv1a, conv1b, conv2a, conv2b, conv3a, conv3b, conv4a, conv4b, convPa, convDa in
+ * that order, each repacked to [tap = 3*ky + kx][Cin][Cout]; the 1x1 heads convPb [65,256] and convDb [256,256] row-major
+ * [out, in] as in the state dict. */
+typedef struct mvm_superpoint_weights {
+  const float* w[10];
+  const float* b[10];
+  const float* w_pb; const float* b_pb;
+  const float* w_db; const float* b_db;
+} mvm_superpoint_weights;
+
+size_t mvm_superpoint_workspace_bytes(int batch, int height, int width);
+
+/* Dense part of SuperPoint.forward (:150-170, :213-216): image [batch, height, width] fp32 (grayscale in [0,1]; height,
+ * width multiples of 8) -> scores_nms [batch, height, width] (softmax keypoint scores after simple_nms, 0 where
+ * suppressed) and dense_desc [batch, height/8, width/8, 256] (L2-normalised, channels last). */
+int mvm_superpoint_dense(const mvm_superpoint_weights* w, const float* image, int batch, int height, int width,
+                         int nms_radius, float* scores_nms, float* dense_desc, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* sample_descriptors (:86-100) for one image: keypoints [n,2] (x, y) pixels, dense_desc [h, w, 256] of that image ->
+ * descriptors [256, n] (bilinear, align_corners=True, L2-normalised). */
+int mvm_superpoint_sample(const float* dense_desc, const float* keypoints, int n, int h, int w, float* descriptors,
+                          void* stream);
+
+/* ---- training-side consumers (first slice of SURVEY.md §8 f-2) ----------------------------------------------- */
+
+/* compute_match_loss (helpers.py:228-241): weighted NLL of the ground-truth assignment on the log-couplings.
+ * log_p [bs, ft, ft] (ft = keypoints + 1), gt_indices [bs, 2, ft] int64 (-1 = dustbin = last index), gt_weights
+ * [bs, 2, ft]; partial_ws: bs doubles; loss: one float.  Backward: grad_log_p [bs, ft, ft] = d loss / d log_p * grad_loss. */
+int mvm_match_loss_forward(const float* log_p, const int64_t* gt_indices, const float* gt_weights, int bs, int ft,
+                           double* partial_ws, float* loss, void* stream);
+int mvm_match_loss_backward(const int64_t* gt_indices, const float* gt_weights, const float* grad_loss, int bs, int ft,
+                            float* grad_log_p, void* stream);
 
 /* ---- instrumentation ----------------------------------------------------------------- */
 /* Kernels launched by the library since load (bench.py's gpu_launches). */
@@ -264,6 +343,16 @@ unsigned long long mvm_launch_count(void);
  * 6 keypoint encoder, 7 w8pt, 8 two-view BA, 9 multi-view BA, 10 misc). */
 void mvm_profile_enable(int on);
 int mvm_profile_collect(double* ms_per_tag, int* n_per_tag, int n_tags);
+
+/* ---- debug / A-B hooks (process-wide defaults; not used on the mvm_matcher_forward_ex call path) ------------ */
+void mvm_debug_set_score_kernel(int tensor_cores);      /* default of mvm_matcher_options.score_kernel */
+void mvm_debug_set_gemm_tile(int bn);                   /* default of .gemm_tile (128 | 256) */
+void mvm_debug_set_gemm_kernel(int persistent);         /* default of .gemm_kernel */
+void mvm_debug_set_attention_split(int fp16);           /* default of .attention_split */
+/* clock64 phase traces of CTA 0 (device buffers of 8 / 6 / 8 long long; NULL switches the trace off) */
+void mvm_debug_set_attention_timing(long long* buf);
+void mvm_debug_set_sinkhorn_timing(long long* buf);
+void mvm_debug_set_mvba_timing(long long* buf);
 
 /* Library/build info: returns "mvm_b200 <version> sm_100a". */
 const char* mvm_version(void);

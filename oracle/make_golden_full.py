@@ -48,7 +48,7 @@ def input_digest(sd, data):
     for k in sorted(sd):
         h.update(np.ascontiguousarray(sd[k]).tobytes())
     for k in sorted(data):
-        if isinstance(data[k], np.ndarray) and not k.startswith('image'):
+        if isinstance(data[k], np.ndarray) and k.startswith(('keypoints', 'scores', 'descriptors')):
             h.update(np.ascontiguousarray(data[k]).tobytes())
     return h.hexdigest()
 

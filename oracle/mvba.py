@@ -200,6 +200,162 @@ def solve(pb, max_iterations=50, function_tolerance=1e-6, gradient_tolerance=1e-
 
 
 # ---------------------------------------------------------------------------------------------
+# the same solver with the point blocks eliminated by a Schur complement (what DENSE_SCHUR does,
+# ba_problem.cpp:150-152): identical iterates to `solve` up to rounding, O(P) instead of O(P^3)
+# ---------------------------------------------------------------------------------------------
+def _blocks(pb, cams, points, want_J=True):
+    """Vectorised residuals and per-observation Jacobian blocks: r [O,2], Jc [O,2,6] (zero for the
+    fixed camera), Jp [O,2,3]."""
+    fx, fy, cx, cy = pb.intr
+    oc, ok, w = pb.obs_cam, pb.obs_pt, pb.obs_w
+    C = cams.shape[0]
+    Rs = np.stack([np.eye(3) if c == pb.fixed else angle_axis_to_R(cams[c, :3]) for c in range(C)])
+    ts = np.stack([np.zeros(3) if c == pb.fixed else cams[c, 3:] for c in range(C)])
+    p = points[ok]
+    q = np.einsum('oij,oj->oi', Rs[oc], p) + ts[oc]
+    r = np.stack([w[:, 0] * (fx * q[:, 0] / q[:, 2] + cx - pb.obs_xy[:, 0]),
+                  w[:, 1] * (fy * q[:, 1] / q[:, 2] + cy - pb.obs_xy[:, 1])], 1)
+    if not want_J:
+        return r, None, None
+    O = len(oc)
+    Jpi = np.zeros((O, 2, 3))
+    Jpi[:, 0, 0] = w[:, 0] * fx / q[:, 2]
+    Jpi[:, 0, 2] = -w[:, 0] * fx * q[:, 0] / q[:, 2] ** 2
+    Jpi[:, 1, 1] = w[:, 1] * fy / q[:, 2]
+    Jpi[:, 1, 2] = -w[:, 1] * fy * q[:, 1] / q[:, 2] ** 2
+    Jp = Jpi @ Rs[oc]
+    Jc = np.zeros((O, 2, 6))
+    free_obs = oc != pb.fixed
+    Jc[free_obs, :, 3:] = Jpi[free_obs]
+    # d(R(w) p)/dw = -R [p]x (w w^T + (R^T - I)[w]x) / |w|^2   (-[p]x at w = 0), per camera
+    px = np.zeros((O, 3, 3))
+    px[:, 0, 1], px[:, 0, 2] = -p[:, 2], p[:, 1]
+    px[:, 1, 0], px[:, 1, 2] = p[:, 2], -p[:, 0]
+    px[:, 2, 0], px[:, 2, 1] = -p[:, 1], p[:, 0]
+    for c in range(C):
+        if c == pb.fixed:
+            continue
+        sel = oc == c
+        if not sel.any():
+            continue
+        wv = cams[c, :3]
+        th2 = float(wv @ wv)
+        if th2 < 1e-16:
+            dR = -px[sel]
+        else:
+            R = Rs[c]
+            M_ = (np.outer(wv, wv) + (R.T - np.eye(3)) @ hat(wv)) / th2
+            dR = -(R @ px[sel]) @ M_
+        Jc[sel, :, :3] = Jpi[sel] @ dR
+    return r, Jc, Jp
+
+
+def solve_schur(pb, max_iterations=50, function_tolerance=1e-6, gradient_tolerance=1e-10,
+                parameter_tolerance=1e-8):
+    """`solve` with (H + D) d = -g solved through the reduced camera system.  Same returns."""
+    cams, points = pb.cams.copy(), pb.points.copy()
+    C, P = cams.shape[0], points.shape[0]
+    free = [c for c in range(C) if c != pb.fixed]
+    slot = np.full(C, -1)
+    slot[free] = np.arange(len(free))
+    nf = len(free)
+    oc, ok = pb.obs_cam, pb.obs_pt
+    os_ = slot[oc]
+    fo = os_ >= 0
+
+    def evaluate(cams, points, want_J=True):
+        r, Jc, Jp = _blocks(pb, cams, points, want_J)
+        return r, Jc, Jp
+
+    r, Jc, Jp = evaluate(cams, points)
+    cost = 0.5 * (r * r).sum()
+    # jacobi_scaling, fixed after iteration 0
+    nc = np.zeros((nf, 6))
+    np.add.at(nc, os_[fo], (Jc[fo] ** 2).sum(1))
+    npt = np.zeros((P, 3))
+    np.add.at(npt, ok, (Jp ** 2).sum(1))
+    sc, sp = 1.0 / (1.0 + np.sqrt(nc)), 1.0 / (1.0 + np.sqrt(npt))
+    radius, decrease = 1e4, 2.0
+    info = {'iterations': 0, 'initial_cost': cost, 'termination': 'max_iterations'}
+
+    def gradient_max(r, Jc, Jp):
+        gc = np.zeros((nf, 6))
+        np.add.at(gc, os_[fo], np.einsum('oij,oi->oj', Jc[fo], r[fo]))
+        gp = np.zeros((P, 3))
+        np.add.at(gp, ok, np.einsum('oij,oi->oj', Jp, r))
+        return max(np.abs(gc).max() if nf else 0.0, np.abs(gp).max())
+
+    if gradient_max(r, Jc, Jp) <= gradient_tolerance:
+        info['termination'] = 'gradient'
+        info['final_cost'] = cost
+        return cams, points, info
+    for it in range(max_iterations):
+        info['iterations'] = it + 1
+        Jcs = Jc * sc[np.maximum(os_, 0)][:, None, :] * fo[:, None, None]
+        Jps = Jp * sp[ok][:, None, :]
+        gc = np.zeros((nf, 6))
+        np.add.at(gc, os_[fo], np.einsum('oij,oi->oj', Jcs[fo], r[fo]))
+        gp = np.zeros((P, 3))
+        np.add.at(gp, ok, np.einsum('oij,oi->oj', Jps, r))
+        B = np.zeros((nf, 6, 6))
+        np.add.at(B, os_[fo], np.einsum('oij,oik->ojk', Jcs[fo], Jcs[fo]))
+        Cb = np.zeros((P, 3, 3))
+        np.add.at(Cb, ok, np.einsum('oij,oik->ojk', Jps, Jps))
+        E = np.zeros((nf, P, 6, 3))
+        np.add.at(E, (os_[fo], ok[fo]), np.einsum('oij,oik->ojk', Jcs[fo], Jps[fo]))
+        i6, i3 = np.arange(6), np.arange(3)
+        B[:, i6, i6] += np.clip(B[:, i6, i6], 1e-6, 1e32) / radius
+        Cb[:, i3, i3] += np.clip(Cb[:, i3, i3], 1e-6, 1e32) / radius
+        try:
+            Ci = np.linalg.inv(Cb)
+            ECi = np.einsum('apij,pjk->apik', E, Ci)                       # [nf,P,6,3]
+            S = np.zeros((nf * 6, nf * 6))
+            for a in range(nf):
+                S[6 * a:6 * a + 6, 6 * a:6 * a + 6] = B[a]
+            S -= np.einsum('apij,bpkj->aibk', ECi, E).reshape(nf * 6, nf * 6)
+            rhs = -gc.reshape(-1) + np.einsum('apij,pj->ai', ECi, gp).reshape(-1)
+            dc = np.linalg.solve(S, rhs).reshape(nf, 6)
+            dp = np.einsum('pij,pj->pi', Ci, -gp - np.einsum('apij,ai->pj', E, dc))
+        except np.linalg.LinAlgError:
+            radius /= decrease
+            decrease *= 2
+            continue
+        model = r + np.einsum('oij,oj->oi', Jcs, dc[np.maximum(os_, 0)]) + np.einsum('oij,oj->oi', Jps, dp[ok])
+        model_change = cost - 0.5 * (model * model).sum()
+        d_c, d_p = dc * sc, dp * sp
+        cams_n, points_n = cams.copy(), points.copy()
+        cams_n[free] += d_c
+        points_n += d_p
+        r_n, _, _ = evaluate(cams_n, points_n, want_J=False)
+        cost_n = 0.5 * (r_n * r_n).sum()
+        step_norm = np.sqrt((d_c ** 2).sum() + (d_p ** 2).sum())
+        x_norm = np.sqrt((cams[free] ** 2).sum() + (points ** 2).sum())
+        if step_norm <= parameter_tolerance * (x_norm + parameter_tolerance):
+            info['termination'] = 'parameter'
+            break
+        rho = (cost - cost_n) / model_change if model_change > 0 else -1.0
+        if rho > 1e-3:
+            cost_change = cost - cost_n
+            cams, points = cams_n, points_n
+            radius = min(radius / max(1.0 / 3.0, 1.0 - (2 * rho - 1) ** 3), 1e16)
+            decrease = 2.0
+            converged = abs(cost_change) <= function_tolerance * cost
+            cost = cost_n
+            r, Jc, Jp = evaluate(cams, points)
+            if converged:
+                info['termination'] = 'function'
+                break
+            if gradient_max(r, Jc, Jp) <= gradient_tolerance:
+                info['termination'] = 'gradient'
+                break
+        else:
+            radius /= decrease
+            decrease *= 2
+    info['final_cost'] = cost
+    return cams, points, info
+
+
+# ---------------------------------------------------------------------------------------------
 # reference known-answer scenes (test_ba_problem.cpp:30-184)
 # ---------------------------------------------------------------------------------------------
 class _GlibcRand:
@@ -269,13 +425,12 @@ def spanning_tree_extrinsics(n_images, rel_pose, weight):
 
 def triangulate_dlt(P0, P1, x0, x1):
     """cv2.triangulatePoints (bundle_adjust_io.py:222): DLT, smallest right-singular vector."""
-    out = np.zeros((x0.shape[0], 3))
-    for k in range(x0.shape[0]):
-        A = np.stack([x0[k, 0] * P0[2] - P0[0], x0[k, 1] * P0[2] - P0[1],
-                      x1[k, 0] * P1[2] - P1[0], x1[k, 1] * P1[2] - P1[1]])
-        v = np.linalg.svd(A)[2][-1]
-        out[k] = v[:3] / v[3]
-    return out
+    if x0.shape[0] == 0:
+        return np.zeros((0, 3))
+    A = np.stack([x0[:, 0:1] * P0[2] - P0[0], x0[:, 1:2] * P0[2] - P0[1],
+                  x1[:, 0:1] * P1[2] - P1[0], x1[:, 1:2] * P1[2] - P1[1]], 1)       # [n,4,4]
+    v = np.linalg.svd(A)[2][:, -1]
+    return v[:, :3] / v[:, 3:4]
 
 
 def build_problem(n_images, pair_matches, extrinsics):
@@ -403,6 +558,6 @@ def multi_view_pipeline(scene, conf_thresh=0.0, n_it2=10, max_iterations=50, use
         keep = {k: v for k, v in rel.items() if int(info_all[k]['inliers'].sum()) >= min_inliers or k in tree}
         extr0 = ba_initialize(T, extr_tree, keep)
     pb = build_problem(T, pm, extr0)
-    cams, pts, info = solve(pb, max_iterations=max_iterations)
+    cams, pts, info = solve_schur(pb, max_iterations=max_iterations)
     return {'rel': rel, 'extr_tree': extr_tree, 'extr_init': extr0, 'extr': cams_to_extrinsics(cams), 'info': info, 'pairs': info_all,
             'weight': weight}

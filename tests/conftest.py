@@ -23,4 +23,6 @@ def _default_math_mode(request):
     if request.node.get_closest_marker('gpu') is not None:
         import e2e_multi_view_matching_b200 as pkg
         pkg.set_math_mode(3)
+        from e2e_multi_view_matching_b200 import _lib
+        _lib.lib().mvm_debug_set_attention_split(1)
     yield

@@ -1,0 +1,53 @@
+"""fp16x3 attention (attention_h3.cu): hi = fp16(x), lo = fp16(x - hi) operand planes, three kind::f16 MMAs per product.
+Stage parity against the fp32 CUDA-core attention, and the whole matcher with this variant against the reference
+goldens at the same tolerances as the tf32x3 default."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import GOLDEN, MATCHER_CASES, load_case, case_inputs, compare_matcher_outputs, score_tol_for
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('cfg', [(1, 2, 128, [128, 128]), (2, 3, 192, [100, 192, 77]), (1, 5, 256, [256] * 5)])
+@pytest.mark.parametrize('scale', [1.0, 6.0])
+def test_attention_h3_vs_fp32(cfg, scale):
+    from e2e_multi_view_matching_b200 import ops
+    B, T, n_pad, counts = cfg
+    g = torch.Generator().manual_seed(n_pad + T)
+    qkv = (torch.randn(B * T, n_pad, 768, generator=g) * scale).cuda()
+    for is_cross in (0, 1):
+        ref = ops.attention(qkv, B, T, counts, is_cross)                     # fp32 CUDA cores
+        out = ops.attention(qkv, B, T, counts, is_cross, tc_passes='h3')
+        tc3 = ops.attention(qkv, B, T, counts, is_cross, tc_passes=3)        # tf32x3
+        for b in range(B):
+            for t in range(T):
+                v = b * T + t
+                e_h = (out[v, :counts[t]] - ref[v, :counts[t]]).abs().max().item()
+                e_t = (tc3[v, :counts[t]] - ref[v, :counts[t]]).abs().max().item()
+                assert e_h < max(3e-5 * scale, 2.0 * e_t + 1e-6), (cfg, scale, is_cross, e_h, e_t)
+
+
+@pytest.mark.parametrize('name', MATCHER_CASES)
+def test_matcher_h3_vs_reference_golden(name):
+    import e2e_multi_view_matching_b200 as pkg
+    from e2e_multi_view_matching_b200 import _lib
+    from tests.test_matcher_gpu import run_ours
+    lib = _lib.lib()
+    meta, ref = load_case(name)
+    sd, data = case_inputs(meta)
+    pkg.set_math_mode(3)
+    try:
+        lib.mvm_debug_set_attention_split(1)
+        got = run_ours(meta, sd, data)
+        lib.mvm_debug_set_attention_split(0)
+        base = run_ours(meta, sd, data)
+    finally:
+        lib.mvm_debug_set_attention_split(1)
+    rep = compare_matcher_outputs(ref, got, tau=2e-3, score_tol=score_tol_for(name), min_stable=0.0 if name == 'pair_flat' else 0.9)
+    rep0 = compare_matcher_outputs(ref, base, tau=2e-3, score_tol=score_tol_for(name))
+    print(name, 'fp16x3', rep, 'tf32x3 max_score_err', rep0['max_score_err'])

@@ -3,7 +3,8 @@ import sys, ctypes, torch
 sys.path.insert(0, '.')
 from e2e_multi_view_matching_b200 import ops, _lib
 lib = _lib.lib()
-mode = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+mode = sys.argv[1] if len(sys.argv) > 1 else 'h3'        # 'h3' (fp16x3), 3 (tf32x3) or 1 (single-pass tf32)
+mode = mode if mode == 'h3' else int(mode)
 buf = torch.zeros(64 * 16 + 2048 * 8, dtype=torch.int64, device='cuda')
 lib.mvm_debug_set_attention_timing.argtypes = [ctypes.c_void_p]
 g = torch.Generator().manual_seed(0)
