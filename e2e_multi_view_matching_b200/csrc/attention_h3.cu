@@ -16,7 +16,11 @@
 //   warps 3-6 / 7-10   softmax groups 0 / 1 (even / odd key tiles): thread r owns query row r; S row -> registers,
 //               exp2, P split into packed half2 hi / lo planes written OVER S in tensor memory (32 + 32 columns),
 //               per-group output accumulator resident in TMEM with lazy rescaling, merged once at the end.
-// TMEM columns: S0/P0 [0,64)  S1/P1 [64,128)  O0 [128,192)  O1 [192,256)  Q_hi [256,288)  Q_lo [288,320).
+// S and P do NOT share tensor-memory columns (the half-precision P planes are small): the S buffer of a group is free
+// again as soon as its softmax threads have read the row into registers (barrier s_free), so Q K^T of the group's next
+// tile is issued under the exponentials of the current one instead of after its P V product.
+// TMEM columns: S0 [0,64)  S1 [64,128)  O0 [128,192)  O1 [192,256)  Q_hi [256,288)  Q_lo [288,320)
+//               P0 hi|lo [320,384)  P1 hi|lo [384,448).
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -31,14 +35,16 @@ constexpr int K_BYTES = BKV * HD * 2;         //  8 KB  [64 keys x 64 d] fp16, 1
 constexpr int V_BYTES = HD * BKV * 2;         //  8 KB  [64 d x 64 keys] fp16
 
 struct HCfg {
-  static constexpr int ST = 3;                          // K and V^T ring depth
+  // K and V^T ring depth.  The clock trace showed the Q K^T issuer waiting ~770 clk per tile for K with a 3-deep ring:
+  // a TMA load lands ~2 us after it is requested under this load, and the tile period settled at latency / depth.
+  static constexpr int ST = 6;
   static constexpr int OFF_K = 0;                       // per stage: hi | lo
   static constexpr int OFF_V = OFF_K + ST * K_BYTES * 2;
   static constexpr int OFF_BAR = OFF_V + ST * V_BYTES * 2;
   static constexpr int OFF_ML = OFF_BAR + 512;          // (m, l) of both softmax groups: float [2][2][128]
   static constexpr int SMEM_BYTES = OFF_ML + 2048 + 1024;
   static constexpr int NTHREADS = 352;
-  static constexpr int TMEM_COLS = 512;                 // 320 used (allocation sizes are powers of two)
+  static constexpr int TMEM_COLS = 512;                 // 448 used (allocation sizes are powers of two)
 };
 
 struct AttnH3Args {
@@ -97,18 +103,18 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::OFF_BAR);
-  uint64_t* q_ready = bars + 0;    // Q rows stored to tensor memory (128 arrivals)
-  uint64_t* k_full = bars + 1;     // [ST]
-  uint64_t* k_empty = bars + 4;    // [ST]
-  uint64_t* k_split = bars + 7;    // [ST]
-  uint64_t* v_full = bars + 10;    // [ST]
-  uint64_t* v_empty = bars + 13;   // [ST]
-  uint64_t* v_split = bars + 16;   // [ST]
-  uint64_t* s_full = bars + 19;    // [2]  S(j) landed in TMEM
-  uint64_t* p_ready = bars + 21;   // [2]  keys 0-31 of P(j) stored over S(j) (128 arrivals)
-  uint64_t* p_ready_b = bars + 25; // [2]  keys 32-63 of P(j) stored
-  uint64_t* o_full = bars + 23;    // [2]  P.V(j) landed in the TMEM accumulator (alternating, see the softmax warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* q_ready = bars + 0;             // Q rows stored to tensor memory (128 arrivals)
+  uint64_t* k_full = bars + 1;              // [ST]
+  uint64_t* k_empty = k_full + ST;          // [ST]
+  uint64_t* v_full = k_empty + ST;          // [ST]
+  uint64_t* v_empty = v_full + ST;          // [ST]
+  uint64_t* s_full = v_empty + ST;          // [2]  S(j) landed in TMEM
+  uint64_t* p_ready = s_full + 2;           // [2]  keys 0-31 of P(j) stored (128 arrivals)
+  uint64_t* o_full = p_ready + 2;           // [2]  P.V(j) landed in the TMEM accumulator of the tile's group
+  uint64_t* p_ready_b = o_full + 2;         // [2]  keys 32-63 of P(j) stored
+  uint64_t* s_free = p_ready_b + 2;         // [2]  S(j) read into registers by the softmax group (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  static_assert((1 + 4 * ST + 10 + 1) * 8 <= 512, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool trace_cta = g.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -171,11 +177,12 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   if (threadIdx.x == 0) {
     tc::mbar_init(q_ready, 128);
     for (int i = 0; i < ST; ++i) {
-      tc::mbar_init(k_full + i, 1); tc::mbar_init(k_empty + i, 1); tc::mbar_init(k_split + i, 128);
-      tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1); tc::mbar_init(v_split + i, 128);
+      tc::mbar_init(k_full + i, 1); tc::mbar_init(k_empty + i, 1);
+      tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1);
     }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(s_full + i, 1); tc::mbar_init(p_ready + i, 128); tc::mbar_init(p_ready_b + i, 128); }
     tc::mbar_init(o_full, 1); tc::mbar_init(o_full + 1, 1);
+    tc::mbar_init(s_free, 128); tc::mbar_init(s_free + 1, 128);
     tc::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -189,7 +196,7 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   if (threadIdx.x == 0) cmark(2);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 128, tmem_O1 = tmem_base + 192;
-  const uint32_t tmem_Q = tmem_base + 256, tmem_Qlo = tmem_base + 288;
+  const uint32_t tmem_Q = tmem_base + 256, tmem_Qlo = tmem_base + 288, tmem_P0 = tmem_base + 320;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -240,11 +247,11 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       const int s = j % ST, sb = j & 1;
       mark(j, 8);
       tc::mbar_wait(k_full + s, (j / ST) & 1);
-      // P.V(j-2) done reading P / P_lo of this buffer.  P.V(j) cannot have completed (it needs this S), so the
-      // barrier is at most one phase ahead of the phase awaited: the parity wait is sound.
-      if (j >= 2) tc::mbar_wait(o_full + sb, ((j - 2) >> 1) & 1);
+      mark(j, 9);                      // K landed; what follows until slot 6 is the S-buffer wait + the issue
+      // S(j-2) of this buffer has been read into registers by its softmax group.  S(j) cannot have been read yet
+      // (it is not written), so the barrier is at most one phase ahead of the phase awaited: the parity wait is sound.
+      if (j >= 2) tc::mbar_wait(s_free + sb, ((j - 2) >> 1) & 1);
       tc::tc_fence_after();
-      mark(j, 9);
       const uint32_t k_hi = tc::smem_u32(sK(s)), k_lo = k_hi + K_BYTES;
       const uint32_t d = tmem_S0 + sb * 64;
       if (tc::elect_one()) {
@@ -274,7 +281,7 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       tc::tc_fence_after();
       mark(j, 10);
       const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
-      const uint32_t p_hi = tmem_S0 + sb * 64, p_lo = p_hi + 32;          // P planes over S: hi [0,32) lo [32,64)
+      const uint32_t p_hi = tmem_P0 + sb * 64, p_lo = p_hi + 32;          // P planes of the group: hi [0,32) lo [32,64)
       const uint32_t o_acc = sb ? tmem_O1 : tmem_O;
       auto issue_PV = [&](int kk0) {                                       // two K = 16 steps = 32 keys
 #pragma unroll
@@ -325,7 +332,7 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     // TENSOR MEMORY.  The reference m_ref of a row is only raised (and O_g, l rescaled) when the row maximum
     // outgrows it by more than 2^8: softmax is invariant to the reference, P stays <= 2^8, and the common tile
     // costs no TMEM read of O at all.  Log2 units throughout (scores * log2(e) / sqrt(d)).
-    const uint32_t tm_S = tmem_S0 + grp * 64, tm_O = grp ? tmem_O1 : tmem_O;
+    const uint32_t tm_S = tmem_S0 + grp * 64, tm_P = tmem_P0 + grp * 64, tm_O = grp ? tmem_O1 : tmem_O;
     uint64_t* my_o_full = o_full + grp;
     float m_ref = -INFINITY, l_run = 0.f;
     const float scale_l2e = 0.125f * 1.4426950408889634f;
@@ -345,6 +352,8 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         tc::tmem_ld32(tm_S + lane_addr, s);
         tc::tmem_ld32(tm_S + lane_addr + 32, s + 32);
         tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(s_free + grp);          // the S buffer may be overwritten by Q K^T of tile j + 2
         if (q == 3) mark(j, 2);
         if (nvalid < BKV) {
 #pragma unroll
@@ -376,6 +385,12 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           }
         }
         if (q == 3) mark(j, 3);
+        if (mine > 0 && !__any_sync(0xffffffffu, grow)) {
+          // P(j) overwrites the planes P.V(j-2) read: that product must have completed (it has, long ago, in the
+          // steady state -- it was issued one softmax period back)
+          tc::mbar_wait(my_o_full, (mine - 1) & 1);
+          tc::tc_fence_after();
+        }
         const float nm = -m_ref;
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
         // P(j) overwrites S(j) in tensor memory (row r = lane r, keys along columns): A operand of P.V,
@@ -391,8 +406,8 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
             rs4[2 + (i & 1)] += p1;
             split_pack(p0, p1, ph[i], pl[i]);
           }
-          tmem_st16(tm_S + lane_addr + c * 16, ph);            // P_hi over S columns [0,32)
-          tmem_st16(tm_S + lane_addr + 32 + c * 16, pl);       // P_lo over S columns [32,64)
+          tmem_st16(tm_P + lane_addr + c * 16, ph);            // P_hi columns [0,32)
+          tmem_st16(tm_P + lane_addr + 32 + c * 16, pl);       // P_lo columns [32,64)
           tc::tmem_st_wait();
           tc::tc_fence_before();
           tc::mbar_arrive((c == 0 ? p_ready : p_ready_b) + grp);

@@ -207,6 +207,15 @@ __global__ void __launch_bounds__(NT) w8pt_kernel(W8ptArgs a) {
     int mi = 0;
     for (int i = 1; i < 9; ++i)
       if (s_M[i * 9 + i] < s_M[mi * 9 + mi]) mi = i;
+    if (N == 8) {
+      // The reference takes V[..., -1] of the REDUCED svd(X) (:72-73).  With exactly 8 matches X is 8 x 9, the
+      // reduced V has only 8 columns and its last one belongs to the smallest of the 8 NON-ZERO singular values --
+      // not to the null vector.  Reproduce that: second-smallest eigenvalue of the 9 x 9 normal matrix.
+      int m2 = mi == 0 ? 1 : 0;
+      for (int i = 0; i < 9; ++i)
+        if (i != mi && s_M[i * 9 + i] < s_M[m2 * 9 + m2]) m2 = i;
+      mi = m2;
+    }
     double F[9];
     for (int i = 0; i < 9; ++i) F[i] = s_V[i * 9 + mi];
     // rank-2 projection (:76-79): F - (F v3) v3^T with v3 the smallest right-singular vector

@@ -41,24 +41,22 @@ def _cuda(a, dtype=None):
 def estimate_relative_pose_w8pt_ba(intr0, intr1, mkpts0, mkpts1, conf):
     """numpy in, numpy out, batch of one (bundle_adjust_io.py:12-23): weighted eight-point with the inlier
     test, matches behind a camera dropped, ten LM iterations of two-view bundle adjustment."""
-    pred_T021, info = estimate_relative_pose_w8pt(_cuda(mkpts0).unsqueeze(0), _cuda(mkpts1).unsqueeze(0),
-                                                  _cuda(intr0).unsqueeze(0), _cuda(intr1).unsqueeze(0),
-                                                  _cuda(conf).unsqueeze(0), determine_inliers=True)
-    if pred_T021 is None:
+    args = [_cuda(a).unsqueeze(0) for a in (mkpts0, mkpts1, intr0, intr1, conf)]
+    T, info = estimate_relative_pose_w8pt(*args, determine_inliers=True)
+    if T is None:                                   # fewer than 8 matches
         return False, None, None, None
-    confidence = info["confidence"]
-    confidence[torch.logical_not(info["pos_depth_mask"])] = 0.
-    pred_T021_refine, valid_refine = run_bundle_adjust_2_view(info["kpts0_norm"], info["kpts1_norm"], confidence,
-                                                              pred_T021, n_iterations=10)
-    pred_T021[valid_refine] = pred_T021_refine
-    return True, pred_T021[0, :3, :3].cpu().numpy(), pred_T021[0, :3, 3].cpu().numpy(), \
-        info["inliers"].squeeze(0).cpu().numpy()
+    weights = info["confidence"].masked_fill(~info["pos_depth_mask"].unsqueeze(-1), 0.)
+    refined, ok = run_bundle_adjust_2_view(info["kpts0_norm"], info["kpts1_norm"], weights, T, n_iterations=10)
+    if bool(ok[0]):
+        T = refined
+    T = T[0].cpu().numpy()
+    return True, T[:3, :3], T[:3, 3], info["inliers"][0].cpu().numpy()
 
 
 def normalize_confidences(obs_xyc):
-    conf = obs_xyc[:, 2:]
-    sum_conf = conf.sum(axis=0, keepdims=True) + 1e-3
-    obs_xyc[:, 2:] = conf / (0.5 * sum_conf)     # two observations per match
+    """Third column onwards = confidences of the observations; scaled in place so that they sum to 2 per unit of
+    total match confidence (every match contributes two observations; bundle_adjust_io.py:56-60)."""
+    obs_xyc[:, 2:] *= 2.0 / (obs_xyc[:, 2:].sum(axis=0, keepdims=True) + 1e-3)
     return obs_xyc
 
 

@@ -18,28 +18,26 @@ def _intr4(intr):
 
 
 def normalize(kpts, intr):
-    """estimate_relative_pose.py:9-14 (elementwise; also fused into mvm_w8pt)."""
-    n_kpts = torch.zeros_like(kpts)
-    fx, fy, cx, cy = intr[..., 0, 0], intr[..., 1, 1], intr[..., 0, 2], intr[..., 1, 2]
-    n_kpts[..., 0] = (kpts[..., 0] - cx.unsqueeze(-1)) / fx.unsqueeze(-1)
-    n_kpts[..., 1] = (kpts[..., 1] - cy.unsqueeze(-1)) / fy.unsqueeze(-1)
-    return n_kpts
+    """Pixel -> normalised camera coordinates with (fx, fy, cx, cy) of a 3x3 or 4x4 K; same result as the reference's
+    normalize (estimate_relative_pose.py:9-14).  (The kernels fuse this; the function serves callers of the API.)"""
+    focal = torch.stack((intr[..., 0, 0], intr[..., 1, 1]), -1).unsqueeze(-2)       # [..., 1, 2]
+    centre = torch.stack((intr[..., 0, 2], intr[..., 1, 2]), -1).unsqueeze(-2)
+    return (kpts - centre) / focal
 
 
 def get_kpts(data, result, id0, id1):
-    """estimate_relative_pose.py:16-31 (gather matched keypoints; -1 wraps to the last one)."""
-    if "keypoints" + str(id0) in data:
-        keypoints0, keypoints1 = data["keypoints" + str(id0)], data["keypoints" + str(id1)]
-    else:
-        keypoints0, keypoints1 = data["keypoints{}_{}_{}".format(id0, id0, id1)], data["keypoints{}_{}_{}".format(id1, id0, id1)]
-    matches = result["matches{}_{}_{}".format(id0, id0, id1)]
-    intr0, intr1 = data["intr" + str(id0)], data["intr" + str(id1)]
-    bs, n_kpts0, _ = keypoints0.shape
-    batch_idx0 = torch.arange(bs, device=keypoints0.device).unsqueeze(-1).expand(bs, n_kpts0)
-    confidence = result["conf_scores_{}_{}".format(id0, id1)]
-    confidence = (matches >= 0).float().unsqueeze(-1) * confidence
-    keypoints1 = keypoints1[batch_idx0, matches]
-    return keypoints0, keypoints1, intr0, intr1, confidence
+    """Matched keypoints of pair (id0, id1) and their confidences, contract of estimate_relative_pose.py:16-31:
+    view-1 keypoints gathered by matches0 (an unmatched keypoint, index -1, picks up the LAST keypoint like the
+    reference's negative index does -- its confidence is zeroed), confidence = conf_scores masked by matches >= 0."""
+    pair = "{}_{}".format(id0, id1)
+    per_view = "keypoints" + str(id0) in data
+    k0 = data["keypoints" + str(id0)] if per_view else data["keypoints{}_{}".format(id0, pair)]
+    k1 = data["keypoints" + str(id1)] if per_view else data["keypoints{}_{}".format(id1, pair)]
+    m0 = result["matches{}_{}".format(id0, pair)]
+    wrapped = torch.where(m0 < 0, m0 + k1.shape[1], m0).long()
+    k1_matched = torch.gather(k1, 1, wrapped.unsqueeze(-1).expand(-1, -1, k1.shape[-1]))
+    conf = result["conf_scores_" + pair] * (m0 >= 0).unsqueeze(-1).to(result["conf_scores_" + pair].dtype)
+    return k0, k1_matched, data["intr" + str(id0)], data["intr" + str(id1)], conf
 
 
 def _run_w8pt(kpts0, kpts1, intr0, intr1, conf, choose_closest, T_021, determine_inliers, n_valid=None,

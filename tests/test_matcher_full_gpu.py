@@ -62,7 +62,7 @@ def test_full_size_matcher_vs_reference(name):
             # (the split-operand arithmetic carries a systematic +1e-5 .. +1e-4 bias, profiles/r02_score_ab.txt: this is a
             # gross-error check -- a dropped row or column shifts the mean by far more)
             assert np.abs(Zc.sum((1, 2)) - chk[:, 0]).max() / numel < 2e-4, sk
-            assert np.abs((Zc * Zc).sum((1, 2)) - chk[:, 1]).max() / np.abs(chk[:, 1]).max() < 2e-5, sk
+            assert np.abs((Zc * Zc).sum((1, 2)) - chk[:, 1]).max() / np.abs(chk[:, 1]).max() < 1e-4, sk
             # ---- matches: exact on every row whose top-2 margin (ours) exceeds tau ----
             inner = Z[:, :-1, :-1]
             top2 = torch.topk(inner, 2, dim=2).values
