@@ -45,6 +45,7 @@ struct HCfg {
   static constexpr int SMEM_BYTES = OFF_ML + 2048 + 1024;
   static constexpr int NTHREADS = 352;
   static constexpr int TMEM_COLS = 512;                 // 448 used (allocation sizes are powers of two)
+  static constexpr int MAX_TILES = 256;                 // key tiles per query view: 7 segments x 2048 keys / 64 = 224
 };
 
 struct AttnH3Args {
@@ -124,6 +125,8 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   // CTA-level trace (second half of the debug buffer): [cta][8] = smid, start, setup done, Q stored, first S read,
   // last tile done, merged + stored
   const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  // producer timeline (third region of the debug buffer): [tile][4] = K wait done, K requested, V wait done, V requested
+  auto pmark = [&](int tile, int slot) { if (trace_cta && tile < 64) g.dbg[64 * 16 + 2048 * 8 + tile * 4 + slot] = clock64(); };
   auto cmark = [&](int slot) {
     if (g.dbg != nullptr && cta_lin < 2048) g.dbg[64 * 16 + cta_lin * 8 + slot] = clock64();
   };
@@ -171,6 +174,21 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     seg = 0; k0 = 0; cnt = 0;
   };
 
+  // Tile table, filled once by the whole CTA: the producer warp shares its scheduler with two softmax warps, and
+  // recomputing (segment, offset) with loops and divisions for every K and V tile made its ~400 instructions per
+  // tile the bottleneck of the fp16 kernel (clock trace r02: the producer issued a tile's loads 1.5 k cycles apart,
+  // the MMA issuer waited 800 cycles per tile for K).  One shared-memory load per tile instead.
+  __shared__ int s_krow[C_::MAX_TILES];       // row of the tile's first key in the K planes
+  __shared__ int s_vrow[C_::MAX_TILES];       // first row of the (view, head) block in the V^T planes
+  __shared__ int s_vk0[C_::MAX_TILES];        // first key (column) of the tile in the V^T planes
+  for (int j = threadIdx.x; j < nt; j += C_::NTHREADS) {
+    int seg, k0, cnt;
+    tile_info(j, seg, k0, cnt);
+    s_krow[j] = (b * T + seg) * g.n_pad + k0;
+    s_vrow[j] = (b * T + seg) * 256 + h * HD;
+    s_vk0[j] = k0;
+  }
+
   auto sK = [&](int s) { return smem + C_::OFF_K + s * K_BYTES * 2; };
   auto sV = [&](int s) { return smem + C_::OFF_V + s * V_BYTES * 2; };
 
@@ -201,30 +219,30 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   if (warp == 0) {
     // =========================== TMA producer ===========================
     auto load_K = [&](int j) {
-      int seg, k0, cnt;
-      tile_info(j, seg, k0, cnt);
       const int s = j % ST;
       tc::mbar_wait(k_empty + s, ((j / ST) & 1) ^ 1);
+      if (lane == 0) pmark(j, 0);
       if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(k_full + s, K_BYTES * 2);
-        const int krow = (b * T + seg) * g.n_pad + k0;
+        const int krow = s_krow[j];
         tc::tma_load_2d(sK(s), &tmK, k_full + s, h * HD, krow);
         tc::tma_load_2d(sK(s) + K_BYTES, &tmKlo, k_full + s, h * HD, krow);
       }
       __syncwarp();
+      if (lane == 0) pmark(j, 1);
     };
     auto load_V = [&](int j) {
-      int seg, k0, cnt;
-      tile_info(j, seg, k0, cnt);
       const int s = j % ST;
       tc::mbar_wait(v_empty + s, ((j / ST) & 1) ^ 1);
+      if (lane == 0) pmark(j, 2);
       if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(v_full + s, V_BYTES * 2);
-        const int vrow = (b * T + seg) * 256 + h * HD;
+        const int vrow = s_vrow[j], k0 = s_vk0[j];
         tc::tma_load_2d(sV(s), &tmV, v_full + s, k0, vrow);
         tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, k0, vrow);
       }
       __syncwarp();
+      if (lane == 0) pmark(j, 3);
     };
     load_K(0);
     for (int j = 0; j < nt; ++j) {
@@ -470,6 +488,8 @@ int launch_attention_h3(const float* qkv, const __half* kh, const __half* kl, co
   MVM_REQUIRE(qkv && kh && kl && vth && vtl && out);
   MVM_REQUIRE(n_pad % 64 == 0 && segs.n_views >= 1 && segs.n_views <= 8);
   MVM_REQUIRE(!is_cross || segs.n_views >= 2);
+  MVM_REQUIRE((segs.n_views - 1) * (n_pad / 64) <= HCfg::MAX_TILES || !is_cross);
+  MVM_REQUIRE(n_pad / 64 <= HCfg::MAX_TILES);
   MvmProfScope prof__(MVM_TAG_ATTN, stream);
   using C_ = HCfg;
   mvm_once_per_device(MVM_ONCE_ATTN_H3, [&] {

@@ -5,7 +5,7 @@ from e2e_multi_view_matching_b200 import ops, _lib
 lib = _lib.lib()
 mode = sys.argv[1] if len(sys.argv) > 1 else 'h3'        # 'h3' (fp16x3), 3 (tf32x3) or 1 (single-pass tf32)
 mode = mode if mode == 'h3' else int(mode)
-buf = torch.zeros(64 * 16 + 2048 * 8, dtype=torch.int64, device='cuda')
+buf = torch.zeros(64 * 16 + 2048 * 8 + 64 * 4, dtype=torch.int64, device='cuda')
 lib.mvm_debug_set_attention_timing.argtypes = [ctypes.c_void_p]
 g = torch.Generator().manual_seed(0)
 B, T, N = 8, 5, 1024
@@ -17,7 +17,8 @@ ops.attention(qkv, B, T, [N] * T, 1, tc_passes=mode)
 torch.cuda.synchronize()
 lib.mvm_debug_set_attention_timing(ctypes.c_void_p(0))
 t = buf[:64 * 16].view(64, 16).cpu().numpy()
-c = buf[64 * 16:].view(2048, 8).cpu().numpy()
+c = buf[64 * 16:64 * 16 + 2048 * 8].view(2048, 8).cpu().numpy()
+pr = buf[64 * 16 + 2048 * 8:].view(64, 4).cpu().numpy()
 t0 = t[0, 8]
 names = ['sm:wait S', 'sm:S ready', 'sm:ld done', 'sm:max done', 'sm:P half a', 'sm:P half b', 'S:issued', 'S:committed',
          'S:iter start', 'S:K+buffer ready', 'PV:P a ready', 'PV:a issued', 'PV:P b ready', 'PV:b issued', 'PV:commit1', 'PV:commit2']
@@ -25,6 +26,10 @@ print('tile ' + ' '.join('%16s' % n for n in names))
 for j in range(20, 28):
     print('%4d ' % j + ' '.join('%16d' % (t[j, k] - t0) for k, n in enumerate(names)))
 print('period per tile: %.0f clk' % ((t[40, 8] - t[20, 8]) / 20))
+if mode == 'h3' and pr.any():
+    print('producer (relative to the same origin): tile, K slot free, K requested, V slot free, V requested | S warp: iter start, K landed')
+    for j in list(range(0, 10)) + list(range(20, 28)):
+        print('%4d ' % j + ' '.join('%9d' % (pr[j, k] - t0) for k in range(4)) + ' | %9d %9d' % (t[j, 8] - t0, t[j, 9] - t0))
 for a, b, label in ((1, 2, 'S ready -> ld done'), (2, 3, 'ld -> max/vote'), (3, 4, 'exp half a + st + arrive'), (4, 5, 'exp half b + st + arrive'),
                     (0, 1, 'softmax warp waits for S'), (8, 9, 'S warp: waits (K, buffer)'), (9, 6, 'S warp: 24 UMMAs issue'), (6, 7, 'S warp: two commits'),
                     (10, 11, 'PV warp: 12 UMMAs a'), (11, 12, 'PV warp: wait P b'), (12, 13, 'PV warp: 12 UMMAs b'), (13, 15, 'PV warp: two commits')):
