@@ -335,6 +335,8 @@ def main():
                     help='3xTF32 GEMM kernel: persistent (default) or the one-tile-per-CTA kernel (A/B comparison)')
     ap.add_argument('--attn-split', type=int, default=-1, choices=[-1, 0, 1],
                     help='operand planes of the mode-3 attention: 0 = tf32 hi/lo, 1 = fp16 hi/lo, -1 = library default')
+    ap.add_argument('--gemm-split', type=int, default=-1, choices=[-1, 0, 1],
+                    help='operand planes of the mode-3 layer GEMMs (persistent kernel): 0 = tf32 hi/lo, 1 = fp16 hi/lo')
     ap.add_argument('--math-mode', type=int, default=3, choices=[0, 1, 3],
                     help='3 = tcgen05 3xTF32 (fp32-faithful, default), 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA cores')
     args = ap.parse_args()
@@ -364,6 +366,8 @@ def main():
     lib.mvm_debug_set_gemm_kernel(1 if args.gemm_kernel == 'persistent' else 0)
     if args.attn_split >= 0:
         lib.mvm_debug_set_attention_split(args.attn_split)
+    if args.gemm_split >= 0:
+        lib.mvm_debug_set_gemm_split(args.gemm_split)
     opt = _lib.MatcherOptions()
     lib.mvm_matcher_options_default(opt)
     B = args.tuples or cfg['batch']
@@ -539,11 +543,12 @@ def main():
         line = {
             'metric': cfg['metric'], 'value': value, 'unit': cfg['unit'], 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': {3: 'tf32x3 on tcgen05 (fp32-faithful) / f64 pose kernels', 1: 'tf32 on tcgen05 / f64 pose kernels',
+            'vs_baseline': None, 'dtype': {3: 'f32 via split operands on tcgen05 (fp16x3 / tf32x3, fp32-faithful) / f64 pose kernels', 1: 'tf32 on tcgen05 / f64 pose kernels',
                       0: 'f32 CUDA cores / f64 pose kernels'}[args.math_mode], 'data': 'synthetic',
             'config': workload_config(cfg), 'units_per_step': B * world,
             'run': {'units_per_step_per_gpu': B, 'l2': 'flushed between timed steps (256 MB write)',
                     'math_mode': args.math_mode, 'attention_split': {0: 'tf32 hi/lo', 1: 'fp16 hi/lo'}[opt.attention_split],
+                    'gemm_split': {0: 'tf32 hi/lo', 1: 'fp16 hi/lo'}[opt.gemm_split],
                     'parallelism': 'dp%d' % world,
                     'weights': 'seeded random GNN (final_proj gain 12) + score-driven confidence head (synthetic.py)'},
             'e2e': {'value': e2e, 'unit': cfg['unit'], 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,

@@ -33,7 +33,8 @@ class MatcherWeights(C.Structure):
                 ('conf_wf1', _fp), ('conf_bf1', _fp),
                 ('conf_wc0', _fp), ('conf_bc0', _fp),
                 ('conf_wc1', _fp), ('conf_bc1', _fp),
-                ('conf_wl', _fp), ('conf_bl', C.c_float)]
+                ('conf_wl', _fp), ('conf_bl', C.c_float),
+                ('flat_base', _fp), ('w16_hi', _fp), ('w16_lo', _fp), ('w16_scale', C.c_float)]
 
 
 class PairIO(C.Structure):
@@ -45,7 +46,7 @@ class PairIO(C.Structure):
 
 class MatcherOptions(C.Structure):
     _fields_ = [('math_mode', C.c_int), ('score_kernel', C.c_int), ('gemm_tile', C.c_int), ('gemm_kernel', C.c_int),
-                ('sinkhorn_variant', C.c_int), ('attention_split', C.c_int)]
+                ('sinkhorn_variant', C.c_int), ('attention_split', C.c_int), ('gemm_split', C.c_int)]
 
 
 class SuperPointWeights(C.Structure):
@@ -85,7 +86,7 @@ def lib():
         C.c_float, C.c_float, C.c_int, C.c_float, C.POINTER(PairIO), C.c_int, _fp, C.c_size_t,
         C.POINTER(MatcherOptions), _fp]
     for name in ('mvm_debug_set_score_kernel', 'mvm_debug_set_gemm_tile', 'mvm_debug_set_gemm_kernel',
-                 'mvm_debug_set_attention_split'):
+                 'mvm_debug_set_attention_split', 'mvm_debug_set_gemm_split'):
         getattr(L, name).restype = None
         getattr(L, name).argtypes = [C.c_int]
     for name in ('mvm_debug_set_attention_timing', 'mvm_debug_set_sinkhorn_timing', 'mvm_debug_set_mvba_timing'):
@@ -97,6 +98,9 @@ def lib():
     L.mvm_linear_tc_presplit.restype = C.c_int
     L.mvm_linear_tc_presplit.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_int, _fp, _fp, C.c_int, _fp, _fp, C.c_int,
                                          _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp]
+    L.mvm_linear_tc_h16.restype = C.c_int
+    L.mvm_linear_tc_h16.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_int, _fp, _fp, C.c_int,
+                                    _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp]
     L.mvm_linear_tc.restype = C.c_int
     L.mvm_linear_tc.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int,
                                 _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _fp]

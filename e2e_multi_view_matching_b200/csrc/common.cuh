@@ -86,6 +86,8 @@ struct GemmDesc {
   const float* A2; int lda2; int K1;
   const float* W;  int ldw;
   const float* Whi; const float* Wlo;          // optional pre-split tf32 planes of W (3xTF32 mode)
+  const void* Whi16; const void* Wlo16;        // optional half-precision planes of wscale * W (fp16x3 mode, persistent kernel)
+  float wscale;
   const float* bias;
   const float* R;  int ldr;
   float* C;        int ldc;

@@ -31,14 +31,23 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 4;
+constexpr int BM = 128, BN = 128;
 constexpr int NTHREADS = 320;
-constexpr int A_BYTES = BM * BK * 4;              // 16 KB
-constexpr int W_BYTES = BN * BK * 4;              // 16 KB per plane
-constexpr int STAGE_BYTES = A_BYTES + 2 * W_BYTES;
+// Two operand arithmetics (template parameter F16 of the kernel):
+//   tf32x3 (F16 = false): k-block 32, W planes fp32 (tf32 values), kind::tf32 K = 8 per MMA, 4 stages of 48 KB
+//   fp16x3 (F16 = true):  k-block 64, W planes fp16 (pre-scaled by a power of two, packing.py), kind::f16 K = 16 per
+//                         MMA: the same 22-bit operands at half the tensor-pipe time; 3 stages of 64 KB
+// A W plane tile is 16 KB in both ([128 x 32] fp32 or [128 x 64] fp16, 128-byte rows), the raw fp32 A tile 16 / 32 KB.
+template <bool F16> struct GCfg {
+  static constexpr int BK = F16 ? 64 : 32;
+  static constexpr int STAGES = F16 ? 3 : 4;
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int W_BYTES = 16384;
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * W_BYTES;
+};
+static_assert(GCfg<true>::STAGES * GCfg<true>::STAGE_BYTES == GCfg<false>::STAGES * GCfg<false>::STAGE_BYTES, "same ring size");
 constexpr int STG_BYTES = 32 * 128;               // one staged [32 rows x 32 cols] block per epilogue warp
-constexpr int OFF_STG = STAGES * STAGE_BYTES;     // 4 warps x 2 buffers
+constexpr int OFF_STG = GCfg<false>::STAGES * GCfg<false>::STAGE_BYTES;     // 4 warps x 2 buffers
 constexpr int OFF_BIAS = OFF_STG + 8 * STG_BYTES;
 constexpr int OFF_BAR = OFF_BIAS + BN * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
@@ -73,12 +82,36 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
-template <bool SCORE>
+__device__ __forceinline__ void split_pack_h(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {   // D = F32, A = B = F16, both K-major
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <bool SCORE, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                        const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmKLO, PArgs g,
                        const __grid_constant__ ScoreTab st) {
+  using G_ = GCfg<F16>;
+  constexpr int BK = G_::BK, STAGES = G_::STAGES, A_BYTES = G_::A_BYTES, W_BYTES = G_::W_BYTES, STAGE_BYTES = G_::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
@@ -142,6 +175,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int k = kt * BK;
           if (k < g.K1) tc::tma_load_2d(sp, &tmA, full + s, k, a_row);
           else tc::tma_load_2d(sp, &tmA2, full + s, k - g.K1, a_row);
+          if (F16) {   // second [128 x 32] fp32 box of the 64-wide k-block (K1 is a multiple of 64: same side of the concat)
+            if (k < g.K1) tc::tma_load_2d(sp + 16384, &tmA, full + s, k + 32, a_row);
+            else tc::tma_load_2d(sp + 16384, &tmA2, full + s, k + 32 - g.K1, a_row);
+          }
           tc::tma_load_2d(sp + A_BYTES, &tmWhi, full + s, k, w_row);
           tc::tma_load_2d(sp + A_BYTES + W_BYTES, &tmWlo, full + s, k, w_row);
         }
@@ -151,7 +188,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     // the whole warp walks the loop (converged); one elected lane issues
-    constexpr uint32_t idesc = tc::make_idesc_tf32(BM, BN);
+    constexpr uint32_t idesc = F16 ? make_idesc_f16(BM, BN) : tc::make_idesc_tf32(BM, BN);
     uint32_t it = 0;
     int i = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
@@ -169,11 +206,17 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint32_t a_hi = tmem_base + TM_A + s * 64, a_lo = a_hi + 32;
         if (tc::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk) {
+          for (int kk = 0; kk < 4; ++kk) {        // 4 x (K = 8 tf32 | K = 16 halves) = 32 bytes of a 128-byte row each
             const uint64_t dhi = tc::make_kmajor_sw128_desc(whi + kk * 32);
-            tc::umma_tf32_ts(acc, a_hi + kk * 8, dhi, idesc, (kt | kk) != 0);
-            tc::umma_tf32_ts(acc, a_hi + kk * 8, tc::make_kmajor_sw128_desc(wlo + kk * 32), idesc, 1);
-            tc::umma_tf32_ts(acc, a_lo + kk * 8, dhi, idesc, 1);
+            if (F16) {
+              umma_f16_ts(acc, a_hi + kk * 8, dhi, idesc, (kt | kk) != 0);
+              umma_f16_ts(acc, a_hi + kk * 8, tc::make_kmajor_sw128_desc(wlo + kk * 32), idesc, 1);
+              umma_f16_ts(acc, a_lo + kk * 8, dhi, idesc, 1);
+            } else {
+              tc::umma_tf32_ts(acc, a_hi + kk * 8, dhi, idesc, (kt | kk) != 0);
+              tc::umma_tf32_ts(acc, a_hi + kk * 8, tc::make_kmajor_sw128_desc(wlo + kk * 32), idesc, 1);
+              tc::umma_tf32_ts(acc, a_lo + kk * 8, dhi, idesc, 1);
+            }
           }
           tc::umma_commit(empty + s);
           if (kt == nk - 1) tc::umma_commit(acc_full + buf);
@@ -194,12 +237,28 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // row r of the 128B-swizzled tile: 16-byte chunk c sits at position c ^ (r & 7)
         const float4* a = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES + row * 128);
         float hi[32], lo[32];
+        if (F16) {
+          // 64 fp32 of the row (two swizzled 128-byte rows, 16 KB apart) -> 32 + 32 packed half2 columns
+          uint32_t* hp = reinterpret_cast<uint32_t*>(hi);
+          uint32_t* lp = reinterpret_cast<uint32_t*>(lo);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 x = a[c ^ (row & 7)];
-          hi[4 * c] = tf32_hi(x.x); hi[4 * c + 1] = tf32_hi(x.y); hi[4 * c + 2] = tf32_hi(x.z); hi[4 * c + 3] = tf32_hi(x.w);
-          lo[4 * c] = tf32_hi(x.x - hi[4 * c]); lo[4 * c + 1] = tf32_hi(x.y - hi[4 * c + 1]);
-          lo[4 * c + 2] = tf32_hi(x.z - hi[4 * c + 2]); lo[4 * c + 3] = tf32_hi(x.w - hi[4 * c + 3]);
+          for (int b2 = 0; b2 < 2; ++b2) {
+            const float4* ab = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES + b2 * 16384 + row * 128);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 x = ab[c ^ (row & 7)];
+              split_pack_h(x.x, x.y, hp[b2 * 16 + 2 * c], lp[b2 * 16 + 2 * c]);
+              split_pack_h(x.z, x.w, hp[b2 * 16 + 2 * c + 1], lp[b2 * 16 + 2 * c + 1]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 x = a[c ^ (row & 7)];
+            hi[4 * c] = tf32_hi(x.x); hi[4 * c + 1] = tf32_hi(x.y); hi[4 * c + 2] = tf32_hi(x.z); hi[4 * c + 3] = tf32_hi(x.w);
+            lo[4 * c] = tf32_hi(x.x - hi[4 * c]); lo[4 * c + 1] = tf32_hi(x.y - hi[4 * c + 1]);
+            lo[4 * c + 2] = tf32_hi(x.z - hi[4 * c + 2]); lo[4 * c + 3] = tf32_hi(x.w - hi[4 * c + 3]);
+          }
         }
         const uint32_t ta = tmem_base + TM_A + s * 64 + lane_addr;
         tc::tmem_st32(ta, hi);
@@ -382,19 +441,22 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO,
                            cudaStream_t stream, const HalfPlanes* hp) {
   mvm_once_per_device(MVM_ONCE_GEMM_PERSIST, [&] {
-    cudaFuncSetAttribute(gemm_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_persist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_persist_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   const int n_sm = mvm_dev_info().n_sm;
+  // fp16x3 when the half-precision weight planes are given and the shape allows 64-wide k-blocks
+  const bool f16 = d.Whi16 != nullptr && d.Wlo16 != nullptr && d.K % 64 == 0 && d.K1 % 64 == 0 && d.wscale > 0.f;
   const CUtensorMap* tA = mvm_get_tmap_2d(d.A, d.M, d.K1, d.lda, BM);
   const CUtensorMap* tA2 = d.A2 ? mvm_get_tmap_2d(d.A2, d.M, d.K - d.K1, d.lda2, BM) : tA;
-  const CUtensorMap* tWhi = mvm_get_tmap_2d(d.Whi, d.N, d.K, d.ldw, BN);
-  const CUtensorMap* tWlo = mvm_get_tmap_2d(d.Wlo, d.N, d.K, d.ldw, BN);
+  const CUtensorMap* tWhi = f16 ? mvm_get_tmap_2d_f16(d.Whi16, d.N, d.K, d.ldw, BN) : mvm_get_tmap_2d(d.Whi, d.N, d.K, d.ldw, BN);
+  const CUtensorMap* tWlo = f16 ? mvm_get_tmap_2d_f16(d.Wlo16, d.N, d.K, d.ldw, BN) : mvm_get_tmap_2d(d.Wlo, d.N, d.K, d.ldw, BN);
   const CUtensorMap* tC = mvm_get_tmap_2d(d.C, d.M, d.N, d.ldc, 32);
   const CUtensorMap* tK = KLO ? mvm_get_tmap_2d(KLO, d.M, 256, 256, 32) : tC;
   if (!tA || !tA2 || !tWhi || !tWlo || !tC || !tK) return MVM_ERR_LAUNCH;
   PArgs g;
   g.bias = d.bias; g.R = d.R; g.ldr = d.ldr; g.C = d.C; g.ldc = d.ldc; g.M = d.M; g.N = d.N; g.K = d.K;
-  g.K1 = d.K1; g.alpha = d.alpha; g.relu = d.relu; g.VT = VT; g.vt_col0 = vt_col0; g.n_pad = n_pad;
+  g.K1 = d.K1; g.alpha = f16 ? d.alpha / d.wscale : d.alpha; g.relu = d.relu; g.VT = VT; g.vt_col0 = vt_col0; g.n_pad = n_pad;
   g.KLO = KLO; g.VTLO = VTLO;
   g.KH16 = hp ? (__half*)hp->kh : nullptr; g.KL16 = hp ? (__half*)hp->kl : nullptr;
   g.VTH16 = hp ? (__half*)hp->vth : nullptr; g.VTL16 = hp ? (__half*)hp->vtl : nullptr;
@@ -403,7 +465,8 @@ int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad,
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   ScoreTab none;
   none.n_pairs = 0; none.batch = 0; none.n_views = 0; none.n_pad = 0;
-  gemm_tc_persist_kernel<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, g, none);
+  if (f16) gemm_tc_persist_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, g, none);
+  else gemm_tc_persist_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, g, none);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }
@@ -429,7 +492,7 @@ int launch_score_gemm_tc(const float* mdesc, float* hi, float* lo, int n_pad, co
                          float alpha, cudaStream_t stream) {
   MvmProfScope prof__(MVM_TAG_SCORE, stream);
   mvm_once_per_device(MVM_ONCE_GEMM_SCORE, [&] {
-    cudaFuncSetAttribute(gemm_tc_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_persist_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   const int n_sm = mvm_dev_info().n_sm;
   const long long rows = (long long)batch * tab.n_views * n_pad;
@@ -454,7 +517,7 @@ int launch_score_gemm_tc(const float* mdesc, float* hi, float* lo, int n_pad, co
   g.tiles_m = mvm_div_up(max_m, BM); g.tiles_n = mvm_div_up(max_n, BN);
   const long long n_tiles = (long long)g.tiles_m * g.tiles_n * tab.n_pairs * batch;
   const int grid = n_tiles < n_sm ? (int)n_tiles : n_sm;
-  gemm_tc_persist_kernel<true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA, *tWhi, *tWlo, *tA, *tA, g, st);
+  gemm_tc_persist_kernel<true, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA, *tWhi, *tWlo, *tA, *tA, g, st);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }

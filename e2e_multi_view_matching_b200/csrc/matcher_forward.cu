@@ -59,7 +59,8 @@ GemmDesc make_gemm(const float* A, int lda, const float* W, int K, const float* 
                    int ldc, int M, int N, int relu) {
   GemmDesc g;
   g.A = A; g.lda = lda; g.A2 = nullptr; g.lda2 = 0; g.K1 = K;
-  g.W = W; g.ldw = K; g.Whi = nullptr; g.Wlo = nullptr; g.bias = bias; g.R = nullptr; g.ldr = 0;
+  g.W = W; g.ldw = K; g.Whi = nullptr; g.Wlo = nullptr; g.Whi16 = nullptr; g.Wlo16 = nullptr; g.wscale = 0.f;
+  g.bias = bias; g.R = nullptr; g.ldr = 0;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = 1.f; g.relu = relu;
   g.batch = 1; g.sA = g.sA2 = g.sW = g.sR = g.sC = 0;
   return g;
@@ -71,17 +72,31 @@ GemmDesc make_gemm(const float* A, int lda, const float* W, int K, const float* 
 // math mode: 3 = tcgen05 3xTF32 (fp32-faithful, DEFAULT), 1 = tcgen05 single-pass TF32, 0 = fp32 CUDA cores
 int g_math_mode = 3;
 int g_score_tc = 1;                     // score GEMM on the tensor cores in mode 3 (mvm_debug_set_score_kernel)
+int g_gemm_split = 1;                   // operand planes of the mode-3 GEMMs: 1 = fp16 hi/lo (default, needs the packed half planes), 0 = tf32
 int g_attn_split = 1;                   // operand planes of the mode-3 attention: 1 = fp16 hi/lo (default), 0 = tf32 hi/lo
 
 // everything a forward needs to know beyond its arguments, by value
 struct Ctx {
   int math_mode, score_tc, gemm_tile, gemm_persist, sinkhorn_variant, attn_split;
   long long hi_off, lo_off;             // tf32 planes of the weights (mvm_matcher_weights)
+  const float* flat_base;               // start of the flat fp32 weight buffer the half planes mirror element for element
+  const __half* w16_hi; const __half* w16_lo; float w16_scale;   // fp16 planes of w16_scale * W (null: tf32x3 GEMMs)
 };
+
+// the W planes of a GEMM: tf32 (always, the one-tile kernels use them) and, when packed, the half-precision ones
+void set_planes(const Ctx& cx, GemmDesc& g) {
+  if (cx.math_mode == 3 && cx.lo_off != 0) {
+    g.Whi = g.W + cx.hi_off; g.Wlo = g.W + cx.lo_off;
+    if (cx.w16_hi) {
+      const long long e = g.W - cx.flat_base;
+      g.Whi16 = cx.w16_hi + e; g.Wlo16 = cx.w16_lo + e; g.wscale = cx.w16_scale;
+    }
+  }
+}
 
 int run_gemm(const Ctx& cx, const GemmDesc& g_in, cudaStream_t s) {
   GemmDesc g = g_in;
-  if (cx.math_mode == 3 && cx.lo_off != 0) { g.Whi = g.W + cx.hi_off; g.Wlo = g.W + cx.lo_off; }
+  set_planes(cx, g);
   if (cx.math_mode != 0 && g.batch == 1 && g.N % 128 == 0 && g.K % 32 == 0 && g.K1 % 32 == 0 && g.ldc % 4 == 0)
     return launch_gemm_tc(g, cx.math_mode, nullptr, 0, 0, s, nullptr, nullptr, cx.gemm_tile, cx.gemm_persist);
   return launch_gemm_simt(g, s);
@@ -120,6 +135,7 @@ extern "C" {
 
 void mvm_debug_set_score_kernel(int tc) { g_score_tc = tc ? 1 : 0; }
 void mvm_debug_set_attention_split(int fp16) { g_attn_split = fp16 ? 1 : 0; }
+void mvm_debug_set_gemm_split(int fp16) { g_gemm_split = fp16 ? 1 : 0; }
 
 const char* mvm_version(void) { return "mvm_b200 0.1 sm_100a"; }
 
@@ -135,6 +151,7 @@ void mvm_matcher_options_default(mvm_matcher_options* o) {
   o->gemm_kernel = mvm_default_gemm_persistent();
   o->sinkhorn_variant = 0;
   o->attention_split = g_attn_split;
+  o->gemm_split = g_gemm_split;
 }
 
 int mvm_matcher_forward(const mvm_matcher_weights* w, int batch, int n_views, int n_pad,
@@ -170,6 +187,11 @@ int mvm_matcher_forward_ex(const mvm_matcher_weights* w, int batch, int n_views,
   cx.hi_off = w->hi_offset; cx.lo_off = w->lo_offset;
   // the fp16x3 attention needs the persistent GEMM (its epilogue writes the half-precision planes) and pre-split weights
   cx.attn_split = (o.attention_split == 1 && cx.math_mode == 3 && cx.lo_off != 0) ? 1 : 0;
+  const bool g16 = o.gemm_split == 1 && cx.math_mode == 3 && cx.gemm_persist && w->w16_hi && w->w16_lo && w->flat_base && w->w16_scale > 0.f;
+  cx.flat_base = w->flat_base;
+  cx.w16_hi = g16 ? (const __half*)w->w16_hi : nullptr;
+  cx.w16_lo = g16 ? (const __half*)w->w16_lo : nullptr;
+  cx.w16_scale = w->w16_scale;
   const int V = batch * n_views;
   const int rows = V * n_pad;
   AttnSegs segs;
@@ -196,7 +218,7 @@ int mvm_matcher_forward_ex(const mvm_matcher_weights* w, int batch, int n_views,
       __half* vth = reinterpret_cast<__half*>(ws.VTLO);
       HalfPlanes hp = {kh, kh + (size_t)rows * 256, vth, vth + (size_t)rows * 256};
       GemmDesc gq = make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0);
-      gq.Whi = gq.W + cx.hi_off; gq.Wlo = gq.W + cx.lo_off;
+      set_planes(cx, gq);
       MVM_TRY(launch_gemm_tc_persist(gq, nullptr, 512, n_pad, nullptr, nullptr, s, &hp));
       MVM_TRY(launch_attention_h3(ws.QKV, (const __half*)hp.kh, (const __half*)hp.kl, (const __half*)hp.vth,
                                   (const __half*)hp.vtl, ws.MSG, batch, n_pad, segs, L.is_cross, s));
@@ -297,6 +319,18 @@ int mvm_linear_tc_presplit(const float* A, int lda, const float* A2, int lda2, i
   if (A2) { g.A2 = A2; g.lda2 = lda2; g.K1 = K1; }
   if (R) { g.R = R; g.ldr = ldr; }
   return launch_gemm_tc(g, 3, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+int mvm_linear_tc_h16(const float* A, int lda, const float* A2, int lda2, int K1, const void* W16_hi, const void* W16_lo,
+                      float wscale, int ldw, const float* bias, const float* R, int ldr, float* C, int ldc, int M, int N, int K,
+                      float alpha, int relu, void* stream) {
+  MVM_REQUIRE(A && W16_hi && W16_lo && C && wscale > 0.f && K % 64 == 0 && N % 128 == 0);
+  GemmDesc g = make_gemm(A, lda, reinterpret_cast<const float*>(W16_hi), K, bias, C, ldc, M, N, relu);
+  g.ldw = ldw; g.alpha = alpha; g.Whi = g.W; g.Wlo = g.W;       // (the tf32 planes are not read in the fp16 mode)
+  g.Whi16 = W16_hi; g.Wlo16 = W16_lo; g.wscale = wscale;
+  if (A2) { g.A2 = A2; g.lda2 = lda2; g.K1 = K1; MVM_REQUIRE(K1 % 64 == 0); }
+  if (R) { g.R = R; g.ldr = ldr; }
+  return launch_gemm_tc_persist(g, nullptr, 0, 0, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int mvm_attention(const float* qkv, float* out, int batch, int n_views, int n_pad,

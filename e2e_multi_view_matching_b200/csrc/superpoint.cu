@@ -343,7 +343,8 @@ int mvm_superpoint_dense(const mvm_superpoint_weights* wt, const float* image, i
   {
     GemmDesc g;
     g.A = Bf; g.lda = 256; g.A2 = nullptr; g.lda2 = 0; g.K1 = 256;
-    g.W = wt->w_db; g.ldw = 256; g.Whi = nullptr; g.Wlo = nullptr; g.bias = wt->b_db; g.R = nullptr; g.ldr = 0;
+    g.W = wt->w_db; g.ldw = 256; g.Whi = nullptr; g.Wlo = nullptr; g.Whi16 = nullptr; g.Wlo16 = nullptr; g.wscale = 0.f;
+    g.bias = wt->b_db; g.R = nullptr; g.ldr = 0;
     g.C = dense_desc; g.ldc = 256; g.M = (int)cpx; g.N = 256; g.K = 256; g.alpha = 1.f; g.relu = 0;
     g.batch = 1; g.sA = g.sA2 = g.sW = g.sR = g.sC = 0;
     SP_TRY(launch_gemm_tc(g, 3, nullptr, 0, 0, s, nullptr, nullptr, 128, 0));

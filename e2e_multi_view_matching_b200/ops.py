@@ -18,6 +18,22 @@ def linear(a, w, bias=None, a2=None, residual=None, relu=False, alpha=1.0, tc_pa
     presplit (with tc_passes=3): hand W over as its tf32 hi/lo planes, like the packed matcher weights do --
     this is the production path (persistent kernel)."""
     lib = _lib.lib()
+    if tc_passes == 'h16':      # fp16x3 on the persistent kernel (what the packed matcher weights use by default)
+        M, K1 = a.shape
+        K = K1 + (a2.shape[1] if a2 is not None else 0)
+        N = w.shape[0]
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        scale = 64.0
+        ws = w.double() * scale
+        w_hi = ws.to(torch.float16)
+        w_lo = (ws - w_hi.double()).to(torch.float16).contiguous()
+        w_hi = w_hi.contiguous()
+        rc = lib.mvm_linear_tc_h16(_lib.ptr(a), a.stride(0), _lib.ptr(a2), a2.stride(0) if a2 is not None else 0, K1,
+                                   _lib.ptr(w_hi), _lib.ptr(w_lo), scale, w_hi.stride(0), _lib.ptr(bias), _lib.ptr(residual),
+                                   residual.stride(0) if residual is not None else 0, _lib.ptr(out), N, M, N, K,
+                                   float(alpha), int(relu), _lib.stream_ptr())
+        _lib.check(rc, 'mvm_linear_tc_h16')
+        return out
     if tc_passes:
         M, K1 = a.shape
         K = K1 + (a2.shape[1] if a2 is not None else 0)

@@ -124,6 +124,14 @@ class PackedMatcher:
         hi = rn_tf32(flat)
         lo = rn_tf32(flat - hi)
         self.flat = torch.cat([flat, hi, lo]).to(device)
+        # half-precision planes for the fp16x3 GEMMs: hi = fp16(S w), lo = fp16(S w - hi); the power-of-two scale S lifts
+        # the lo plane out of the fp16 subnormals (|w| ~ 0.06 -> |lo| ~ 2e-5 unscaled) and is divided out in the epilogue
+        self.w16_scale = 64.0
+        assert float(flat.abs().max()) * self.w16_scale < 6.0e4, 'weight magnitude exceeds the fp16 range of the fp16x3 GEMM planes'
+        scaled = flat.double() * self.w16_scale
+        h16 = scaled.to(torch.float16)
+        l16 = (scaled - h16.double()).to(torch.float16)
+        self.flat16 = torch.cat([h16, l16]).to(device)
         self.offsets = offsets
         base = self.flat.data_ptr()
 
@@ -151,6 +159,10 @@ class PackedMatcher:
                       'conf_wc1', 'conf_bc1', 'conf_wl'):
                 setattr(W, f, P(f))
             W.conf_bl = conf_bl
+        W.flat_base = base
+        W.w16_hi = self.flat16.data_ptr()
+        W.w16_lo = self.flat16.data_ptr() + 2 * off
+        W.w16_scale = self.w16_scale
         self.struct = W
         self.n_layers = len(layer_names)
         self.has_conf = bool(conf_mlp)

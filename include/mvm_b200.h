@@ -64,6 +64,12 @@ typedef struct mvm_matcher_weights {
   const float* conf_wc0; const float* conf_bc0; /* [256] each: layers_c.0 (1->256, +BN) */
   const float* conf_wc1; const float* conf_bc1; /* [256,256] layers_c.3 (+BN) */
   const float* conf_wl;  float conf_bl;         /* [256], scalar: layers.0 */
+  /* fp16x3 GEMMs (optional; NULL = tf32x3): half-precision hi / lo planes of w16_scale * (the whole flat weight buffer
+   * starting at flat_base), element for element; w16_scale is a power of two that lifts the lo plane out of the fp16
+   * subnormals (packing.py uses 64) */
+  const float* flat_base;
+  const void* w16_hi; const void* w16_lo;
+  float w16_scale;
 } mvm_matcher_weights;
 
 /* Outputs of one view pair (a < b), batch-major, exactly the tensors the reference returns
@@ -111,6 +117,7 @@ typedef struct mvm_matcher_options {
   int sinkhorn_variant; /* 0 = automatic (see mvm_log_optimal_transport_ex) */
   int attention_split;  /* math mode 3: operand planes of attention, 0 = tf32 hi/lo (3 x kind::tf32), 1 = fp16 hi/lo
                          * (3 x kind::f16: same 22-bit operands, half the tensor-pipe time) */
+  int gemm_split;       /* the same choice for the 1x1-conv GEMMs (1 needs mvm_matcher_weights.w16_*) */
 } mvm_matcher_options;
 void mvm_matcher_options_default(mvm_matcher_options* opt);
 int mvm_matcher_forward_ex(const mvm_matcher_weights* w, int batch, int n_views, int n_pad,
@@ -141,6 +148,12 @@ int mvm_linear_tc(const float* A, int lda, const float* A2, int lda2, int K1, co
 int mvm_linear_tc_presplit(const float* A, int lda, const float* A2, int lda2, int K1, const float* W_hi,
                            const float* W_lo, int ldw, const float* bias, const float* R, int ldr, float* C,
                            int ldc, int M, int N, int K, float alpha, int relu, void* stream);
+
+/* fp16x3 on the persistent kernel: W16_hi / W16_lo = fp16 planes of wscale * W (hi = fp16(wscale W), lo = fp16(wscale W - hi));
+ * K and K1 multiples of 64, N of 128. */
+int mvm_linear_tc_h16(const float* A, int lda, const float* A2, int lda2, int K1, const void* W16_hi, const void* W16_lo,
+                      float wscale, int ldw, const float* bias, const float* R, int ldr, float* C, int ldc, int M, int N, int K,
+                      float alpha, int relu, void* stream);
 
 /* Math mode of the matcher's GEMMs/attention inside mvm_matcher_forward: 0 = fp32 CUDA cores,
  * 3 = tcgen05 3xTF32 (fp32-faithful), 1 = tcgen05 single-pass TF32 (torch 1.10's Ampere default). */
@@ -349,6 +362,7 @@ void mvm_debug_set_score_kernel(int tensor_cores);      /* default of mvm_matche
 void mvm_debug_set_gemm_tile(int bn);                   /* default of .gemm_tile (128 | 256) */
 void mvm_debug_set_gemm_kernel(int persistent);         /* default of .gemm_kernel */
 void mvm_debug_set_attention_split(int fp16);           /* default of .attention_split */
+void mvm_debug_set_gemm_split(int fp16);                /* default of .gemm_split */
 /* clock64 phase traces of CTA 0 (device buffers of 8 / 6 / 8 long long; NULL switches the trace off) */
 void mvm_debug_set_attention_timing(long long* buf);
 void mvm_debug_set_sinkhorn_timing(long long* buf);

@@ -25,4 +25,5 @@ def _default_math_mode(request):
         pkg.set_math_mode(3)
         from e2e_multi_view_matching_b200 import _lib
         _lib.lib().mvm_debug_set_attention_split(1)
+        _lib.lib().mvm_debug_set_gemm_split(1)
     yield

@@ -51,3 +51,46 @@ def test_matcher_h3_vs_reference_golden(name):
     rep = compare_matcher_outputs(ref, got, tau=2e-3, score_tol=score_tol_for(name), min_stable=0.0 if name == 'pair_flat' else 0.9)
     rep0 = compare_matcher_outputs(ref, base, tau=2e-3, score_tol=score_tol_for(name))
     print(name, 'fp16x3', rep, 'tf32x3 max_score_err', rep0['max_score_err'])
+
+
+@pytest.mark.parametrize('shape', [(300, 256, 128, 0), (1024, 768, 256, 0), (130, 512, 256, 256), (4096, 256, 512, 0)])
+def test_linear_h16_vs_fp64(shape):
+    """fp16x3 GEMM (persistent kernel, half-precision W planes pre-scaled by 64, A split on chip) against fp64, and
+    against the tf32x3 kernel on the same operands."""
+    from e2e_multi_view_matching_b200 import ops
+    M, N, K1, K2 = shape
+    g = torch.Generator().manual_seed(M + N)
+    a = (torch.randn(M, K1, generator=g) * 3).cuda()
+    a2 = (torch.randn(M, K2, generator=g) * 3).cuda() if K2 else None
+    w = (torch.randn(N, K1 + K2, generator=g) / 16).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    r = torch.randn(M, N, generator=g).cuda()
+    A = torch.cat([a, a2], 1) if a2 is not None else a
+    ref = torch.relu(A.double() @ w.double().T + b.double()) + r.double()
+    out = ops.linear(a, w, bias=b, a2=a2, residual=r, relu=True, tc_passes='h16')
+    t32 = ops.linear(a, w, bias=b, a2=a2, residual=r, relu=True, tc_passes=3, presplit=True)
+    e_h, e_t = (out.double() - ref).abs().max().item(), (t32.double() - ref).abs().max().item()
+    assert e_h < max(1e-4, 2.0 * e_t), (shape, e_h, e_t)
+
+
+@pytest.mark.parametrize('name', ['pair_18l_128', 'mv5_28l_96_sharp', 'mv4_ragged_sharp'])
+def test_matcher_gemm_split_ab(name):
+    """Whole matcher with the GEMMs in fp16x3 (default) and in tf32x3: both within the golden tolerance, and close to
+    each other."""
+    import e2e_multi_view_matching_b200 as pkg
+    from e2e_multi_view_matching_b200 import _lib
+    from tests.test_matcher_gpu import run_ours
+    lib = _lib.lib()
+    meta, ref = load_case(name)
+    sd, data = case_inputs(meta)
+    pkg.set_math_mode(3)
+    try:
+        lib.mvm_debug_set_gemm_split(1)
+        got = run_ours(meta, sd, data)
+        lib.mvm_debug_set_gemm_split(0)
+        base = run_ours(meta, sd, data)
+    finally:
+        lib.mvm_debug_set_gemm_split(1)
+    rep = compare_matcher_outputs(ref, got, tau=2e-3, score_tol=score_tol_for(name), min_stable=0.9)
+    rep0 = compare_matcher_outputs(ref, base, tau=2e-3, score_tol=score_tol_for(name), min_stable=0.9)
+    print(name, 'gemm fp16x3', rep['max_score_err'], 'gemm tf32x3', rep0['max_score_err'])

@@ -72,7 +72,9 @@ def test_attention_tc_vs_simt(cfg, passes):
 def test_gemm_kernel_variants_bit_identical():
     """The persistent kernel (A operand split into tensor memory, 128-column tiles, TMA-store epilogue) and the
     one-tile-per-CTA kernel with 128- or 256-column tiles accumulate over K in the same order with the same three
-    passes, so the whole matcher must produce bit-identical outputs with any of them."""
+    passes, so the whole matcher must produce bit-identical outputs with any of them (operand split 0 = tf32 hi/lo
+    in all three; the persistent kernel's default fp16 hi/lo planes are a different rounding, covered by
+    tests/test_h3_gpu.py::test_matcher_gemm_split_ab)."""
     import e2e_multi_view_matching_b200 as pkg
     from e2e_multi_view_matching_b200 import _lib
     from tests.test_matcher_gpu import run_ours
@@ -83,6 +85,7 @@ def test_gemm_kernel_variants_bit_identical():
     outs = []
     try:
         lib.mvm_debug_set_score_kernel(0)       # same (fp32 CUDA-core) score GEMM for every variant
+        lib.mvm_debug_set_gemm_split(0)
         for persist, tile in ((1, 256), (0, 128), (0, 256)):
             lib.mvm_debug_set_gemm_kernel(persist)
             lib.mvm_debug_set_gemm_tile(tile)
@@ -92,6 +95,7 @@ def test_gemm_kernel_variants_bit_identical():
         lib.mvm_debug_set_gemm_kernel(1)
         lib.mvm_debug_set_gemm_tile(256)
         lib.mvm_debug_set_score_kernel(1)
+        lib.mvm_debug_set_gemm_split(1)
     for other in outs[1:]:
         for k in outs[0]:
             assert np.array_equal(outs[0][k], other[k]), k
