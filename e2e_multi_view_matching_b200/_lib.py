@@ -86,7 +86,7 @@ def lib():
         C.c_float, C.c_float, C.c_int, C.c_float, C.POINTER(PairIO), C.c_int, _fp, C.c_size_t,
         C.POINTER(MatcherOptions), _fp]
     for name in ('mvm_debug_set_score_kernel', 'mvm_debug_set_gemm_tile', 'mvm_debug_set_gemm_kernel',
-                 'mvm_debug_set_attention_split', 'mvm_debug_set_gemm_split'):
+                 'mvm_debug_set_attention_split', 'mvm_debug_set_gemm_split', 'mvm_debug_set_attention_h3_variant'):
         getattr(L, name).restype = None
         getattr(L, name).argtypes = [C.c_int]
     for name in ('mvm_debug_set_attention_timing', 'mvm_debug_set_sinkhorn_timing', 'mvm_debug_set_mvba_timing'):

@@ -27,6 +27,9 @@
 #include <cuda_fp16.h>
 
 extern long long* g_attn_dbg;   // attention_tc.cu (mvm_debug_set_attention_timing)
+// 0 = two softmax groups, one CTA per SM; 1 = one softmax group, two CTAs per SM (attention_h3s_kernel)
+int g_attn_h3_variant = 1;
+extern "C" void mvm_debug_set_attention_h3_variant(int v) { g_attn_h3_variant = v ? 1 : 0; }
 
 namespace {
 
@@ -94,6 +97,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+
+// 32 lanes x 8 columns load / store (the rare accumulator rescale of the two-CTA kernel: few live registers)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 
 __global__ void __launch_bounds__(HCfg::NTHREADS, 1)
@@ -480,6 +498,343 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   if (threadIdx.x == 32) cmark(7);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Two CTAs per SM, one softmax group each ("h3s").  The two-group kernel above keeps the tensor pipe busy inside the
+// key-tile loop, but every CTA pays ~14 k cycles outside it (barrier / TMEM set-up, Q load, pipeline fill, merge of
+// the two partial softmaxes, output store, CTA launch gap; clock trace profiles/r02_attn_timing_h3.txt) with the SM
+// idle: 18 % of a cross-attention CTA, 47 % of a self-attention CTA (16 key tiles).  Here a CTA is HALF of that
+// machine -- one softmax warpgroup, a 3-deep K/V ring (96 KB), 256 tensor-memory columns -- so two CTAs are resident
+// per SM and the set-up / drain of one runs under the key-tile loop of the other.  All key tiles of the query block
+// go through the one group, so there is no merge: out = O / l.
+// TMEM columns: S [0,64)  O [64,128)  Q_hi [128,160)  Q_lo [160,192)  P hi|lo [192,256).
+struct SCfg {
+  static constexpr int ST = 3;
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + ST * K_BYTES * 2;
+  static constexpr int OFF_BAR = OFF_V + ST * V_BYTES * 2;
+  static constexpr int OFF_TAB = OFF_BAR + 256;         // tile table: int [3][MAX_TILES]
+  static constexpr int MAX_TILES = HCfg::MAX_TILES;
+  static constexpr int SMEM_BYTES = OFF_TAB + 3 * MAX_TILES * 4 + 1024;
+  static constexpr int NTHREADS = 224;                  // producer, two MMA issuers, four softmax warps
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int OUT_LD = HD + 4;                 // output staging row (floats): conflict-free float4 rows
+};
+static_assert(2 * (SCfg::SMEM_BYTES + 1024) <= 227 * 1024, "two CTAs per SM");
+static_assert(BQ * SCfg::OUT_LD * 4 <= SCfg::ST * K_BYTES * 2, "output staging fits in the K ring");
+
+__global__ void __launch_bounds__(SCfg::NTHREADS, 2)
+attention_h3s_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo, AttnH3Args g) {
+  using C_ = SCfg;
+  constexpr int ST = C_::ST;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::OFF_BAR);
+  uint64_t* q_ready = bars + 0;             // Q rows stored to tensor memory (128 arrivals)
+  uint64_t* k_full = bars + 1;              // [ST]
+  uint64_t* k_empty = k_full + ST;          // [ST]
+  uint64_t* v_full = k_empty + ST;          // [ST]
+  uint64_t* v_empty = v_full + ST;          // [ST]
+  uint64_t* s_full = v_empty + ST;          // S(j) landed in TMEM
+  uint64_t* s_free = s_full + 1;            // S(j) read into registers (128 arrivals)
+  uint64_t* p_ready = s_free + 1;           // keys 0-31 of P(j) stored (128 arrivals)
+  uint64_t* p_ready_b = p_ready + 1;        // keys 32-63 of P(j) stored
+  uint64_t* o_full = p_ready_b + 1;         // P.V(j) landed in the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  static_assert((1 + 4 * ST + 5 + 1) * 8 <= 256, "barrier area");
+  int* s_krow = reinterpret_cast<int*>(smem + C_::OFF_TAB);
+  int* s_vrow = s_krow + C_::MAX_TILES;
+  int* s_vk0 = s_vrow + C_::MAX_TILES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  auto cmark = [&](int slot) {
+    if (g.dbg != nullptr && cta_lin < 2048) g.dbg[64 * 16 + cta_lin * 8 + slot] = clock64();
+  };
+  if (threadIdx.x == 0 && g.dbg != nullptr && cta_lin < 2048) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g.dbg[64 * 16 + cta_lin * 8 + 0] = smid;
+    cmark(1);
+  }
+  const int q0 = blockIdx.x * BQ;
+  const int h = blockIdx.y;
+  const int v = blockIdx.z;
+  const int T = g.segs.n_views;
+  const int t = v % T, b = v / T;
+  if (q0 >= g.segs.counts[t]) return;
+
+  // the softmax threads own the Q rows: global loads first, their latency runs under the set-up
+  float qr[HD];
+  if (warp >= 3) {
+    const int qrow = (warp & 3) * 32 + lane;
+    const float4* qg = reinterpret_cast<const float4*>(g.qkv + ((long long)v * g.n_pad + q0 + qrow) * 768 + h * HD);
+    const bool in_range = (long long)v * g.n_pad + q0 + qrow < (long long)gridDim.z * g.n_pad;
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) {
+      const float4 x = in_range ? __ldg(qg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      qr[4 * i] = x.x; qr[4 * i + 1] = x.y; qr[4 * i + 2] = x.z; qr[4 * i + 3] = x.w;
+    }
+  }
+
+  // tile table (see attention_h3_kernel): key segments (views) in ascending order, 64 keys per tile
+  int nt = 0;
+  for (int s = 0; s < T; ++s) {
+    if (g.is_cross ? (s == t) : (s != t)) continue;
+    nt += (g.segs.counts[s] + BKV - 1) / BKV;
+  }
+  for (int j = threadIdx.x; j < nt; j += C_::NTHREADS) {
+    int acc = 0, seg = 0, k0 = 0;
+    for (int s = 0; s < T; ++s) {
+      if (g.is_cross ? (s == t) : (s != t)) continue;
+      const int n = (g.segs.counts[s] + BKV - 1) / BKV;
+      if (j < acc + n) { seg = s; k0 = (j - acc) * BKV; break; }
+      acc += n;
+    }
+    s_krow[j] = (b * T + seg) * g.n_pad + k0;
+    s_vrow[j] = (b * T + seg) * 256 + h * HD;
+    s_vk0[j] = k0;
+  }
+
+  auto sK = [&](int s) { return smem + C_::OFF_K + s * K_BYTES * 2; };
+  auto sV = [&](int s) { return smem + C_::OFF_V + s * V_BYTES * 2; };
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(q_ready, 128);
+    for (int i = 0; i < ST; ++i) {
+      tc::mbar_init(k_full + i, 1); tc::mbar_init(k_empty + i, 1);
+      tc::mbar_init(v_full + i, 1); tc::mbar_init(v_empty + i, 1);
+    }
+    tc::mbar_init(s_full, 1); tc::mbar_init(s_free, 128);
+    tc::mbar_init(p_ready, 128); tc::mbar_init(p_ready_b, 128);
+    tc::mbar_init(o_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
+    tc::prefetch_tmap(&tmKlo); tc::prefetch_tmap(&tmVlo);
+  }
+  if (warp == 1) tc::tmem_alloc<C_::TMEM_COLS>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (threadIdx.x == 0) cmark(2);
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
+  const uint32_t tmem_Q = tmem_base + 128, tmem_Qlo = tmem_base + 160, tmem_P = tmem_base + 192;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    auto load_K = [&](int j) {
+      const int s = j % ST;
+      tc::mbar_wait(k_empty + s, ((j / ST) & 1) ^ 1);
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(k_full + s, K_BYTES * 2);
+        const int krow = s_krow[j];
+        tc::tma_load_2d(sK(s), &tmK, k_full + s, h * HD, krow);
+        tc::tma_load_2d(sK(s) + K_BYTES, &tmKlo, k_full + s, h * HD, krow);
+      }
+      __syncwarp();
+    };
+    auto load_V = [&](int j) {
+      const int s = j % ST;
+      tc::mbar_wait(v_empty + s, ((j / ST) & 1) ^ 1);
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(v_full + s, V_BYTES * 2);
+        const int vrow = s_vrow[j], k0 = s_vk0[j];
+        tc::tma_load_2d(sV(s), &tmV, v_full + s, k0, vrow);
+        tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, k0, vrow);
+      }
+      __syncwarp();
+    };
+    load_K(0);
+    for (int j = 0; j < nt; ++j) {
+      load_V(j);
+      if (j + 1 < nt) load_K(j + 1);
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer 1: S = Q K^T ===========================
+    constexpr uint32_t idesc = make_idesc_f16(BQ, BKV);
+    tc::mbar_wait(q_ready, 0);
+    tc::tc_fence_after();
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % ST;
+      tc::mbar_wait(k_full + s, (j / ST) & 1);
+      if (j >= 1) tc::mbar_wait(s_free, (j - 1) & 1);           // S(j-1) is in the softmax threads' registers
+      tc::tc_fence_after();
+      const uint32_t k_hi = tc::smem_u32(sK(s)), k_lo = k_hi + K_BYTES;
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint64_t dk = tc::make_kmajor_sw128_desc(k_hi + kk * 32);
+          umma_f16_ts(tmem_S, tmem_Q + kk * 8, dk, idesc, kk != 0);
+          umma_f16_ts(tmem_S, tmem_Q + kk * 8, tc::make_kmajor_sw128_desc(k_lo + kk * 32), idesc, 1);
+          umma_f16_ts(tmem_S, tmem_Qlo + kk * 8, dk, idesc, 1);
+        }
+        tc::umma_commit(s_full);
+        tc::umma_commit(k_empty + s);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    // =========================== MMA issuer 2: O += P V ===========================
+    constexpr uint32_t idesc = make_idesc_f16(BQ, HD);
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % ST;
+      tc::mbar_wait(p_ready, j & 1);
+      tc::mbar_wait(v_full + s, (j / ST) & 1);
+      tc::tc_fence_after();
+      const uint32_t v_hi = tc::smem_u32(sV(s)), v_lo = v_hi + V_BYTES;
+      const uint32_t p_hi = tmem_P, p_lo = tmem_P + 32;
+      auto issue_PV = [&](int kk0) {
+#pragma unroll
+        for (int kk = kk0; kk < kk0 + 2; ++kk) {
+          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + kk * 32);
+          umma_f16_ts(tmem_O, p_hi + kk * 8, dv, idesc, (j | kk) != 0);
+          umma_f16_ts(tmem_O, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + kk * 32), idesc, 1);
+          umma_f16_ts(tmem_O, p_lo + kk * 8, dv, idesc, 1);
+        }
+      };
+      if (tc::elect_one()) issue_PV(0);
+      __syncwarp();
+      tc::mbar_wait(p_ready_b, j & 1);
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        issue_PV(2);
+        tc::umma_commit(o_full);
+        tc::umma_commit(v_empty + s);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== softmax (one warpgroup, every key tile) ===========================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    {
+      uint32_t qh[32], ql[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) split_pack(qr[2 * i], qr[2 * i + 1], qh[i], ql[i]);
+      tmem_st16(tmem_Q + lane_addr, qh);
+      tmem_st16(tmem_Q + lane_addr + 16, qh + 16);
+      tmem_st16(tmem_Qlo + lane_addr, ql);
+      tmem_st16(tmem_Qlo + lane_addr + 16, ql + 16);
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(q_ready);
+      if (warp == 3 && lane == 0) cmark(3);
+    }
+    float m_ref = -INFINITY, l_run = 0.f;
+    const float scale_l2e = 0.125f * 1.4426950408889634f;
+    int j = 0;
+    for (int sg = 0; sg < T; ++sg) {
+      if (g.is_cross ? (sg == t) : (sg != t)) continue;
+      const int cnt = g.segs.counts[sg];
+      for (int k0 = 0; k0 < cnt; k0 += BKV, ++j) {
+        const int nvalid = cnt - k0;
+        tc::mbar_wait(s_full, j & 1);
+        tc::tc_fence_after();
+        if (warp == 3 && lane == 0 && j == 0) cmark(4);
+        float s[BKV];
+        tc::tmem_ld32(tmem_S + lane_addr, s);
+        tc::tmem_ld32(tmem_S + lane_addr + 32, s + 32);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(s_free);                 // Q K^T of tile j + 1 may overwrite S
+        if (nvalid < BKV) {
+#pragma unroll
+          for (int i = 0; i < BKV; ++i) s[i] = (i < nvalid) ? s[i] : -INFINITY;
+        }
+        float mx4[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+        for (int i = 4; i < BKV; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], s[i]);
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_l2e;
+        const bool grow = mx > m_ref + 8.f;
+        bool o_waited = false;
+        if (__any_sync(0xffffffffu, grow)) {
+          float f = 1.f;
+          if (grow) { f = ex2_ftz(m_ref - mx); m_ref = mx; l_run *= f; }
+          if (j > 0) {
+            tc::mbar_wait(o_full, (j - 1) & 1);   // P.V(j-1) has landed: the accumulator may be rescaled
+            tc::tc_fence_after();
+            o_waited = true;
+            // eight columns at a time: the S row stays in registers (this path is rare -- first tiles of a row)
+#pragma unroll 1
+            for (int c = 0; c < HD; c += 8) {
+              float o[8];
+              tmem_ld8(tmem_O + lane_addr + c, o);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] *= f;
+              tmem_st8(tmem_O + lane_addr + c, o);
+            }
+            tc::tmem_st_wait();
+          }
+        }
+        const float nm = -m_ref;
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ph[16], pl[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_ftz(fmaf(s[c * 32 + 2 * i], scale_l2e, nm));
+            const float p1 = ex2_ftz(fmaf(s[c * 32 + 2 * i + 1], scale_l2e, nm));
+            rs4[i & 1] += p0;
+            rs4[2 + (i & 1)] += p1;
+            split_pack(p0, p1, ph[i], pl[i]);
+          }
+          if (c == 0 && j > 0 && !o_waited) {
+            // P(j) overwrites the planes P.V(j-1) reads: wait for that product as late as possible
+            tc::mbar_wait(o_full, (j - 1) & 1);
+            tc::tc_fence_after();
+          }
+          tmem_st16(tmem_P + lane_addr + c * 16, ph);
+          tmem_st16(tmem_P + lane_addr + 32 + c * 16, pl);
+          tc::tmem_st_wait();
+          tc::tc_fence_before();
+          tc::mbar_arrive(c == 0 ? p_ready : p_ready_b);
+        }
+        l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      }
+    }
+    // ---- out = O / l, staged through the (now idle) K ring so that the global stores are full 256-byte rows
+    if (j > 0) {
+      tc::mbar_wait(o_full, (j - 1) & 1);
+      tc::tc_fence_after();
+    }
+    if (warp == 3 && lane == 0) cmark(5);
+    const float inv = 1.f / l_run;
+    float* stage = reinterpret_cast<float*>(smem + C_::OFF_K);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float o[32];
+      tc::tmem_ld32(tmem_O + lane_addr + c * 32, o);
+      tc::tmem_ld_wait();
+      float4* d4 = reinterpret_cast<float4*>(stage + row * C_::OUT_LD + c * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d4[i] = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+    }
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    // warp q writes rows [32 q, 32 q + 32): one instruction = two rows of 64 floats
+    const int sub = lane >> 4, c4 = lane & 15;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int r = q * 32 + 2 * i + sub;
+      if (q0 + r < g.n_pad) {
+        const float4 x = *reinterpret_cast<const float4*>(stage + r * C_::OUT_LD + c4 * 4);
+        *reinterpret_cast<float4*>(g.out + ((long long)v * g.n_pad + q0 + r) * 256 + h * HD + c4 * 4) = x;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) cmark(6);
+  if (warp == 1) tc::tmem_dealloc<C_::TMEM_COLS>(tmem_base);
+  if (threadIdx.x == 32) cmark(7);
+}
+
 }  // namespace
 
 // K / V^T planes in half precision: kh, kl [rows, 256]; vth, vtl [V * 256, n_pad] (written by the QKV GEMM epilogue)
@@ -505,6 +860,14 @@ int launch_attention_h3(const float* qkv, const __half* kh, const __half* kl, co
   AttnH3Args g;
   g.qkv = qkv; g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross; g.dbg = g_attn_dbg;
   dim3 grid(mvm_div_up(n_pad, BQ), 4, V);
+  if (g_attn_h3_variant == 1) {
+    mvm_once_per_device(MVM_ONCE_ATTN_H3S, [&] {
+      cudaFuncSetAttribute(attention_h3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg::SMEM_BYTES);
+    });
+    attention_h3s_kernel<<<grid, SCfg::NTHREADS, SCfg::SMEM_BYTES, stream>>>(*tK, *tV, *tKlo, *tVlo, g);
+    MVM_CHECK_LAUNCH();
+    return MVM_OK;
+  }
   attention_h3_kernel<<<grid, C_::NTHREADS, C_::SMEM_BYTES, stream>>>(*tK, *tV, *tKlo, *tVlo, g);
   MVM_CHECK_LAUNCH();
   return MVM_OK;

@@ -362,6 +362,8 @@ void mvm_debug_set_score_kernel(int tensor_cores);      /* default of mvm_matche
 void mvm_debug_set_gemm_tile(int bn);                   /* default of .gemm_tile (128 | 256) */
 void mvm_debug_set_gemm_kernel(int persistent);         /* default of .gemm_kernel */
 void mvm_debug_set_attention_split(int fp16);           /* default of .attention_split */
+void mvm_debug_set_attention_h3_variant(int v);         /* fp16-plane attention kernel: 1 = one softmax group, two CTAs per SM
+                                                          (default), 0 = two softmax groups, one CTA per SM (A/B comparison) */
 void mvm_debug_set_gemm_split(int fp16);                /* default of .gemm_split */
 /* clock64 phase traces of CTA 0 (device buffers of 8 / 6 / 8 long long; NULL switches the trace off) */
 void mvm_debug_set_attention_timing(long long* buf);

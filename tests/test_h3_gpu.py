@@ -13,9 +13,21 @@ from tests.util import GOLDEN, MATCHER_CASES, load_case, case_inputs, compare_ma
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('cfg', [(1, 2, 128, [128, 128]), (2, 3, 192, [100, 192, 77]), (1, 5, 256, [256] * 5)])
+@pytest.fixture(params=[1, 0], ids=['two_ctas_per_sm', 'two_groups_one_cta'])
+def h3_variant(request):
+    """Both fp16-plane kernels of attention_h3.cu: one softmax group with two CTAs per SM (default), and the
+    two-group one-CTA-per-SM kernel kept for A/B."""
+    from e2e_multi_view_matching_b200 import _lib
+    lib = _lib.lib()
+    lib.mvm_debug_set_attention_h3_variant(request.param)
+    yield request.param
+    lib.mvm_debug_set_attention_h3_variant(1)
+
+
+@pytest.mark.parametrize('cfg', [(1, 2, 128, [128, 128]), (2, 3, 192, [100, 192, 77]), (1, 5, 256, [256] * 5),
+                                 (3, 4, 1024, [1024, 1000, 1024, 65])])
 @pytest.mark.parametrize('scale', [1.0, 6.0])
-def test_attention_h3_vs_fp32(cfg, scale):
+def test_attention_h3_vs_fp32(cfg, scale, h3_variant):
     from e2e_multi_view_matching_b200 import ops
     B, T, n_pad, counts = cfg
     g = torch.Generator().manual_seed(n_pad + T)
@@ -33,7 +45,7 @@ def test_attention_h3_vs_fp32(cfg, scale):
 
 
 @pytest.mark.parametrize('name', MATCHER_CASES)
-def test_matcher_h3_vs_reference_golden(name):
+def test_matcher_h3_vs_reference_golden(name, h3_variant):
     import e2e_multi_view_matching_b200 as pkg
     from e2e_multi_view_matching_b200 import _lib
     from tests.test_matcher_gpu import run_ours
