@@ -219,7 +219,10 @@ int mvm_matcher_forward_ex(const mvm_matcher_weights* w, int batch, int n_views,
       HalfPlanes hp = {kh, kh + (size_t)rows * 256, vth, vth + (size_t)rows * 256};
       GemmDesc gq = make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0);
       set_planes(cx, gq);
-      MVM_TRY(launch_gemm_tc_persist(gq, nullptr, 512, n_pad, nullptr, nullptr, s, &hp));
+      {
+        MvmProfScope prof__(MVM_TAG_GEMM, s);      // (launch_gemm_tc opens the scope on the other paths)
+        MVM_TRY(launch_gemm_tc_persist(gq, nullptr, 512, n_pad, nullptr, nullptr, s, &hp));
+      }
       MVM_TRY(launch_attention_h3(ws.QKV, (const __half*)hp.kh, (const __half*)hp.kl, (const __half*)hp.vth,
                                   (const __half*)hp.vtl, ws.MSG, batch, n_pad, segs, L.is_cross, s));
     } else if (cx.math_mode != 0) {

@@ -32,6 +32,17 @@ class MultiViewPoseEngine:
         self.min_inliers = min_inliers
         self._ws = None
 
+    def _pair_index(self, pair_ids, dev):
+        """Device index tensors (view a / view b of every pair), built once per pair list: indexing with a Python
+        list would stage a pageable host->device copy every call, which blocks the host until the matcher's
+        kernels have drained (measured: host enqueue time == GPU step time, tools/step_gaps.py)."""
+        key = (tuple(pair_ids), str(dev))
+        if getattr(self, '_pair_index_key', None) != key:
+            self._pair_index_val = (torch.tensor([a for a, _ in pair_ids], dtype=torch.int64, device=dev),
+                                    torch.tensor([b for _, b in pair_ids], dtype=torch.int64, device=dev))
+            self._pair_index_key = key
+        return self._pair_index_val
+
     def run(self, state, intr, global_ba=True):
         """state: MatcherEngine.last of the matcher call; intr: list (per view) of [B,3,3]/[B,4,4]
         intrinsics.  Returns dict with pairwise poses and (if global_ba) absolute extrinsics."""
@@ -52,8 +63,9 @@ class MultiViewPoseEngine:
                                               _lib.ptr(mk0), _lib.ptr(mk1), _lib.ptr(mconf), _lib.ptr(n_valid), sp),
                        'mvm_gather_matches')
             i4 = torch.stack([_intr4(k.to(dev)) for k in intr], 1)                    # [B,T,4]
-            ia = i4[:, [a for a, _ in pair_ids]].contiguous()                         # [B,P,4]
-            ib = i4[:, [b for _, b in pair_ids]].contiguous()
+            ia_idx, ib_idx = self._pair_index(pair_ids, dev)
+            ia = i4.index_select(1, ia_idx)                                           # [B,P,4]
+            ib = i4.index_select(1, ib_idx)
             BP = B * P
             T_w8 = torch.empty(B, P, 4, 4, **f32)
             k0n = torch.empty(B, P, n_pad, 2, **f32)
