@@ -116,7 +116,8 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
 
 __global__ void __launch_bounds__(HCfg::NTHREADS, 1)
 attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                    const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo, AttnH3Args g) {
+                    const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo,
+                    const __grid_constant__ AttnH3Args g) {
   using C_ = HCfg;
   constexpr int ST = C_::ST;
   extern __shared__ uint8_t smem_raw[];
@@ -525,7 +526,8 @@ static_assert(BQ * SCfg::OUT_LD * 4 <= SCfg::ST * K_BYTES * 2, "output staging f
 
 __global__ void __launch_bounds__(SCfg::NTHREADS, 2)
 attention_h3s_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                     const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo, AttnH3Args g) {
+                     const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo,
+                    const __grid_constant__ AttnH3Args g) {
   using C_ = SCfg;
   constexpr int ST = C_::ST;
   extern __shared__ uint8_t smem_raw[];

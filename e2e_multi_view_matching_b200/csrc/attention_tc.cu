@@ -77,7 +77,8 @@ __device__ __forceinline__ float tf32_hi(float x) {
 template <int NPASS>
 __global__ void __launch_bounds__(ACfg<NPASS>::NTHREADS, ACfg<NPASS>::MIN_CTAS)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                    const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo, AttnTcArgs g) {
+                    const __grid_constant__ CUtensorMap tmKlo, const __grid_constant__ CUtensorMap tmVlo,
+                    const __grid_constant__ AttnTcArgs g) {
   using C_ = ACfg<NPASS>;
   constexpr int ST = C_::ST;
   extern __shared__ uint8_t smem_raw[];

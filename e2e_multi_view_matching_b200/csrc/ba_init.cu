@@ -49,7 +49,7 @@ __device__ inline void aa_mul(const double* a, const double* b, double* out) {
 
 __device__ inline double wsum(double v) { return warp_sum_d(v); }
 
-__global__ void __launch_bounds__(32) ba_init_kernel(BaInitArgs g) {
+__global__ void __launch_bounds__(32) ba_init_kernel(const __grid_constant__ BaInitArgs g) {
   __shared__ double rot[MV][3], prot[ME][3], ppos[ME][3], dirs[ME][3], cpos[MV][3], cprev[MV][3];
   __shared__ int ei[ME], ej[ME];
   __shared__ double GJ[(MV - 1) * 2 * (MV - 1)], Linv[(MV - 1) * (MV - 1)];

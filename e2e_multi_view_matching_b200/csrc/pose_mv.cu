@@ -119,7 +119,7 @@ struct TreeArgs {
   unsigned char* on_tree;        // [B,P] or null
 };
 
-__global__ void spanning_tree_kernel(TreeArgs t) {
+__global__ void spanning_tree_kernel(const __grid_constant__ TreeArgs t) {
   const int bi = blockIdx.x * blockDim.x + threadIdx.x;
   if (bi >= t.batch) return;
   const int T = t.n_views, P = t.n_pairs;
@@ -366,7 +366,7 @@ __device__ __forceinline__ void wacc(double* dst, double v, int lane) {
   if (lane == 0) *dst += v;
 }
 
-__global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
+__global__ void __launch_bounds__(NT) mvba_kernel(const __grid_constant__ MvbaArgs g) {
   extern __shared__ double s_rec[];   // [P][NPART] all partial records of the tuple, staged once per exchange
   __shared__ double s_acc[NW][NPART];
   __shared__ double s_tot[NPART];
@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(NT) mvba_kernel(MvbaArgs g) {
 
 // cv2.triangulatePoints of every match of every (tuple, pair) with given extrinsics
 // (write_bundle_adjust_problem, bundle_adjust_io.py:219-225)
-__global__ void __launch_bounds__(NT) triangulate_pairs_kernel(MvbaArgs g, double* __restrict__ out) {
+__global__ void __launch_bounds__(NT) triangulate_pairs_kernel(const __grid_constant__ MvbaArgs g, double* __restrict__ out) {
   const int P = g.n_pairs, T = g.n_views;
   const long long prob = blockIdx.x;
   const int bi = (int)(prob / P), p = (int)(prob % P);
