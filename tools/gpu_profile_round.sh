@@ -10,7 +10,7 @@ timeout 600 python bench.py --config cfg2 --steps 10 --warmup 3 2>>$O/${TAG}_ben
 timeout 600 python bench.py --config cfg4 --steps 10 --warmup 3 2>>$O/${TAG}_bench.err | tail -1 > $O/bench_${TAG}_cfg4.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-torch-gpu > $O/${TAG}_ncu_bench.log 2>&1
-for k in attention_h3_kernel gemm_tc_persist_kernel sinkhorn_cl_kernel mvba_kernel; do
+for k in attention_h3s_kernel gemm_tc_persist_kernel sinkhorn_cl_kernel mvba_kernel ba_init_kernel; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 8 -c 2 -f -o $O/${TAG}_$k \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-torch-gpu > $O/${TAG}_ncu_$k.log 2>&1
 done
