@@ -80,6 +80,13 @@ def make_inputs(cfg, seed, batch, kpts=None):
 TF32_PEAK_TFLOPS = 148 * 4096 * 1.965e9 / 1e12      # tcgen05 kind::tf32 issue floor x SMs x max SM clock
 
 
+def emit(line):
+    """The one JSON line, on a line of its own even if another writer (NCCL_DEBUG=INFO, a warning) left stdout mid-line."""
+    sys.stdout.flush()
+    sys.stdout.write('\n' + json.dumps(line) + '\n')
+    sys.stdout.flush()
+
+
 def load_traffic(workload, batch):
     """Per-launch DRAM traffic of the dominant kernels from the committed ncu capture (profiles/ncu_traffic.json),
     valid for the workload / batch size it was captured at."""
@@ -313,7 +320,7 @@ def run_reference_arm(args, cfg, rank, world):
             'config': workload_config(cfg), 'units_per_step': 1,
             'cpu_baseline': {'value': val, 'unit': cfg['unit'], 'cores': cpu_threads(), 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': cfg['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -411,30 +418,42 @@ def main():
             sharding.all_reduce_step_loss(loss)
         return pose
 
-    # End-to-end step through the public API.  Every step's inputs come from pinned host memory: the copy of
-    # step k+1 is issued on a copy stream right after step k's kernels are enqueued (double-buffered device
-    # inputs), so it overlaps step k's compute; the step's result (poses) is read back to pinned host memory.
+    # End-to-end step through the public API.  Every step's inputs come from pinned host memory into one of two
+    # PERSISTENT device input sets (allocated once: a per-step allocation on the copy stream made the caching
+    # allocator grow and synchronise, 30-70 ms hiccups in the cfg2 / cfg4 e2e steps of r02_v10): the copy of step
+    # k+1 is issued on a copy stream right after step k's kernels are enqueued, so it overlaps step k's compute; a
+    # set is overwritten only after the step that read it has finished (event on the compute stream); the step's
+    # result (poses) is read back to pinned host memory.
     copy_stream = torch.cuda.Stream(device=dev)
+    dev_in = [{k: torch.empty_like(host[k], device=dev) for k in h2d_keys} for _ in range(2)]
+    consumed = [None, None]          # compute-stream event: the last step that read this set has been enqueued
     staged = {}
+    e2e_count = [0]
 
-    def stage_inputs():
+    def stage_inputs(slot):
         with torch.cuda.stream(copy_stream):
-            d = {k: host[k].to(dev, non_blocking=True) for k in h2d_keys}
+            if consumed[slot] is not None:
+                copy_stream.wait_event(consumed[slot])
+            for k in h2d_keys:
+                dev_in[slot][k].copy_(host[k], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        staged['d'], staged['ev'] = d, ev
+        staged[slot] = ev
 
     def step_e2e():
-        if 'd' not in staged:
-            stage_inputs()
-        d, ev = staged.pop('d'), staged.pop('ev')
-        torch.cuda.current_stream().wait_event(ev)
-        for t in d.values():
-            t.record_stream(torch.cuda.current_stream())
+        slot = e2e_count[0] % 2
+        e2e_count[0] += 1
+        if slot not in staged:
+            stage_inputs(slot)
+        torch.cuda.current_stream().wait_event(staged.pop(slot))
+        d = dict(dev_in[slot])
         d.update(meta)
         d['ids'] = data_np['ids']
         res, pose = pipe(d)
-        stage_inputs()                               # next step's H2D, overlapped with this step's kernels
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        consumed[slot] = done
+        stage_inputs(1 - slot)                       # next step's H2D, overlapped with this step's kernels
         for k, v in out_host.items():
             v.copy_(pose[k], non_blocking=True)
         if world > 1:
@@ -607,7 +626,7 @@ def main():
                 line['pose_auc_parity'] = pose_auc_parity(cfg, model, sd, dev)
             except Exception as e:
                 line['pose_auc_parity'] = {'error': repr(e)[:300]}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

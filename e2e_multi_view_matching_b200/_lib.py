@@ -78,6 +78,9 @@ def lib():
     L.mvm_matcher_forward.argtypes = [
         C.POINTER(MatcherWeights), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _fp, _fp, _fp,
         C.c_float, C.c_float, C.c_int, C.c_float, C.POINTER(PairIO), C.c_int, _fp, C.c_size_t, _fp]
+    L.mvm_pack_views.restype = C.c_int
+    L.mvm_pack_views.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int),
+                                 C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]
     L.mvm_matcher_options_default.restype = None
     L.mvm_matcher_options_default.argtypes = [C.POINTER(MatcherOptions)]
     L.mvm_matcher_forward_ex.restype = C.c_int

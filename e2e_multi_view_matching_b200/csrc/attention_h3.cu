@@ -9,8 +9,9 @@
 // of the other views (multi_view_matcher.py:76-78,92-95).  prob[B,4,N,M] is never materialised.
 //
 // Same structure as attention_tc.cu: one CTA = 128 queries of one (view, head), key tiles of 64;
-//   warp 0      TMA producer: K_hi | K_lo [64 keys x 64 d] and V^T_hi | V^T_lo [64 d x 64 keys] fp16 tiles (8 KB each,
-//               one 128-byte swizzle row per matrix row), 3-deep rings; the planes are written by the QKV GEMM epilogue
+//   warp 0      TMA producer: K_hi | K_lo and V_hi | V_lo [64 keys x 64 d] fp16 tiles (8 KB each, one 128-byte swizzle
+//               row per key), 3-deep rings; the planes are written by the QKV GEMM epilogue.  V is read KEY-major, i.e.
+//               as an MN-major B operand of P.V (instruction-descriptor bit 16): no transposed copy of V exists
 //   warp 1      tcgen05.mma issuer S = Q K^T   (M128 N64 K16 kind::f16, A = Q_hi / Q_lo from tensor memory)
 //   warp 2      tcgen05.mma issuer O_g += P V  (A = P_hi / P_lo from tensor memory)
 //   warps 3-6 / 7-10   softmax groups 0 / 1 (even / odd key tiles): thread r owns query row r; S row -> registers,
@@ -35,7 +36,7 @@ namespace {
 
 constexpr int BQ = 128, BKV = 64, HD = 64;
 constexpr int K_BYTES = BKV * HD * 2;         //  8 KB  [64 keys x 64 d] fp16, 128-byte rows
-constexpr int V_BYTES = HD * BKV * 2;         //  8 KB  [64 d x 64 keys] fp16
+constexpr int V_BYTES = BKV * HD * 2;         //  8 KB  [64 keys x 64 d] fp16 (MN-major B operand of P.V)
 
 struct HCfg {
   // K and V^T ring depth.  The clock trace showed the Q K^T issuer waiting ~770 clk per tile for K with a 3-deep ring:
@@ -78,6 +79,10 @@ __device__ __forceinline__ void split_pack(float x0, float x1, uint32_t& hi, uin
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {   // D = F32, A = B = F16, both K-major
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+// the same with the B operand MN-major (cute::UMMA::InstrDescriptor b_major_, bit 16): B tile stored [K rows][N
+// contiguous], here V [keys][64 d] with 128-byte swizzled rows -- 8 keys per 1024-byte swizzle atom (SBO = 1024), one
+// K = 16 step = 2 atoms = 2048 bytes
+__host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) { return make_idesc_f16(M, N) | (1u << 16); }
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
@@ -197,15 +202,11 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   // recomputing (segment, offset) with loops and divisions for every K and V tile made its ~400 instructions per
   // tile the bottleneck of the fp16 kernel (clock trace r02: the producer issued a tile's loads 1.5 k cycles apart,
   // the MMA issuer waited 800 cycles per tile for K).  One shared-memory load per tile instead.
-  __shared__ int s_krow[C_::MAX_TILES];       // row of the tile's first key in the K planes
-  __shared__ int s_vrow[C_::MAX_TILES];       // first row of the (view, head) block in the V^T planes
-  __shared__ int s_vk0[C_::MAX_TILES];        // first key (column) of the tile in the V^T planes
+  __shared__ int s_krow[C_::MAX_TILES];       // row of the tile's first key in the K and V planes
   for (int j = threadIdx.x; j < nt; j += C_::NTHREADS) {
     int seg, k0, cnt;
     tile_info(j, seg, k0, cnt);
     s_krow[j] = (b * T + seg) * g.n_pad + k0;
-    s_vrow[j] = (b * T + seg) * 256 + h * HD;
-    s_vk0[j] = k0;
   }
 
   auto sK = [&](int s) { return smem + C_::OFF_K + s * K_BYTES * 2; };
@@ -256,9 +257,9 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       if (lane == 0) pmark(j, 2);
       if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(v_full + s, V_BYTES * 2);
-        const int vrow = s_vrow[j], k0 = s_vk0[j];
-        tc::tma_load_2d(sV(s), &tmV, v_full + s, k0, vrow);
-        tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, k0, vrow);
+        const int krow = s_krow[j];
+        tc::tma_load_2d(sV(s), &tmV, v_full + s, h * HD, krow);
+        tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, h * HD, krow);
       }
       __syncwarp();
       if (lane == 0) pmark(j, 3);
@@ -308,7 +309,7 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     }
   } else if (warp == 2) {
     // =========================== MMA issuer 2: O_g += P V ===========================
-    constexpr uint32_t idesc = make_idesc_f16(BQ, HD);         // M=128, N=64
+    constexpr uint32_t idesc = make_idesc_f16_bmn(BQ, HD);  // M=128, N=64 (d), B = V key-major         // M=128, N=64
     for (int j = 0; j < nt; ++j) {
       const int s = j % ST, sb = j & 1;
       // P(j) arrives in two halves (keys 0-31, 32-63): the first 12 MMAs start while the softmax threads are
@@ -323,9 +324,9 @@ attention_h3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       auto issue_PV = [&](int kk0) {                                       // two K = 16 steps = 32 keys
 #pragma unroll
         for (int kk = kk0; kk < kk0 + 2; ++kk) {
-          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + kk * 32);
+          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + kk * 2048);   // 16 keys x 128 B
           umma_f16_ts(o_acc, p_hi + kk * 8, dv, idesc, ((j >> 1) | kk) != 0);  // A = P from tensor memory; O_g accumulates over the group's tiles
-          umma_f16_ts(o_acc, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + kk * 32), idesc, 1);
+          umma_f16_ts(o_acc, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + kk * 2048), idesc, 1);
           umma_f16_ts(o_acc, p_lo + kk * 8, dv, idesc, 1);
         }
       };
@@ -514,9 +515,9 @@ struct SCfg {
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + ST * K_BYTES * 2;
   static constexpr int OFF_BAR = OFF_V + ST * V_BYTES * 2;
-  static constexpr int OFF_TAB = OFF_BAR + 256;         // tile table: int [3][MAX_TILES]
+  static constexpr int OFF_TAB = OFF_BAR + 256;         // tile table: int [MAX_TILES]
   static constexpr int MAX_TILES = HCfg::MAX_TILES;
-  static constexpr int SMEM_BYTES = OFF_TAB + 3 * MAX_TILES * 4 + 1024;
+  static constexpr int SMEM_BYTES = OFF_TAB + MAX_TILES * 4 + 1024;
   static constexpr int NTHREADS = 224;                  // producer, two MMA issuers, four softmax warps
   static constexpr int TMEM_COLS = 256;
   static constexpr int OUT_LD = HD + 4;                 // output staging row (floats): conflict-free float4 rows
@@ -546,8 +547,6 @@ attention_h3s_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
   static_assert((1 + 4 * ST + 5 + 1) * 8 <= 256, "barrier area");
   int* s_krow = reinterpret_cast<int*>(smem + C_::OFF_TAB);
-  int* s_vrow = s_krow + C_::MAX_TILES;
-  int* s_vk0 = s_vrow + C_::MAX_TILES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
@@ -595,8 +594,6 @@ attention_h3s_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       acc += n;
     }
     s_krow[j] = (b * T + seg) * g.n_pad + k0;
-    s_vrow[j] = (b * T + seg) * 256 + h * HD;
-    s_vk0[j] = k0;
   }
 
   auto sK = [&](int s) { return smem + C_::OFF_K + s * K_BYTES * 2; };
@@ -644,9 +641,9 @@ attention_h3s_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       tc::mbar_wait(v_empty + s, ((j / ST) & 1) ^ 1);
       if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(v_full + s, V_BYTES * 2);
-        const int vrow = s_vrow[j], k0 = s_vk0[j];
-        tc::tma_load_2d(sV(s), &tmV, v_full + s, k0, vrow);
-        tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, k0, vrow);
+        const int krow = s_krow[j];
+        tc::tma_load_2d(sV(s), &tmV, v_full + s, h * HD, krow);
+        tc::tma_load_2d(sV(s) + V_BYTES, &tmVlo, v_full + s, h * HD, krow);
       }
       __syncwarp();
     };
@@ -681,7 +678,7 @@ attention_h3s_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     }
   } else if (warp == 2) {
     // =========================== MMA issuer 2: O += P V ===========================
-    constexpr uint32_t idesc = make_idesc_f16(BQ, HD);
+    constexpr uint32_t idesc = make_idesc_f16_bmn(BQ, HD);  // M=128, N=64 (d), B = V key-major
     for (int j = 0; j < nt; ++j) {
       const int s = j % ST;
       tc::mbar_wait(p_ready, j & 1);
@@ -692,9 +689,9 @@ attention_h3s_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       auto issue_PV = [&](int kk0) {
 #pragma unroll
         for (int kk = kk0; kk < kk0 + 2; ++kk) {
-          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + kk * 32);
+          const uint64_t dv = tc::make_kmajor_sw128_desc(v_hi + kk * 2048);   // 16 keys x 128 B
           umma_f16_ts(tmem_O, p_hi + kk * 8, dv, idesc, (j | kk) != 0);
-          umma_f16_ts(tmem_O, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + kk * 32), idesc, 1);
+          umma_f16_ts(tmem_O, p_hi + kk * 8, tc::make_kmajor_sw128_desc(v_lo + kk * 2048), idesc, 1);
           umma_f16_ts(tmem_O, p_lo + kk * 8, dv, idesc, 1);
         }
       };
@@ -839,10 +836,10 @@ attention_h3s_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
 
 }  // namespace
 
-// K / V^T planes in half precision: kh, kl [rows, 256]; vth, vtl [V * 256, n_pad] (written by the QKV GEMM epilogue)
-int launch_attention_h3(const float* qkv, const __half* kh, const __half* kl, const __half* vth, const __half* vtl,
+// K / V planes in half precision: kh, kl, vh, vl [rows, 256] (written by the QKV GEMM epilogue)
+int launch_attention_h3(const float* qkv, const __half* kh, const __half* kl, const __half* vh, const __half* vl,
                         float* out, int batch, int n_pad, AttnSegs segs, int is_cross, cudaStream_t stream) {
-  MVM_REQUIRE(qkv && kh && kl && vth && vtl && out);
+  MVM_REQUIRE(qkv && kh && kl && vh && vl && out);
   MVM_REQUIRE(n_pad % 64 == 0 && segs.n_views >= 1 && segs.n_views <= 8);
   MVM_REQUIRE(!is_cross || segs.n_views >= 2);
   MVM_REQUIRE((segs.n_views - 1) * (n_pad / 64) <= HCfg::MAX_TILES || !is_cross);
@@ -856,8 +853,8 @@ int launch_attention_h3(const float* qkv, const __half* kh, const __half* kl, co
   const long long rows = (long long)V * n_pad;
   const CUtensorMap* tK = mvm_get_tmap_2d_f16(kh, rows, 256, 256, BKV);
   const CUtensorMap* tKlo = mvm_get_tmap_2d_f16(kl, rows, 256, 256, BKV);
-  const CUtensorMap* tV = mvm_get_tmap_2d_f16(vth, (long long)V * 256, n_pad, n_pad, HD);
-  const CUtensorMap* tVlo = mvm_get_tmap_2d_f16(vtl, (long long)V * 256, n_pad, n_pad, HD);
+  const CUtensorMap* tV = mvm_get_tmap_2d_f16(vh, rows, 256, 256, BKV);
+  const CUtensorMap* tVlo = mvm_get_tmap_2d_f16(vl, rows, 256, 256, BKV);
   if (!tK || !tV || !tKlo || !tVlo) return MVM_ERR_LAUNCH;
   AttnH3Args g;
   g.qkv = qkv; g.out = out; g.n_pad = n_pad; g.segs = segs; g.is_cross = is_cross; g.dbg = g_attn_dbg;

@@ -331,6 +331,32 @@ const CUtensorMap* mvm_get_tmap_2d_f16(const void* base, long long rows, long lo
   return tm;
 }
 
+// 2-D fp16 row-major [rows, cols] STORE map of the persistent GEMM's plane epilogue: box = [32 rows, 32 cols = 64 B],
+// 64-byte swizzle (a warp stages 32 rows x 64 B conflict-free and one TMA store writes them as full lines)
+const CUtensorMap* mvm_get_tmap_2d_f16_store(const void* base, long long rows, long long cols, long long ld) {
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  TmKey key(base, -17, rows, cols, ld, 0, 32);
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) return it->second;
+  EncodeFn enc = get_encode();
+  if (!enc) return nullptr;
+  CUtensorMap* tm = new CUtensorMap;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[mvm_b200] cuTensorMapEncodeTiled (f16 store) failed (%d) rows=%lld cols=%lld ld=%lld\n", (int)r, rows, cols, ld);
+    delete tm;
+    return nullptr;
+  }
+  g_tmaps[key] = tm;
+  return tm;
+}
+
 int g_gemm_bn = 256;   // output tile width of the one-tile-per-CTA tcgen05 GEMM (128 or 256), see mvm_debug_set_gemm_tile
 extern "C" void mvm_debug_set_gemm_tile(int bn) { g_gemm_bn = bn == 256 ? 256 : 128; }
 int g_gemm_persist = 1;   // 1: the persistent kernel of gemm_tc_persist.cu serves the 3xTF32 path (default)

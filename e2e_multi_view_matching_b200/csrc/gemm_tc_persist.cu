@@ -62,9 +62,10 @@ struct PArgs {
   int relu;
   float* VT; int vt_col0; int n_pad;   // transposed output for columns >= vt_col0 (see gemm_tc.cu)
   float* KLO; float* VTLO;             // tf32 lo planes of the K / V^T attention operands
-  // half-precision operand planes for attention_h3.cu (fp16x3): K hi / lo [rows, 256], V^T hi / lo [V*256, n_pad];
-  // when set they replace the fp32 K third of C, KLO, VT and VTLO
-  __half* KH16; __half* KL16; __half* VTH16; __half* VTL16;
+  // half-precision operand planes for attention_h3.cu (fp16x3): K hi / lo and V hi / lo, all [rows, 256] (V stays
+  // key-major: the attention reads it as an MN-major B operand); when set they replace the fp32 K and V thirds of C,
+  // KLO, VT and VTLO
+  __half* KH16; __half* KL16; __half* VH16; __half* VL16;
   int tiles_m, tiles_n;
 };
 
@@ -108,7 +109,9 @@ template <bool SCORE, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                        const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
-                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmKLO, PArgs g,
+                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmKLO,
+                       const __grid_constant__ CUtensorMap tmKH, const __grid_constant__ CUtensorMap tmKL,
+                       const __grid_constant__ CUtensorMap tmVH, const __grid_constant__ CUtensorMap tmVL, PArgs g,
                        const __grid_constant__ ScoreTab st) {
   using G_ = GCfg<F16>;
   constexpr int BK = G_::BK, STAGES = G_::STAGES, A_BYTES = G_::A_BYTES, W_BYTES = G_::W_BYTES, STAGE_BYTES = G_::STAGE_BYTES;
@@ -153,6 +156,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA); tc::prefetch_tmap(&tmA2); tc::prefetch_tmap(&tmWhi); tc::prefetch_tmap(&tmWlo);
     tc::prefetch_tmap(&tmC); tc::prefetch_tmap(&tmKLO);
+    if (g.KH16) { tc::prefetch_tmap(&tmKH); tc::prefetch_tmap(&tmKL); tc::prefetch_tmap(&tmVH); tc::prefetch_tmap(&tmVL); }
   }
   if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
   tc::tc_fence_before();
@@ -342,19 +346,12 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (has_r) x += r[j];
           v[j] = x;
         }
-        if ((g.VT || g.VTH16) && nb >= g.vt_col0) {
-          // V^T (and its lo plane) for the attention kernel: lanes = consecutive keypoints -> coalesced
+        if (g.VT && nb >= g.vt_col0) {
+          // V^T (and its tf32 lo plane) for the tf32 attention kernel: lanes = consecutive keypoints -> coalesced
           if (m < g.M) {
             const int slab = m / g.n_pad, ii = m % g.n_pad;
             const long long off = ((long long)slab * (g.N - g.vt_col0) + (nb - g.vt_col0)) * g.n_pad + ii;
-            if (g.VTH16) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const __half h = __float2half_rn(v[j]);
-                g.VTH16[off + (long long)j * g.n_pad] = h;
-                g.VTL16[off + (long long)j * g.n_pad] = __float2half_rn(v[j] - __half2float(h));
-              }
-            } else if (g.VTLO) {
+            if (g.VTLO) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float h = tf32_hi(v[j]);
@@ -368,26 +365,39 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
           continue;
         }
-        if (g.KH16 && nb >= 256 && nb < 512) {
-          // K hi / lo planes in half precision: 64 contiguous bytes per row and plane
-          if (m < g.M) {
-            uint32_t hp[16], lp[16];
+        if (g.KH16 && nb >= 256) {
+          // K (columns 256..511) and V (512..767) hi / lo planes in half precision: the warp stages its 32 rows x 64 B
+          // per plane (64-byte swizzle: conflict-free 16-byte stores) and one TMA store per plane writes full lines --
+          // 16-byte row-strided global stores cost 32 L1 wavefronts per instruction and made this epilogue as long as
+          // the tile's MMAs (QKV GEMM at 34 % tensor pipe, profiles/r02_v10_gemm_tc_persist_kernel_ncu.txt)
+          uint32_t hp[16], lp[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-              const float2 hf = __half22float2(h);
-              const __half2 l = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-              hp[j] = *reinterpret_cast<const uint32_t*>(&h);
-              lp[j] = *reinterpret_cast<const uint32_t*>(&l);
-            }
-            uint4* dh = reinterpret_cast<uint4*>(g.KH16 + (long long)m * 256 + (nb - 256));
-            uint4* dl = reinterpret_cast<uint4*>(g.KL16 + (long long)m * 256 + (nb - 256));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              dh[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
-              dl[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
-            }
+          for (int j = 0; j < 16; ++j) {
+            const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+            hp[j] = *reinterpret_cast<const uint32_t*>(&h);
+            lp[j] = *reinterpret_cast<const uint32_t*>(&l);
           }
+          tc::tma_store_wait_read<1>();                        // the buffer used two stores ago is free
+          __syncwarp();
+          uint8_t* sb = stg + sbuf * STG_BYTES + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint4*>(sb + ((j ^ sw) << 4)) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+            *reinterpret_cast<uint4*>(sb + 2048 + ((j ^ sw) << 4)) = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+          }
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (tc::elect_one()) {
+            const bool is_v = nb >= 512;
+            const int col = nb - (is_v ? 512 : 256);
+            tc::tma_store_2d(is_v ? &tmVH : &tmKH, stg + sbuf * STG_BYTES, col, m0 + q * 32);
+            tc::tma_store_2d(is_v ? &tmVL : &tmKL, stg + sbuf * STG_BYTES + 2048, col, m0 + q * 32);
+            tc::tma_store_commit();
+          }
+          sbuf ^= 1;
           continue;
         }
         const bool split_k = g.KLO != nullptr && nb >= 256 && nb < 512;
@@ -453,20 +463,24 @@ int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad,
   const CUtensorMap* tWlo = f16 ? mvm_get_tmap_2d_f16(d.Wlo16, d.N, d.K, d.ldw, BN) : mvm_get_tmap_2d(d.Wlo, d.N, d.K, d.ldw, BN);
   const CUtensorMap* tC = mvm_get_tmap_2d(d.C, d.M, d.N, d.ldc, 32);
   const CUtensorMap* tK = KLO ? mvm_get_tmap_2d(KLO, d.M, 256, 256, 32) : tC;
-  if (!tA || !tA2 || !tWhi || !tWlo || !tC || !tK) return MVM_ERR_LAUNCH;
+  const CUtensorMap* tKH = hp ? mvm_get_tmap_2d_f16_store(hp->kh, d.M, 256, 256) : tC;
+  const CUtensorMap* tKL = hp ? mvm_get_tmap_2d_f16_store(hp->kl, d.M, 256, 256) : tC;
+  const CUtensorMap* tVH = hp ? mvm_get_tmap_2d_f16_store(hp->vh, d.M, 256, 256) : tC;
+  const CUtensorMap* tVL = hp ? mvm_get_tmap_2d_f16_store(hp->vl, d.M, 256, 256) : tC;
+  if (!tA || !tA2 || !tWhi || !tWlo || !tC || !tK || !tKH || !tKL || !tVH || !tVL) return MVM_ERR_LAUNCH;
   PArgs g;
   g.bias = d.bias; g.R = d.R; g.ldr = d.ldr; g.C = d.C; g.ldc = d.ldc; g.M = d.M; g.N = d.N; g.K = d.K;
   g.K1 = d.K1; g.alpha = f16 ? d.alpha / d.wscale : d.alpha; g.relu = d.relu; g.VT = VT; g.vt_col0 = vt_col0; g.n_pad = n_pad;
   g.KLO = KLO; g.VTLO = VTLO;
   g.KH16 = hp ? (__half*)hp->kh : nullptr; g.KL16 = hp ? (__half*)hp->kl : nullptr;
-  g.VTH16 = hp ? (__half*)hp->vth : nullptr; g.VTL16 = hp ? (__half*)hp->vtl : nullptr;
+  g.VH16 = hp ? (__half*)hp->vh : nullptr; g.VL16 = hp ? (__half*)hp->vl : nullptr;
   g.tiles_m = mvm_div_up(d.M, BM); g.tiles_n = d.N / BN;
   const int n_tiles = g.tiles_m * g.tiles_n;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   ScoreTab none;
   none.n_pairs = 0; none.batch = 0; none.n_views = 0; none.n_pad = 0;
-  if (f16) gemm_tc_persist_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, g, none);
-  else gemm_tc_persist_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, g, none);
+  if (f16) gemm_tc_persist_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, *tKH, *tKL, *tVH, *tVL, g, none);
+  else gemm_tc_persist_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, *tKH, *tKL, *tVH, *tVL, g, none);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }
@@ -517,7 +531,7 @@ int launch_score_gemm_tc(const float* mdesc, float* hi, float* lo, int n_pad, co
   g.tiles_m = mvm_div_up(max_m, BM); g.tiles_n = mvm_div_up(max_n, BN);
   const long long n_tiles = (long long)g.tiles_m * g.tiles_n * tab.n_pairs * batch;
   const int grid = n_tiles < n_sm ? (int)n_tiles : n_sm;
-  gemm_tc_persist_kernel<true, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA, *tWhi, *tWlo, *tA, *tA, g, st);
+  gemm_tc_persist_kernel<true, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA, *tWhi, *tWlo, *tA, *tA, *tA, *tA, *tA, *tA, g, st);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }

@@ -36,8 +36,8 @@ int mvm_default_gemm_tile();
 int mvm_default_gemm_persistent();
 // persistent 3xTF32 kernel (A operand in tensor memory, double-buffered accumulators, TMA-store epilogue)
 // hp != nullptr (QKV projection, vt_col0 = 512): the K third and V^T leave as half-precision hi / lo planes for
-// launch_attention_h3 instead of the fp32 / tf32 buffers (kh, kl [rows, 256]; vth, vtl [V*256, n_pad], as __half)
-struct HalfPlanes { void* kh; void* kl; void* vth; void* vtl; };
+// launch_attention_h3 instead of the fp32 / tf32 buffers (kh, kl, vh, vl: all [rows, 256], as __half; V stays key-major)
+struct HalfPlanes { void* kh; void* kl; void* vh; void* vl; };
 int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO,
                            cudaStream_t stream, const HalfPlanes* hp = nullptr);
 // every (pair, tuple) score matrix in one launch of the persistent kernel (3xTF32); hi / lo: scratch [rows, 256]
@@ -57,7 +57,7 @@ int launch_attention_simt(const float* qkv, float* out, int batch, int n_pad, At
                           int is_cross, cudaStream_t stream);
 // fp32-faithful attention with half-precision operand planes (fp16x3, attention_h3.cu); planes as in HalfPlanes
 struct __half;
-int launch_attention_h3(const float* qkv, const __half* kh, const __half* kl, const __half* vth, const __half* vtl,
+int launch_attention_h3(const float* qkv, const __half* kh, const __half* kl, const __half* vh, const __half* vl,
                         float* out, int batch, int n_pad, AttnSegs segs, int is_cross, cudaStream_t stream);
 
 // scores[p][bi] inner block = mdesc[a] . mdesc[b]^T * alpha   (mdesc: [views, n_pad, 256])

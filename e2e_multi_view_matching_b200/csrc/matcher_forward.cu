@@ -215,16 +215,16 @@ int mvm_matcher_forward_ex(const mvm_matcher_weights* w, int batch, int n_views,
       // fp16x3: K and V^T leave the QKV GEMM as half-precision hi / lo planes (carved out of the tf32 lo-plane
       // buffers: two fp16 planes fill one fp32 plane exactly)
       __half* kh = reinterpret_cast<__half*>(ws.KLO);
-      __half* vth = reinterpret_cast<__half*>(ws.VTLO);
-      HalfPlanes hp = {kh, kh + (size_t)rows * 256, vth, vth + (size_t)rows * 256};
+      __half* vh = reinterpret_cast<__half*>(ws.VTLO);
+      HalfPlanes hp = {kh, kh + (size_t)rows * 256, vh, vh + (size_t)rows * 256};
       GemmDesc gq = make_gemm(ws.X, 256, L.w_qkv, 256, L.b_qkv, ws.QKV, 768, rows, 768, 0);
       set_planes(cx, gq);
       {
         MvmProfScope prof__(MVM_TAG_GEMM, s);      // (launch_gemm_tc opens the scope on the other paths)
         MVM_TRY(launch_gemm_tc_persist(gq, nullptr, 512, n_pad, nullptr, nullptr, s, &hp));
       }
-      MVM_TRY(launch_attention_h3(ws.QKV, (const __half*)hp.kh, (const __half*)hp.kl, (const __half*)hp.vth,
-                                  (const __half*)hp.vtl, ws.MSG, batch, n_pad, segs, L.is_cross, s));
+      MVM_TRY(launch_attention_h3(ws.QKV, (const __half*)hp.kh, (const __half*)hp.kl, (const __half*)hp.vh,
+                                  (const __half*)hp.vl, ws.MSG, batch, n_pad, segs, L.is_cross, s));
     } else if (cx.math_mode != 0) {
       // tensor-core path: the QKV GEMM epilogue also writes V^T [view, 256, n_pad] for the P.V product
       float* klo = cx.math_mode == 3 ? ws.KLO : nullptr;
@@ -382,13 +382,13 @@ int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, i
   return launch_attention_tc(qkv, vt, out, batch, n_pad, segs, is_cross, n_pass, (cudaStream_t)stream, klo, vtlo);
 }
 
-int mvm_attention_h3(const float* qkv, const void* kh, const void* kl, const void* vth, const void* vtl, float* out,
+int mvm_attention_h3(const float* qkv, const void* kh, const void* kl, const void* vh, const void* vl, float* out,
                      int batch, int n_views, int n_pad, const int* counts, int is_cross, void* stream) {
-  MVM_REQUIRE(qkv && kh && kl && vth && vtl && out && counts && n_views >= 1 && n_views <= 8);
+  MVM_REQUIRE(qkv && kh && kl && vh && vl && out && counts && n_views >= 1 && n_views <= 8);
   AttnSegs segs;
   segs.n_views = n_views;
   for (int t = 0; t < 8; ++t) segs.counts[t] = t < n_views ? counts[t] : 0;
-  return launch_attention_h3(qkv, (const __half*)kh, (const __half*)kl, (const __half*)vth, (const __half*)vtl, out, batch,
+  return launch_attention_h3(qkv, (const __half*)kh, (const __half*)kl, (const __half*)vh, (const __half*)vl, out, batch,
                              n_pad, segs, is_cross, (cudaStream_t)stream);
 }
 

@@ -198,6 +198,7 @@ __device__ __forceinline__ float tf32_rn(float x) {
 const CUtensorMap* mvm_get_tmap_2d(const float* base, long long rows, long long cols, long long ld, int box_rows);
 // 2-D fp16 [rows, cols]: box = [box_rows, 64 cols = 128 B]
 const CUtensorMap* mvm_get_tmap_2d_f16(const void* base, long long rows, long long cols, long long ld, int box_rows);
+const CUtensorMap* mvm_get_tmap_2d_f16_store(const void* base, long long rows, long long cols, long long ld);
 // 3-D [slabs, rows, cols]: box = [1, box_rows, 32]
 const CUtensorMap* mvm_get_tmap_3d(const float* base, long long slabs, long long rows, long long cols,
                                    long long ld_row, long long ld_slab, int box_rows);

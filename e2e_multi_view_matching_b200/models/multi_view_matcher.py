@@ -93,14 +93,18 @@ class MatcherEngine:
         dev = views[0][0].device
         counts = [int(v[0].shape[1]) for v in views]
         n_pad = max(64, _round_up(max(counts), 64))
-        kp = torch.zeros(B, T, n_pad, 2, dtype=torch.float32, device=dev)
-        sc = torch.zeros(B, T, n_pad, dtype=torch.float32, device=dev)
-        de = torch.zeros(B, T, 256, n_pad, dtype=torch.float32, device=dev)
-        for t, (k, s, d) in enumerate(views):
-            n = counts[t]
-            kp[:, t, :n] = k
-            sc[:, t, :n] = s
-            de[:, t, :, :n] = d
+        kp = torch.empty(B, T, n_pad, 2, dtype=torch.float32, device=dev)
+        sc = torch.empty(B, T, n_pad, dtype=torch.float32, device=dev)
+        de = torch.empty(B, T, 256, n_pad, dtype=torch.float32, device=dev)
+        # one pack launch (zero padding included) instead of three fills + three strided copies per view
+        views = [tuple(x.contiguous() for x in v) for v in views]
+        for k, s, d in views:
+            assert k.dtype == s.dtype == d.dtype == torch.float32 and d.shape[1] == 256
+        ptrs = [(C.c_void_p * T)(*[v[i].data_ptr() for v in views]) for i in range(3)]
+        cnt_pack = (C.c_int * T)(*counts)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mvm_pack_views(ptrs[0], ptrs[1], ptrs[2], cnt_pack, B, T, n_pad, _lib.ptr(kp), _lib.ptr(sc),
+                                          _lib.ptr(de), _lib.stream_ptr()), 'mvm_pack_views')
         n_pairs = len(pair_ids)
         pairs = (_lib.PairIO * n_pairs)()
         outs = {}

@@ -78,10 +78,11 @@ def attention(qkv, batch, n_views, counts, is_cross, tc_passes=0):
         kh = k.half()
         kl = (k - kh.float()).half().reshape(-1, 256).contiguous()
         kh = kh.reshape(-1, 256).contiguous()
-        vt = qkv[:, :, 512:].transpose(1, 2).contiguous()      # [V, 256, n_pad]
-        vth = vt.half()
-        vtl = (vt - vth.float()).half().contiguous()
-        rc = lib.mvm_attention_h3(_lib.ptr(qkv), _lib.ptr(kh), _lib.ptr(kl), _lib.ptr(vth.contiguous()), _lib.ptr(vtl),
+        v = qkv[:, :, 512:].contiguous()                      # V stays key-major [rows, 256] (MN-major B operand)
+        vh = v.half()
+        vl = (v - vh.float()).half().reshape(-1, 256).contiguous()
+        vh = vh.reshape(-1, 256).contiguous()
+        rc = lib.mvm_attention_h3(_lib.ptr(qkv), _lib.ptr(kh), _lib.ptr(kl), _lib.ptr(vh), _lib.ptr(vl),
                                   _lib.ptr(out), batch, n_views, n_pad, cnt, int(is_cross), _lib.stream_ptr())
         _lib.check(rc, 'mvm_attention_h3')
         return out

@@ -84,6 +84,14 @@ typedef struct mvm_pair_io {
   float* conf;
 } mvm_pair_io;
 
+/* Gathers the per-view inputs of a matcher call -- the reference's `data` dict, keypoints{i} [B,n_i,2], scores{i}
+ * [B,n_i], descriptors{i} [B,256,n_i] (models/models/multi_view_matcher.py:229-262) -- into the zero-padded
+ * view-slot-major buffers mvm_matcher_forward reads (kpts [B,T,n_pad,2], scores [B,T,n_pad], desc [B,T,256,n_pad]).
+ * kpts / scores / desc: HOST arrays of n_views device pointers; counts[t] = n_t <= n_pad.  One launch. */
+int mvm_pack_views(const float* const* kpts, const float* const* scores, const float* const* desc,
+                   const int* counts, int batch, int n_views, int n_pad, float* out_kpts, float* out_scores,
+                   float* out_desc, void* stream);
+
 /* Bytes of scratch mvm_matcher_forward needs for this shape. */
 size_t mvm_matcher_workspace_bytes(int batch, int n_views, int n_pad, int n_pairs, int has_conf);
 
@@ -177,9 +185,10 @@ int mvm_attention_tc(const float* qkv, const float* vt, float* out, int batch, i
 
 /* fp32-faithful attention with HALF-PRECISION operand planes (fp16x3: hi = fp16(x), lo = fp16(x - hi); three
  * kind::f16 MMAs per product, half the tensor-pipe time of the tf32 variant at the same 22-bit operand precision).
- * kh, kl [n_views_total * n_pad, 256] and vth, vtl [n_views_total * 256, n_pad] are fp16 buffers (the QKV GEMM
- * epilogue writes them inside mvm_matcher_forward); the q third of qkv is read as fp32. */
-int mvm_attention_h3(const float* qkv, const void* kh, const void* kl, const void* vth, const void* vtl, float* out,
+ * kh, kl, vh, vl [n_views_total * n_pad, 256] are fp16 buffers, point-major like K and V themselves (the QKV GEMM
+ * epilogue writes them inside mvm_matcher_forward; V is read as an MN-major tensor-core operand, no transposed copy);
+ * the q third of qkv is read as fp32. */
+int mvm_attention_h3(const float* qkv, const void* kh, const void* kl, const void* vh, const void* vl, float* out,
                      int batch, int n_views, int n_pad, const int* counts, int is_cross, void* stream);
 
 /* log_optimal_transport (superglue.py:143-172).  scores: [batch, m+1, n+1] buffers whose

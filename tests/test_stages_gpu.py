@@ -87,3 +87,29 @@ def test_extract_matches_vs_oracle():
             assert np.array_equal(r[1], g[1].cpu().numpy())
             np.testing.assert_allclose(g[2].cpu().numpy(), r[2], rtol=1e-5)
             np.testing.assert_allclose(g[3].cpu().numpy(), r[3], rtol=1e-5)
+
+
+def test_pack_views_matches_slice_copies():
+    """mvm_pack_views == the per-view zero-padded slice copies (multi_view_matcher.py:229-262 layout), ragged views."""
+    import ctypes as C
+    from e2e_multi_view_matching_b200 import _lib
+    lib = _lib.lib()
+    B, counts, n_pad = 3, [100, 192, 1, 77], 192
+    T = len(counts)
+    g = torch.Generator().manual_seed(5)
+    views = [(torch.randn(B, n, 2, generator=g).cuda(), torch.rand(B, n, generator=g).cuda(),
+              torch.randn(B, 256, n, generator=g).cuda()) for n in counts]
+    kp = torch.full((B, T, n_pad, 2), 7.0, device='cuda')           # stale contents must be overwritten by the padding
+    sc = torch.full((B, T, n_pad), 7.0, device='cuda')
+    de = torch.full((B, T, 256, n_pad), 7.0, device='cuda')
+    ptrs = [(C.c_void_p * T)(*[v[i].data_ptr() for v in views]) for i in range(3)]
+    rc = lib.mvm_pack_views(ptrs[0], ptrs[1], ptrs[2], (C.c_int * T)(*counts), B, T, n_pad, _lib.ptr(kp), _lib.ptr(sc),
+                            _lib.ptr(de), _lib.stream_ptr())
+    assert rc == 0
+    for t, (k, s, d) in enumerate(views):
+        n = counts[t]
+        assert torch.equal(kp[:, t, :n], k) and torch.equal(sc[:, t, :n], s) and torch.equal(de[:, t, :, :n], d)
+        assert kp[:, t, n:].abs().max().item() == 0 if n < n_pad else True
+        assert sc[:, t, n:].abs().sum().item() == 0 and de[:, t, :, n:].abs().sum().item() == 0
+    assert lib.mvm_pack_views(ptrs[0], ptrs[1], ptrs[2], (C.c_int * T)(*[n_pad + 1] * T), B, T, n_pad, _lib.ptr(kp),
+                              _lib.ptr(sc), _lib.ptr(de), _lib.stream_ptr()) != 0      # a view longer than n_pad is refused

@@ -14,9 +14,9 @@ k = qkv[:, :, 256:512].contiguous()
 kh = k.half()
 kl = (k - kh.float()).half().reshape(-1, 256).contiguous()
 kh = kh.reshape(-1, 256).contiguous()
-vt = qkv[:, :, 512:].transpose(1, 2).contiguous()
-vth = vt.half().contiguous()
-vtl = (vt - vth.float()).half().contiguous()
+v = qkv[:, :, 512:].contiguous()
+vth = v.half().reshape(-1, 256).contiguous()
+vtl = (v - vth.reshape(v.shape).float()).half().reshape(-1, 256).contiguous()
 cnt = (ctypes.c_int * T)(*([N] * T))
 out_buf = torch.zeros(B * T, N, 256, device='cuda')
 
