@@ -15,7 +15,7 @@ def _load(name):
 
 
 def test_own_arm_line_has_the_contract_keys():
-    d = _load('bench_r01_v32.json')
+    d = _load('bench_r02_v10.json')
     for k in REQUIRED + ['cpu_baseline']:
         assert k in d, k
     base = json.load(open(os.path.join(ROOT, 'BASELINE.json')))
@@ -29,21 +29,35 @@ def test_own_arm_line_has_the_contract_keys():
     for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
         assert k in r, k
     assert r['bound'] in ('hbm', 'tensor') and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert r['traffic'] and r['frac'] > 0.3                      # round 2: attention at > 0.3 of the measured bf16 peak
+    assert d['value'] > 300 and d['run']['attention_split'] == 'fp16 hi/lo'
+    p = d['pose_auc_parity']
+    assert p['max_abs_diff_pt'] <= 0.5 and p['n_errors'] == 320
     c = d['cpu_baseline']
     assert c['kind'] in ('reference', 'port') and c['cores'] >= 1 and c['sample']
     assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
 
 
 def test_reference_arm_line():
-    d = _load('bench_r01_v32_reference_arm.json')
+    d = _load('bench_r02_v10_reference_arm.json')
+    assert d['steps'] == 20 and d['warmup'] == 5            # the arm honours --steps / --warmup
     assert d['impl'] == 'reference' and d['unit'] == 'tuples/s' and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
 
 
 def test_two_gpu_line_scales():
-    one, two = _load('bench_r01_v32.json'), _load('bench_r01_v31_2gpu.json')
-    assert two['n_gpus'] == 2 and two['config']['parallelism'] == 'dp2'
-    assert two['value'] > 1.7 * one['value'] * 0.95      # whole-job aggregate, weak scaling
+    one, two = _load('bench_r02_g16_quick.json'), _load('bench_r02_v8_2gpu.json')      # same commit
+    assert two['n_gpus'] == 2 and two['run']['parallelism'] == 'dp2'
+    assert two['value'] > 1.9 * one['value']             # whole-job aggregate, weak scaling
+
+
+def test_pair_config_lines():
+    for name, unit_min in (('bench_r02_v10_cfg2.json', 2000), ('bench_r02_v10_cfg4.json', 400)):
+        d = _load(name)
+        for k in REQUIRED + ['cpu_baseline']:
+            assert k in d, (name, k)
+        assert d['unit'] == 'pairs/s' and d['value'] > unit_min
+        assert d['pose_auc_parity']['max_abs_diff_pt'] <= 0.1
 
 
 def test_bench_cli_parses_without_gpu():
