@@ -4,6 +4,8 @@ Built:
   * compute_match_loss (helpers.py:228-241) as an autograd.Function on CUDA kernels (csrc/train_loss.cu), forward
     and backward;
   * combine_losses (train.py:36-40);
+  * compute_gt_matches_of_image_pair / compute_gt_matches (helpers.py:121-226): ground-truth assignments from depth
+    maps and poses on CUDA kernels (csrc/gt_matches.cu; the [bs, N, N] error matrix is never materialised);
   * LogOptimalTransport: autograd.Function around the production Sinkhorn kernel whose backward is the EXACT gradient
     of the 100 unrolled iterations (what autograd computes for the reference, superglue.py:143-172).  The backward
     below is stated in torch operations -- it is the executable specification (checked against autograd through the
@@ -122,3 +124,43 @@ class LogOptimalTransport(torch.autograd.Function):
 
 def log_optimal_transport(scores, alpha, iters):
     return LogOptimalTransport.apply(scores, alpha if torch.is_tensor(alpha) else torch.tensor(float(alpha)), iters)
+
+
+def compute_gt_matches_of_image_pair(kpts0, kpts1, K0, K1, T0to1, depth0, depth1, max_matched_reproj_err,
+                                     min_unmatched_reproj_err):
+    """helpers.py:121-203 -> (indices [bs,2,N+1] int64, weights [bs,2,N+1] float32)."""
+    if kpts0.device.type != 'cuda':
+        raise _lib.MvmError('compute_gt_matches_of_image_pair needs CUDA tensors (no CPU fallback)')
+    lib = _lib.lib()
+    bs, n, _ = kpts0.shape
+    assert kpts1.shape == (bs, n, 2) and depth0.shape == depth1.shape and depth0.dim() == 3
+    H, W = depth0.shape[1:]
+    dev = kpts0.device
+    f = lambda t: t.detach().float().contiguous()
+    k0, k1, K0_, K1_, T_, d0, d1 = f(kpts0), f(kpts1), f(K0), f(K1), f(T0to1), f(depth0), f(depth1)
+    assert K0_.shape == (bs, 4, 4) and K1_.shape == (bs, 4, 4) and T_.shape == (bs, 4, 4)
+    indices = torch.empty(bs, 2, n + 1, dtype=torch.int64, device=dev)
+    weights = torch.empty(bs, 2, n + 1, dtype=torch.float32, device=dev)
+    nbytes = lib.mvm_gt_matches_workspace_bytes(bs, n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mvm_gt_matches_pair(_lib.ptr(k0), _lib.ptr(k1), _lib.ptr(K0_), _lib.ptr(K1_), _lib.ptr(T_),
+                                           _lib.ptr(d0), _lib.ptr(d1), bs, n, H, W, float(max_matched_reproj_err),
+                                           float(min_unmatched_reproj_err), _lib.ptr(indices), _lib.ptr(weights),
+                                           _lib.ptr(ws), nbytes, _lib.stream_ptr()), 'mvm_gt_matches_pair')
+    return indices, weights
+
+
+def compute_gt_matches(opt, data):
+    """helpers.py:215-226: gt_indices_k_m / gt_weights_k_m for every pair k < m of the tuple; pops the depth maps."""
+    curr_tuple_size = len(data["ids"])
+    for m in range(curr_tuple_size):
+        for k in range(m):
+            T_k2m = torch.linalg.inv(data["pose" + str(m)]) @ data["pose" + str(k)]
+            data["gt_indices_{}_{}".format(k, m)], data["gt_weights_{}_{}".format(k, m)] = \
+                compute_gt_matches_of_image_pair(data["keypoints" + str(k)], data["keypoints" + str(m)],
+                                                 data["intr" + str(k)], data["intr" + str(m)], T_k2m,
+                                                 data["depth" + str(k)], data["depth" + str(m)],
+                                                 opt.match_reproj_err, opt.unmatch_reproj_err)
+    for m in range(curr_tuple_size):
+        data.pop("depth" + str(m))

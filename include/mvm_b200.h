@@ -356,6 +356,17 @@ int mvm_match_loss_forward(const float* log_p, const int64_t* gt_indices, const 
 int mvm_match_loss_backward(const int64_t* gt_indices, const float* gt_weights, const float* grad_loss, int bs, int ft,
                             float* grad_log_p, void* stream);
 
+/* compute_gt_matches_of_image_pair (helpers.py:121-203, with transform_kpts :115-119 and set_weight :205-213):
+ * ground-truth assignment of an image pair from depth maps and poses, without the [bs, N, N] error matrix.
+ * kpts0/1 [bs, n, 2] pixel x,y (truncated like .long()); K0/K1, T0to1 [bs, 4, 4]; depth0/1 [bs, H, W];
+ * indices [bs, 2, n+1] int64 (-1 = unmatched; last entry = dustbin), weights [bs, 2, n+1] (class-balanced, 0 = dropped).
+ * A keypoint outside the image is clamped to the border (the reference raises an IndexError there). */
+size_t mvm_gt_matches_workspace_bytes(int bs, int n);
+int mvm_gt_matches_pair(const float* kpts0, const float* kpts1, const float* K0, const float* K1, const float* T0to1,
+                        const float* depth0, const float* depth1, int bs, int n, int H, int W,
+                        float max_matched_reproj_err, float min_unmatched_reproj_err, long long* indices,
+                        float* weights, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- instrumentation ----------------------------------------------------------------- */
 /* Kernels launched by the library since load (bench.py's gpu_launches). */
 unsigned long long mvm_launch_count(void);
