@@ -6,6 +6,10 @@ Built:
   * combine_losses (train.py:36-40);
   * compute_gt_matches_of_image_pair / compute_gt_matches (helpers.py:121-226): ground-truth assignments from depth
     maps and poses on CUDA kernels (csrc/gt_matches.cu; the [bs, N, N] error matrix is never materialised);
+  * run_matcher (helpers.py:243-260) and validation_step (the loop body of Trainer.validate, train.py:89-106) for the
+    matcher in EVAL mode -- exactly what the reference's validation pass runs: matcher forward, match loss, weighted
+    eight-point with choose_closest against the ground-truth pose, rotation / translation losses, combine_losses and
+    the validation-loss all-reduce;
   * LogOptimalTransport: autograd.Function around the production Sinkhorn kernel whose backward is the EXACT gradient
     of the 100 unrolled iterations (what autograd computes for the reference, superglue.py:143-172).  The backward
     below is stated in torch operations -- it is the executable specification (checked against autograd through the
@@ -164,3 +168,44 @@ def compute_gt_matches(opt, data):
                                                  opt.match_reproj_err, opt.unmatch_reproj_err)
     for m in range(curr_tuple_size):
         data.pop("depth" + str(m))
+
+
+def run_matcher(opt, data, matcher):
+    """helpers.py:243-260.  The matcher must be in eval mode (the validation pass, train.py:66-68): the training
+    branch of the forward is not built (module docstring)."""
+    from .pose_optimization.two_view.estimate_relative_pose import run_weighted_8_point
+    from .pose_optimization.two_view.compute_pose_error import compute_rotation_error, compute_translation_error_as_angle
+    curr_tuple_size = len(data["ids"])
+    getattr(matcher, 'module', matcher).config["full_output"] = opt.pose_loss        # DataParallel / DDP wrapped or bare
+    result = matcher(data)
+    match_loss = torch.zeros(1, device=data["pose0"].device)
+    rot_loss = torch.zeros(1, device=match_loss.device)
+    transl_loss = torch.zeros(1, device=match_loss.device)
+    for id1 in range(curr_tuple_size):
+        for id0 in range(id1):
+            match_loss = match_loss + compute_match_loss(result["scores_{}_{}".format(id0, id1)],
+                                                         data["gt_indices_{}_{}".format(id0, id1)],
+                                                         data["gt_weights_{}_{}".format(id0, id1)])
+            if opt.pose_loss:
+                target = torch.linalg.inv(data["pose{}".format(id1)]) @ data["pose{}".format(id0)]
+                pred, _ = run_weighted_8_point(data, result, id0, id1, choose_closest=True, target_T_021=target)
+                rot_loss = rot_loss + compute_rotation_error(pred, target)
+                transl_loss = transl_loss + compute_translation_error_as_angle(pred, target)
+    losses = {"match_loss": match_loss, "rot_loss": rot_loss, "transl_loss": transl_loss}
+    return losses, result
+
+
+def validation_step(opt, data, matcher, n_pairs, pose_match_ratio, process_group=None):
+    """One batch of Trainer.validate (train.py:89-106) after SuperPoint: ground-truth matches when the batch still
+    carries depth maps, run_matcher, combine_losses; the scalar validation loss is all-reduced over the ranks
+    (mean) when torch.distributed is initialised.  -> (val_loss tensor [1], losses dict)."""
+    with torch.no_grad():
+        if "depth0" in data:
+            compute_gt_matches(opt, data)
+        losses, _ = run_matcher(opt, data, matcher)
+        val_loss, losses = combine_losses(losses, n_pairs, pose_match_ratio, opt.rot_weight, opt.trans_weight)
+        val_loss = val_loss.reshape(1).clone()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(val_loss, group=process_group)
+            val_loss /= torch.distributed.get_world_size(process_group)
+    return val_loss, losses

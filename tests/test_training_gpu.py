@@ -1,6 +1,8 @@
 """First slice of the training path: compute_match_loss kernels (forward + backward) and the
 exact unrolled-iteration gradient of log_optimal_transport, against autograd through the CPU restatement of the
 reference's functions (helpers.py:228-241, superglue.py:143-172) in double precision."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -64,3 +66,33 @@ def test_combine_losses():
     total, per = combine_losses(losses, 3, 0.25, 2.0, 0.5)
     assert abs(per['match_loss'].item() - 2.0) < 1e-7
     assert abs(total.item() - (0.75 * 2.0 + 0.25 * (2.0 * 1.0 + 0.5 * 3.0))) < 1e-6
+
+
+@pytest.mark.parametrize('name', ['mv3_128', 'pair_192'])
+def test_run_matcher_vs_reference_golden(name):
+    """helpers.run_matcher (helpers.py:243-260) in eval mode -- the reference's validation pass -- against the losses the
+    unmodified reference produced on the same seeded inputs (oracle/make_validation_golden.py, fp32 and fp64 runs)."""
+    import json
+    import types
+    from oracle.make_validation_golden import build
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    from e2e_multi_view_matching_b200.training import run_matcher, validation_step
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'validation_%s.npz' % name))
+    case = json.loads(str(z['meta']))
+    data_np, sd = build(case)
+    model = MultiViewMatcher({'multi_frame_matching': case['views'] > 2, 'GNN_layers': case['layers'], 'conf_mlp': True}).eval()
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model = model.cuda()
+    data = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
+    opt = types.SimpleNamespace(pose_loss=True, rot_weight=1.0, trans_weight=0.5)
+    with torch.no_grad():
+        losses, result = run_matcher(opt, data, model)
+    for k in ('match_loss', 'rot_loss', 'transl_loss'):
+        ours, r32, r64 = float(losses[k]), float(z[k + '_f32']), float(z[k + '_f64'])
+        tol = max(4.0 * abs(r32 - r64), 2e-4 * abs(r64))          # the reference's own fp32 noise is the yardstick
+        print(name, k, 'ours %.8g  ref fp32 %.8g  ref fp64 %.8g  tol %.3g' % (ours, r32, r64, tol))
+        assert abs(ours - r64) <= tol, (k, ours, r32, r64)
+    n_pairs = case['views'] * (case['views'] - 1) // 2
+    val, parts = validation_step(opt, data, model, n_pairs, 0.25)
+    expect = 0.75 * float(losses['match_loss']) / n_pairs + 0.25 * (float(losses['rot_loss']) + 0.5 * float(losses['transl_loss'])) / n_pairs
+    assert abs(float(val) - expect) <= 1e-5 * abs(expect)
