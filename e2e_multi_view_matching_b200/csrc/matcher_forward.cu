@@ -172,7 +172,7 @@ int mvm_matcher_forward_ex(const mvm_matcher_weights* w, int batch, int n_views,
   mvm_matcher_options o;
   if (opt) o = *opt; else mvm_matcher_options_default(&o);
   MVM_REQUIRE(o.math_mode == 0 || o.math_mode == 1 || o.math_mode == 3);
-  MVM_REQUIRE(o.sinkhorn_variant >= 0 && o.sinkhorn_variant <= 3);
+  MVM_REQUIRE(o.sinkhorn_variant >= 0 && o.sinkhorn_variant <= 4);
   MVM_REQUIRE(w && counts && kpts && kscores && desc && pairs && workspace);
   MVM_REQUIRE(batch >= 1 && n_views >= 2 && n_views <= MVM_MAX_VIEWS);
   MVM_REQUIRE(n_pad >= 64 && n_pad % 64 == 0);
@@ -360,7 +360,7 @@ int mvm_log_optimal_transport(float* scores, int batch, int m, int n, float bin_
 
 int mvm_log_optimal_transport_ex(float* scores, int batch, int m, int n, float bin_score, int iters, float* ws,
                                  int variant, void* stream) {
-  MVM_REQUIRE(scores && ws && batch >= 1 && m >= 1 && n >= 1 && variant >= 0 && variant <= 3);
+  MVM_REQUIRE(scores && ws && batch >= 1 && m >= 1 && n >= 1 && variant >= 0 && variant <= 4);
   PairTable tab;
   tab.n_pairs = 1; tab.n_views = 2; tab.a[0] = 0; tab.b[0] = 1; tab.m[0] = m; tab.n[0] = n;
   tab.scores[0] = scores; tab.ws_off[0] = 0;

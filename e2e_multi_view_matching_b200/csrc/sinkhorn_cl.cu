@@ -138,6 +138,23 @@ __device__ __forceinline__ int row16(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+// 32 values per lane, reduced over the 32 lanes in 31 shuffles; afterwards lane l holds the total of value index l.
+// All the exchanges of a level are independent (16, 8, 4, 2, 1 of them): the instruction-level parallelism the
+// two-row-groups-per-warp kernel needs with only four warps per scheduler.
+template <class Op>
+__device__ __forceinline__ float reduce32(float (&p)[32], int lane, Op op) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool hi = lane & w;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float send = hi ? p[k] : p[k + w], keep = hi ? p[k + w] : p[k];
+      p[k] = op(keep, __shfl_xor_sync(0xffffffffu, send, w));
+    }
+  }
+  return p[0];
+}
+
 // b_j of the thread's four columns; 1 beyond the last column (K~ is 0 there)
 __device__ __forceinline__ float4 load_b4(const float* b_s, int col0, int n) {
   float4 b4 = *reinterpret_cast<const float4*>(b_s + col0);
@@ -176,15 +193,21 @@ static_assert(OFF_KS % 4 == 0 && OFF_A % 4 == 0 && OFF_COLPART % 4 == 0 && OFF_A
 static_assert(OFF_MBAR % 2 == 0, "8-byte alignment of the mbarriers");
 inline size_t cl_smem_bytes(int n, int RS) { (void)n; return (size_t)(OFF_KS + 4 * RS * CL_MAXN) * sizeof(float); }
 
-template <int RR, bool TIMING>
-__global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, SinkClCfg cfg) {
+// RG = 16-row groups per warp: 1 (1024 threads, 64 registers each) or 2 (512 threads, 128 registers each: the same
+// K~ tile per SM, but the per-warp overhead of an iteration -- operand addresses the 64-register build keeps
+// rematerialising, b_j loads and masks, absorb checks, the a_i pass -- is paid once per 32 rows instead of once per
+// 16; the phase trace of r02 showed both passes issue-bound with 22 % of the instructions being the FMAs)
+template <int RR, int RG, bool TIMING>
+__global__ void __launch_bounds__(1024 / RG, 1) sinkhorn_cl_kernel(PairTable tab, SinkClCfg cfg) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RS = 16 - RR;
+  constexpr int NW = 32 / RG;                       // warps per CTA
   const int C = cfg.C;
   const unsigned c = cluster_ctarank();
   const int prob = blockIdx.x / C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rg = warp >> 3, cw = warp & 7;
+  const int rp = warp >> 3, cw = warp & 7;         // row groups rp * RG ... rp * RG + RG - 1, column strip cw
+#define RGI(g) (rp * RG + (g))
   const float alpha = cfg.alpha;
 
   const int p = prob / cfg.batch, bi = prob % cfg.batch;
@@ -210,22 +233,24 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
   float* const ea_s = smem + OFF_EA;
   float* const aw_s = smem + OFF_AW;
   float* const dust_s = smem + OFF_DUST;
-  float* const ksm = smem + OFF_KS + (size_t)rg * RS * LD + col0;   // this thread's shared-memory rows (i >= RR)
+  float* const ksm = smem + OFF_KS + (size_t)(rp * RG) * RS * LD + col0;   // this thread's shared-memory rows (i >= RR)
 
   const float mu = 1.0f / (float)(m + n), mu_bin = (float)n / (float)(m + n);
   const float nu = mu, nu_bin = (float)m / (float)(m + n);
   const float norm = -logf((float)(m + n));
 
-  float4 kreg[RR];
-#define K_GET(i) ((i) < RR ? kreg[(i) < RR ? (i) : 0] : *reinterpret_cast<const float4*>(ksm + ((i) - RR) * LD))
-#define K_PUT(i, v)                                                              \
+  float4 kreg[RG][RR];
+#define K_GET(g, i) ((i) < RR ? kreg[g][(i) < RR ? (i) : 0] : *reinterpret_cast<const float4*>(ksm + ((g) * RS + (i) - RR) * LD))
+#define K_PUT(g, i, v)                                                           \
   do {                                                                           \
-    if ((i) < RR) kreg[(i) < RR ? (i) : 0] = (v);                                \
-    else *reinterpret_cast<float4*>(ksm + ((i) - RR) * LD) = (v);                \
+    if ((i) < RR) kreg[g][(i) < RR ? (i) : 0] = (v);                             \
+    else *reinterpret_cast<float4*>(ksm + ((g) * RS + (i) - RR) * LD) = (v);     \
   } while (0)
 
   // ---- init: u~_i = -max(rowmax_i, alpha), v~ = 0, b = 1; K~ = exp(Z + u~) <= 1 ----
-  {
+#pragma unroll
+  for (int g = 0; g < RG; ++g) {
+    const int rg = RGI(g);
     float part[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -255,8 +280,10 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
   }
   __syncthreads();
 #pragma unroll
+  for (int g = 0; g < RG; ++g)
+#pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const int row = rg * 16 + i;
+    const int row = RGI(g) * 16 + i;
     float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active && row < nrows) {
       const float* zr = Zg + (long long)(r0 + row) * ld + col0;
@@ -266,7 +293,7 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
       if (col0 + 2 < n) k4.z = __expf(zr[2] + ut);
       if (col0 + 3 < n) k4.w = __expf(zr[3] + ut);
     }
-    if (active) K_PUT(i, k4);
+    if (active) K_PUT(g, i, k4);
   }
   // ---- exchange machinery: two transaction mbarriers per CTA.  mbar A completes when the C partials of every
   // column this CTA owns have landed in crecv; mbar B when all n+1 merged b_j have landed in b_s.  The values
@@ -289,11 +316,16 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
   const unsigned crecv_addr = smem_u32(crecv), b_addr = smem_u32(b_s);
   // column j = tid of this CTA's partial sums goes to slot (c, j - owner CS) of its owner (n <= 1024: one column per
   // thread; the dustbin column n is pushed by warp 31)
-  unsigned push_addr = 0, push_mbar = 0;
-  if (tid < n) {
-    const int owner = tid / CS, slot = tid - owner * CS;
-    push_addr = mapa_u32(crecv_addr + (unsigned)(((int)c * CS + slot) * 4), (unsigned)owner);
-    push_mbar = mapa_u32(mbarA, (unsigned)owner);
+  unsigned push_addr[RG], push_mbar[RG];
+#pragma unroll
+  for (int q = 0; q < RG; ++q) {
+    const int j = tid + q * (1024 / RG);
+    push_addr[q] = 0; push_mbar[q] = 0;
+    if (j < n) {
+      const int owner = j / CS, slot = j - owner * CS;
+      push_addr[q] = mapa_u32(crecv_addr + (unsigned)(((int)c * CS + slot) * 4), (unsigned)owner);
+      push_mbar[q] = mapa_u32(mbarA, (unsigned)owner);
+    }
   }
   unsigned tacc[6] = {0u, 0u, 0u, 0u, 0u, 0u};
   unsigned tprev = 0;
@@ -320,18 +352,32 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
       const float4 b4 = load_b4(b_s, col0, n);
       // column re-absorption is decided on the freshly merged b (identical in every CTA of the cluster)
       cbad = (fmaxf(fmaxf(b4.x, b4.y), fmaxf(b4.z, b4.w)) > ABSORB_HI) | (fminf(fminf(b4.x, b4.y), fminf(b4.z, b4.w)) < ABSORB_LO);
+      if (RG == 2) {
+        // all 32 row partials of the warp in one transposed reduction: lane l ends up with the strip total of row l
+        float part[32];
 #pragma unroll
-      for (int h8 = 0; h8 < 2; ++h8) {           // two groups of 8 rows: 8 partials live instead of 16
+        for (int g = 0; g < RG; ++g)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 k = K_GET(g, i);
+          part[g * 16 + i] = fmaf(k.w, b4.w, fmaf(k.z, b4.z, fmaf(k.y, b4.y, k.x * b4.x)));
+        }
+        const float v = reduce32(part, lane, OpSum());
+        rowpart[cw * CL_ROWS + rp * 32 + lane] = v;
+      } else {
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {           // groups of 8 rows: 8 partials live instead of 16
         float part[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 k = K_GET(h8 * 8 + i);
+          const float4 k = K_GET(0, h8 * 8 + i);
           part[i] = fmaf(k.w, b4.w, fmaf(k.z, b4.z, fmaf(k.y, b4.y, k.x * b4.x)));
         }
         const float v = reduce8(part, lane, OpSum());
-        if (!(lane & 3)) rowpart[cw * CL_ROWS + rg * 16 + h8 * 8 + row8(lane)] = v;
+        if (!(lane & 3)) rowpart[cw * CL_ROWS + RGI(0) * 16 + h8 * 8 + row8(lane)] = v;
       }
-      if (rg == 0) {   // dustbin row (replicated in every CTA): strip partial of sum_{j<n} kb_j b_j
+      }
+      if (rp == 0) {   // dustbin row (replicated in every CTA): strip partial of sum_{j<n} kb_j b_j
         const float4 kb4 = *reinterpret_cast<const float4*>(kb_s + col0);
         float d = 0.f;
         if (col0 + 0 < n) d = kb4.x * b4.x;
@@ -352,10 +398,12 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
       if (active) {
         const float4 b4 = load_b4(b_s, col0, n);
 #pragma unroll
+        for (int g = 0; g < RG; ++g)
+#pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float4 k = K_GET(i);
+          float4 k = K_GET(g, i);
           k.x *= b4.x; k.y *= b4.y; k.z *= b4.z; k.w *= b4.w;
-          K_PUT(i, k);
+          K_PUT(g, i, k);
         }
       }
       for (int j = tid; j <= n; j += blockDim.x) {
@@ -376,7 +424,8 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
     // ---- every warp: a_i = mu / (sum_j K~_ij b_j + e_i kb_n b_n) for the 16 rows of its row group ----
     float a_abs = 1.f;         // scaling absorbed into u~ this iteration (book-keeping by the strip-0 warp)
     if (active) {
-      const int rl = lane & 15, row = rg * 16 + rl;
+      // RG = 1: lanes 16-31 mirror lanes 0-15; RG = 2: lanes 0-15 take the warp's first row group, 16-31 the second
+      const int rl = lane & 15, row = RGI(RG == 2 ? (lane >> 4) : 0) * 16 + rl;
       float a_mine = 0.f, ea = 0.f;
       {
         float s = 0.f;
@@ -392,52 +441,61 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
       if (__any_sync(0xffffffffu, bad)) {
         // row re-absorption (every strip warp of the row group takes the same decision): K~ row *= a_i, a_i = 1
 #pragma unroll
+        for (int g = 0; g < RG; ++g)
+#pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float ai = __shfl_sync(0xffffffffu, a_mine, i);
-          if (__shfl_sync(0xffffffffu, (int)bad, i)) {
-            float4 k = K_GET(i);
+          const float ai = __shfl_sync(0xffffffffu, a_mine, g * 16 + i);
+          if (__shfl_sync(0xffffffffu, (int)bad, g * 16 + i)) {
+            float4 k = K_GET(g, i);
             k.x *= ai; k.y *= ai; k.z *= ai; k.w *= ai;
-            K_PUT(i, k);
+            K_PUT(g, i, k);
           }
         }
         if (bad) { a_abs = a_mine; a_mine = 1.f; }
       }
-      float* aw = aw_s + warp * 16;
-      if (lane < 16) {
+      float* aw = aw_s + warp * (16 * RG);
+      if (lane < 16 * RG) {
         aw[lane] = a_mine;
         if (cw == 0) { a_s[row] = a_mine; ea_s[row] = ea; }
       }
       __syncwarp();
-      // ---- column pass: partial c_j over this warp's 16 rows ----
+      // ---- column pass: partial c_j over this warp's 16 RG rows ----
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
+      for (int g = 0; g < RG; ++g)
+#pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 a4 = *reinterpret_cast<const float4*>(aw + q * 4);
+        const float4 a4 = *reinterpret_cast<const float4*>(aw + g * 16 + q * 4);
         const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const float4 k = K_GET(q * 4 + t);
+          const float4 k = K_GET(g, q * 4 + t);
           acc.x = fmaf(k.x, av[t], acc.x);
           acc.y = fmaf(k.y, av[t], acc.y);
           acc.z = fmaf(k.z, av[t], acc.z);
           acc.w = fmaf(k.w, av[t], acc.w);
         }
       }
-      *reinterpret_cast<float4*>(colpart + rg * CL_MAXN + col0) = acc;
+      *reinterpret_cast<float4*>(colpart + rp * CL_MAXN + col0) = acc;
     }
     T_MARK(2);
     __syncthreads();
-    if (cw == 0 && lane < 16 && a_abs != 1.f) {     // deferred: nobody reads e_s / ut_s before the next barrier
-      const int row = rg * 16 + lane;
+    if (cw == 0 && lane < 16 * RG && a_abs != 1.f) {     // deferred: nobody reads e_s / ut_s before the next barrier
+      const int row = RGI(RG == 2 ? (lane >> 4) : 0) * 16 + (lane & 15);
       ut_s[row] += logf(a_abs);
       e_s[row] *= a_abs;
     }
     // ---- this CTA's partial of column j goes to the CTA that owns column j ----
-    if (tid < n) {
-      const float s = ((colpart[tid] + colpart[CL_MAXN + tid]) + colpart[2 * CL_MAXN + tid]) + colpart[3 * CL_MAXN + tid];
-      st_async_f32(push_addr, s, push_mbar);
+#pragma unroll
+    for (int q = 0; q < RG; ++q) {
+      const int j = tid + q * (1024 / RG);
+      if (j < n) {
+        const float s = RG == 1 ? ((colpart[j] + colpart[CL_MAXN + j]) + colpart[2 * CL_MAXN + j]) + colpart[3 * CL_MAXN + j]
+                                : colpart[j] + colpart[CL_MAXN + j];
+        st_async_f32(push_addr[q], s, push_mbar[q]);
+      }
     }
-    if (warp == 31) {   // dustbin column: kb_n sum_i e_i a_i
+    if (warp == NW - 1) {   // dustbin column: kb_n sum_i e_i a_i
       float s = ea_s[lane] + ea_s[lane + 32];
       s = warp_sum(s);
       if (lane == 0) {
@@ -476,8 +534,10 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
   __syncthreads();
   if (active) {
 #pragma unroll
+    for (int g = 0; g < RG; ++g)
+#pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int row = rg * 16 + i;
+      const int row = RGI(g) * 16 + i;
       if (row < nrows) {
         const float u = ut_s[row] + logf(a_s[row]) - norm;
         float* zr = Zg + (long long)(r0 + row) * ld + col0;
@@ -494,19 +554,25 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_cl_kernel(PairTable tab, Sin
   }
 #undef K_GET
 #undef K_PUT
+#undef RGI
 }
 
 constexpr int CL_RR = 8;   // rows of every 16-row warp tile held in registers (default)
+int g_cl_default = 16;     // launch_sinkhorn_cluster's rr when the caller passes 0: 16 = two row groups per warp
+#define CL_DEFAULT g_cl_default
 
 void cl_set_attrs() {
   mvm_once_per_device(MVM_ONCE_SINKHORN_CL, [&] {
     const int smem = (int)mvm_dev_info().max_smem;
-    cudaFuncSetAttribute(sinkhorn_cl_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(sinkhorn_cl_kernel<8, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(sinkhorn_cl_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(sinkhorn_cl_kernel<6, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(sinkhorn_cl_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(sinkhorn_cl_kernel<6, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    auto set = [&](const void* k) {
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    };
+    set((const void*)sinkhorn_cl_kernel<8, 1, false>);
+    set((const void*)sinkhorn_cl_kernel<6, 1, false>);
+    set((const void*)sinkhorn_cl_kernel<6, 1, true>);
+    set((const void*)sinkhorn_cl_kernel<8, 2, false>);
+    set((const void*)sinkhorn_cl_kernel<8, 2, true>);
   });
 }
 
@@ -530,17 +596,20 @@ int launch_sinkhorn_cluster(const SinkhornTable& tab, int batch, float bin_score
     MVM_REQUIRE(tab.m[p] >= 1 && tab.n[p] >= 1 && tab.n[p] <= CL_MAXN && tab.m[p] <= C * CL_ROWS);
     max_n = tab.n[p] > max_n ? tab.n[p] : max_n;
   }
-  if (rr == 0) rr = CL_RR;
-  MVM_REQUIRE(rr == 6 || rr == 8);
-  const size_t smem = cl_smem_bytes(max_n, 16 - rr);
-  auto kern = rr == 8 ? sinkhorn_cl_kernel<8, false> : (g_sink_timing ? sinkhorn_cl_kernel<6, true> : sinkhorn_cl_kernel<6, false>);
+  if (rr == 0) rr = CL_DEFAULT;
+  MVM_REQUIRE(rr == 6 || rr == 8 || rr == 16);      // 16 = two row groups per warp (512 threads), 8 register rows each
+  const int rg = rr == 16 ? 2 : 1;
+  const size_t smem = cl_smem_bytes(max_n, 16 - (rr == 16 ? 8 : rr));
+  auto kern = rr == 16 ? (g_sink_timing ? sinkhorn_cl_kernel<8, 2, true> : sinkhorn_cl_kernel<8, 2, false>)
+              : rr == 8 ? sinkhorn_cl_kernel<8, 1, false>
+                        : (g_sink_timing ? sinkhorn_cl_kernel<6, 1, true> : sinkhorn_cl_kernel<6, 1, false>);
   cl_set_attrs();
   MVM_REQUIRE(smem <= mvm_dev_info().max_smem);
   SinkClCfg cfg;
   cfg.C = C; cfg.batch = batch; cfg.iters = iters; cfg.alpha = bin_score; cfg.timing = g_sink_timing;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(tab.n_pairs * batch * C));
-  lc.blockDim = dim3(1024);
+  lc.blockDim = dim3(1024 / rg);
   lc.dynamicSmemBytes = smem;
   lc.stream = stream;
   cudaLaunchAttribute at[1];
@@ -559,11 +628,11 @@ int launch_sinkhorn_cluster(const SinkhornTable& tab, int batch, float bin_score
 // Clusters of size C that can be co-resident on the current device with this kernel's footprint
 // (0: the size is not launchable here).  Used to pick the kernel and reported by bench.py.
 int sinkhorn_cluster_max_active(int C, int n) {
-  auto kern = sinkhorn_cl_kernel<CL_RR, false>;
+  auto kern = CL_DEFAULT == 16 ? sinkhorn_cl_kernel<CL_RR, 2, false> : sinkhorn_cl_kernel<CL_RR, 1, false>;
   cl_set_attrs();
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)(C * 64));
-  lc.blockDim = dim3(1024);
+  lc.blockDim = dim3(CL_DEFAULT == 16 ? 512 : 1024);
   lc.dynamicSmemBytes = cl_smem_bytes(n, 16 - CL_RR);
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;

@@ -225,7 +225,8 @@ extern "C" void mvm_debug_set_sinkhorn_timing(long long* p) { g_sink_timing = p;
 
 // Production dispatch: problems of up to 1024 x 1024 run on one hardware cluster each (sinkhorn_cl.cu);
 // larger ones (cfg4: 2048 keypoints, 16.8 MB per matrix) on the multi-CTA kernel below.
-// variant: 0 = automatic, 1 = force the multi-CTA kernel, 2 / 3 = force the cluster kernel (8 / 6 register rows).
+// variant: 0 = automatic (cluster kernel, two row groups per warp), 1 = force the multi-CTA kernel, 2 / 3 = cluster kernel
+// with one row group per warp (1024 threads; 8 / 6 register rows), 4 = cluster kernel with two row groups per warp.
 int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int iters, float* ws,
                     cudaStream_t stream, int variant) {
   MVM_REQUIRE(tab.n_pairs >= 1 && tab.n_pairs <= MVM_MAX_PAIRS && batch >= 1);
@@ -237,7 +238,7 @@ int launch_sinkhorn(const SinkhornTable& tab, int batch, float bin_score, int it
   if (variant != 1) {
     const int C = sinkhorn_cluster_size(mm, mn);
     if (C > 0 && sinkhorn_cluster_max_active(C, mn) > 0)
-      return launch_sinkhorn_cluster(tab, batch, bin_score, iters, C, stream, variant == 3 ? 6 : 0);
+      return launch_sinkhorn_cluster(tab, batch, bin_score, iters, C, stream, variant == 3 ? 6 : variant == 2 ? 8 : variant == 4 ? 16 : 0);
     MVM_REQUIRE(variant == 0);
   }
   return launch_sinkhorn_multicta(tab, batch, bin_score, iters, ws, stream);

@@ -118,7 +118,7 @@ def log_optimal_transport(scores, alpha, iters, ref_kernel=False, kernel=None):
     Z[:, :m, :n] = scores
     nws = lib.mvm_sinkhorn_workspace_floats(1, B, max(m, n))
     ws = torch.empty(nws, dtype=torch.float32, device=scores.device)
-    variants = {'multicta': 1, 'cluster': 2, 'cluster6': 3}
+    variants = {'multicta': 1, 'cluster': 2, 'cluster6': 3, 'cluster2': 4}
     if kernel in variants:
         rc = lib.mvm_log_optimal_transport_ex(_lib.ptr(Z), B, m, n, float(alpha), int(iters), _lib.ptr(ws),
                                               variants[kernel], _lib.stream_ptr())

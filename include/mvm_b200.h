@@ -203,7 +203,9 @@ int mvm_log_optimal_transport(float* scores, int batch, int m, int n, float bin_
                               int iters, float* ws, void* stream);
 /* variant 0 = what mvm_log_optimal_transport picks (one thread-block cluster per problem when m, n <= 1024 and
  * the device can co-schedule the cluster, else the multi-CTA kernel, launched cooperatively); 1 = multi-CTA
- * kernel; 2 / 3 = cluster kernel with 8 / 6 of every 16 rows in registers (fails when the problem does not fit). */
+ * kernel; 2 / 3 = cluster kernel, one 16-row group per warp (1024 threads) with 8 / 6 of every 16 rows in registers;
+ * 4 = cluster kernel, two row groups per warp (512 threads x 128 registers; the default of variant 0).  2-4 fail when
+ * the problem does not fit a cluster. */
 int mvm_log_optimal_transport_ex(float* scores, int batch, int m, int n, float bin_score, int iters,
                                  float* ws, int variant, void* stream);
 /* co-resident clusters the device offers for an m x n problem (0: the cluster kernel is not used) */

@@ -53,7 +53,7 @@ def test_sinkhorn_kernels_vs_oracle(shape, spread):
     rng = np.random.default_rng(m * 1000 + n)
     s = (rng.standard_normal((B, m, n)) * spread).astype(np.float32)
     ref = log_optimal_transport(s, 1.0, 100)
-    for kernel in ('ref', 'log', None):
+    for kernel in ('ref', 'log', None, 'cluster', 'cluster6', 'cluster2', 'multicta'):
         Z = ops.log_optimal_transport(torch.from_numpy(s).cuda(), 1.0, 100, kernel=kernel).cpu().numpy()
         err = np.abs(Z - ref)
         lim = (1e-4 if spread < 20 else 6e-4) + 1e-5 * np.abs(ref)

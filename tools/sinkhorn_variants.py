@@ -23,7 +23,7 @@ for (B, m, n, spread) in [(2, 60, 50, 1.0), (1, 300, 257, 12.0), (2, 128, 128, 4
     ref = log_optimal_transport(s, 1.0, 100)
     t_or = time.time() - t0
     line = '%dx%dx%d spread %g (oracle %.1fs):' % (B, m, n, spread, t_or)
-    for kernel in ('multicta', 'cluster', 'cluster6'):
+    for kernel in ('multicta', 'cluster', 'cluster6', 'cluster2'):
         Z = ops.log_optimal_transport(torch.from_numpy(s).cuda(), 1.0, 100, kernel=kernel).cpu().numpy()
         err = np.abs(Z - ref)
         line += '  %s %.2e (rel-excess %.2e)' % (kernel, err.max(), (err - 1e-5 * np.abs(ref)).max())
@@ -32,7 +32,7 @@ for (B, m, n, spread) in [(2, 60, 50, 1.0), (1, 300, 257, 12.0), (2, 128, 128, 4
 NP = int(sys.argv[1]) if len(sys.argv) > 1 else 140
 g = torch.Generator().manual_seed(0)
 s = (torch.randn(NP, 1024, 1024, generator=g) * 4).cuda()
-for kernel in ('multicta', 'cluster', 'cluster6'):
+for kernel in ('multicta', 'cluster', 'cluster6', 'cluster2'):
     for _ in range(2):
         ops.log_optimal_transport(s, 1.0, 100, kernel=kernel)
     torch.cuda.synchronize()
@@ -60,8 +60,8 @@ lib.mvm_debug_set_sinkhorn_timing.argtypes = [ctypes.c_void_p]
 lib.mvm_debug_set_sinkhorn_timing(ctypes.c_void_p(t.data_ptr()))
 s7 = s[:7].contiguous()
 for _ in range(2):
-    ops.log_optimal_transport(s7, 1.0, 100, kernel='cluster6')
+    ops.log_optimal_transport(s7, 1.0, 100, kernel='cluster2')
 torch.cuda.synchronize()
 names = ['row pass', 'barrier 1 (+col absorb)', 'a + col pass', 'barrier 2 + push', 'cluster sync 1 + merge', 'cluster sync 2']
-print('cluster6 phases, cycles per iteration:', {n: round(v / 100) for n, v in zip(names, t[:6].tolist())}, flush=True)
+print('cluster2 phases, cycles per iteration:', {n: round(v / 100) for n, v in zip(names, t[:6].tolist())}, flush=True)
 lib.mvm_debug_set_sinkhorn_timing(ctypes.c_void_p(0))
