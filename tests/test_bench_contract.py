@@ -51,6 +51,12 @@ def test_two_gpu_line_scales():
     assert two['value'] > 1.9 * one['value']             # whole-job aggregate, weak scaling
 
 
+def test_eight_gpu_line_scales():
+    one, eight = _load('bench_r02_v14.json'), _load('bench_r02_v15_8gpu.json')
+    assert eight['n_gpus'] == 8 and eight['run']['parallelism'] == 'dp8' and eight['scaling'] == 'weak'
+    assert eight['value'] > 0.95 * 8 * one['value']
+
+
 def test_pair_config_lines():
     for name, unit_min in (('bench_r02_v14_cfg2.json', 2000), ('bench_r02_v14_cfg4.json', 400)):
         d = _load(name)
