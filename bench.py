@@ -20,6 +20,15 @@ import time
 
 import numpy as np
 
+if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+    # multi-rank launch: NCCL's communicator lines ("comm ... rank R nranks N ... Init COMPLETE") go to the job log, so
+    # that whoever launched it can count the ranks that really joined.  Must be in the environment before torch loads
+    # NCCL (the debug level is latched at NCCL's first call); caller-set values win.
+    # (the GPU boxes of this project export NCCL_DEBUG=VERSION: the "NCCL version ..." line of the log is kept as is)
+    if 'NCCL_DEBUG' not in os.environ:
+        os.environ['NCCL_DEBUG'] = 'INFO'
+        os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -631,9 +640,20 @@ def main():
                 line['pose_auc_parity'] = pose_auc_parity(cfg, model, sd, dev)
             except Exception as e:
                 line['pose_auc_parity'] = {'error': repr(e)[:300]}
-        emit(line)
+        if world == 1:
+            emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # the JSON line must be the LAST line of the job's output: every other rank tears its communicator down (and
+        # NCCL logs that) first, rank 0 follows and prints
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
+        else:
+            time.sleep(2.0)
+            dist.destroy_process_group()
+            emit(line)
+            if os.environ.get('NCCL_DEBUG', '').upper() in ('INFO', 'TRACE'):
+                os._exit(0)          # NCCL logs its unload at interpreter exit: keep the JSON line last
 
 
 if __name__ == '__main__':
