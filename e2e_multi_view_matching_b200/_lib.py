@@ -82,6 +82,9 @@ def lib():
     L.mvm_gt_matches_workspace_bytes.argtypes = [C.c_int, C.c_int]
     L.mvm_gt_matches_pair.restype = C.c_int
     L.mvm_gt_matches_pair.argtypes = [_fp] * 7 + [C.c_int] * 4 + [C.c_float, C.c_float, _fp, _fp, _fp, C.c_size_t, _fp]
+    L.mvm_batchnorm_train.restype = C.c_int
+    L.mvm_batchnorm_train.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_int,
+                                      _fp, _fp, C.c_float, _fp, _fp]
     L.mvm_pack_views.restype = C.c_int
     L.mvm_pack_views.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int),
                                  C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]

@@ -358,6 +358,17 @@ int mvm_match_loss_forward(const float* log_p, const int64_t* gt_indices, const 
 int mvm_match_loss_backward(const int64_t* gt_indices, const float* gt_weights, const float* grad_loss, int bs, int ft,
                             float* grad_log_p, void* stream);
 
+/* BatchNorm1d in TRAINING mode on point-major activations x [rows, C] (row stride ld), in place, optionally followed by
+ * ReLU -- the MLPs of the train branch (multi_view_matcher.py:8-22 with self.training).  Statistics over the rows whose
+ * index inside their n_pad-row view slot is < n_valid, restricted to the slots s with s % slot_mod == slot_rem (1, 0 =
+ * every slot; the pairwise train path normalises each view separately); biased variance for the normalisation,
+ * running_mean / running_var (may both be NULL) updated with `momentum` and the unbiased variance like
+ * torch.nn.BatchNorm1d.  ws: 3 C doubles. */
+int mvm_batchnorm_train(float* x, int rows, int C, int ld, int n_pad, int n_valid, int slot_mod, int slot_rem,
+                        const float* gamma,
+                        const float* beta, float eps, int relu, float* running_mean, float* running_var,
+                        float momentum, double* ws, void* stream);
+
 /* compute_gt_matches_of_image_pair (helpers.py:121-203, with transform_kpts :115-119 and set_weight :205-213):
  * ground-truth assignment of an image pair from depth maps and poses, without the [bs, N, N] error matrix.
  * kpts0/1 [bs, n, 2] pixel x,y (truncated like .long()); K0/K1, T0to1 [bs, 4, 4]; depth0/1 [bs, H, W];
