@@ -82,9 +82,23 @@ def lib():
     L.mvm_gt_matches_workspace_bytes.argtypes = [C.c_int, C.c_int]
     L.mvm_gt_matches_pair.restype = C.c_int
     L.mvm_gt_matches_pair.argtypes = [_fp] * 7 + [C.c_int] * 4 + [C.c_float, C.c_float, _fp, _fp, _fp, C.c_size_t, _fp]
-    L.mvm_batchnorm_train.restype = C.c_int
-    L.mvm_batchnorm_train.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_float, C.c_int,
-                                      _fp, _fp, C.c_float, _fp, _fp]
+    I, F = C.c_int, C.c_float
+    L.mvm_batchnorm_train.restype = I
+    L.mvm_batchnorm_train.argtypes = [_fp, _fp, I, I, I, I, I, I, I, _fp, _fp, F, I, _fp, _fp, F, _fp, _fp, _fp]
+    L.mvm_batchnorm_train_backward.restype = I
+    L.mvm_batchnorm_train_backward.argtypes = [_fp, _fp, _fp, I, I, I, I, I, I, I, _fp, _fp, I, _fp, _fp, I, _fp, _fp]
+    L.mvm_colsum.restype = I
+    L.mvm_colsum.argtypes = [_fp, I, I, I, _fp, I, _fp, _fp]
+    L.mvm_transpose_split.restype = I
+    L.mvm_transpose_split.argtypes = [_fp, I, I, I, _fp, _fp, _fp, C.c_longlong, _fp]
+    L.mvm_attention_backward.restype = I
+    L.mvm_attention_backward.argtypes = [_fp, _fp, _fp, _fp, _fp, I, I, I, C.POINTER(C.c_int), I, _fp]
+    L.mvm_sinkhorn_train_pot_floats.restype = C.c_size_t
+    L.mvm_sinkhorn_train_pot_floats.argtypes = [I, I, I, I]
+    L.mvm_sinkhorn_train_forward.restype = I
+    L.mvm_sinkhorn_train_forward.argtypes = [_fp, _fp, I, I, I, I, _fp, _fp, _fp]
+    L.mvm_sinkhorn_train_backward.restype = I
+    L.mvm_sinkhorn_train_backward.argtypes = [_fp, _fp, _fp, I, I, I, I, _fp, _fp, _fp]
     L.mvm_pack_views.restype = C.c_int
     L.mvm_pack_views.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int),
                                  C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]
@@ -189,6 +203,19 @@ def lib():
 def check(status, what):
     if status != 0:
         raise MvmError('%s failed: %s (status %d)' % (what, _STATUS.get(status, 'unknown'), status))
+
+
+def require_cuda(device, what):
+    """There is no CPU fallback: every entry point refuses non-CUDA tensors."""
+    if device.type != 'cuda':
+        raise MvmError('%s needs CUDA tensors (no CPU fallback)' % what)
+
+
+def device_ctx(device):
+    """Context that makes `device` the current CUDA device for the launches inside it."""
+    import contextlib
+    import torch
+    return torch.cuda.device(device) if device.type == 'cuda' else contextlib.nullcontext()
 
 
 def stream_ptr():

@@ -214,16 +214,16 @@ class MultiViewMatcher(nn.Module):
     def forward(self, data):
         if self.training:
             # batch-statistics BatchNorm cannot be folded into the packed weights: the train branch sequences the stage
-            # kernels (models/train_forward.py).  Forward only -- the outputs do not require grad.
+            # kernels (models/train_forward.py); with autograd enabled the `scores_*` outputs carry the graph of
+            # MatcherTrainFn, so loss.backward() fills the parameters' .grad like the reference's autograd does.
             from .train_forward import train_forward
-            with torch.no_grad():
-                if self.config['multi_frame_matching']:
-                    return train_forward(self, data)
-                result = {}
-                for id1 in range(len(data['ids'])):
-                    for id0 in range(id1):
-                        result.update(train_forward(self, data, view_ids=[id0, id1]))
-                return result
+            if self.config['multi_frame_matching']:
+                return train_forward(self, data)
+            result = {}
+            for id1 in range(len(data['ids'])):
+                for id0 in range(id1):
+                    result.update(train_forward(self, data, view_ids=[id0, id1]))
+            return result
         tuple_size = len(data['ids'])
         dev = data['keypoints0'].device
         if dev.type != 'cuda':

@@ -147,3 +147,170 @@ def extract_matches(Z, match_threshold=0.0):
                                  _lib.ptr(m1_), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(ws), _lib.stream_ptr())
     _lib.check(rc, 'mvm_extract_matches')
     return m0, m1_, s0, s1
+
+
+# ---- training-path stage ops: operand staging + backward GEMMs, BatchNorm, attention, Sinkhorn -------
+
+def pack_views(views, n_pad):
+    """views: [(keypoints [B, N, 2], scores [B, N], descriptors [B, 256, N])] per view -> the zero-padded view-slot-major
+    buffers kpts [B, T, n_pad, 2], scores [B, T, n_pad], desc [B, T, 256, n_pad] (mvm_pack_views, one launch)."""
+    lib = _lib.lib()
+    T = len(views)
+    B = views[0][0].shape[0]
+    dev = views[0][0].device
+    kp = torch.empty(B, T, n_pad, 2, dtype=torch.float32, device=dev)
+    sc = torch.empty(B, T, n_pad, dtype=torch.float32, device=dev)
+    de = torch.empty(B, T, 256, n_pad, dtype=torch.float32, device=dev)
+    ptrs = [(C.c_void_p * T)(*[v[i].data_ptr() for v in views]) for i in range(3)]
+    counts = (C.c_int * T)(*[v[0].shape[1] for v in views])
+    _lib.check(lib.mvm_pack_views(ptrs[0], ptrs[1], ptrs[2], counts, B, T, n_pad, _lib.ptr(kp), _lib.ptr(sc), _lib.ptr(de),
+                                  _lib.stream_ptr()), 'mvm_pack_views')
+    return kp, sc, de
+
+
+def transpose_split(x, raw=False, planes=True, out=None):
+    """x [R, C] -> ([C, R] raw copy or None, tf32 hi plane or None, lo plane or None) of x^T (mvm_transpose_split).
+    out: optional (raw, hi, lo) destination views with row stride `ldo` = out[..].stride(0) (concat-by-rows staging)."""
+    lib = _lib.lib()
+    R, Cc = x.shape
+    assert x.stride(1) == 1
+    if out is None:
+        r = torch.empty(Cc, R, dtype=torch.float32, device=x.device) if raw else None
+        h = torch.empty(Cc, R, dtype=torch.float32, device=x.device) if planes else None
+        l = torch.empty(Cc, R, dtype=torch.float32, device=x.device) if planes else None
+    else:
+        r, h, l = out
+    ldo = (r if r is not None else h).stride(0)
+    _lib.check(lib.mvm_transpose_split(_lib.ptr(x), R, Cc, x.stride(0), _lib.ptr(r), _lib.ptr(h), _lib.ptr(l), ldo,
+                                       _lib.stream_ptr()), 'mvm_transpose_split')
+    return r, h, l
+
+
+def linear_presplit(a, w_hi, w_lo, residual=None, alpha=1.0):
+    """alpha * a [M, K] @ w^T + residual with w [N, K] given as its tf32 planes: the 3xTF32 tcgen05 GEMM (fp32 range --
+    the half-precision planes of the inference path would flush small gradients)."""
+    lib = _lib.lib()
+    M, K = a.shape
+    N = w_hi.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    rc = lib.mvm_linear_tc_presplit(_lib.ptr(a), a.stride(0), None, 0, K, _lib.ptr(w_hi), _lib.ptr(w_lo), w_hi.stride(0),
+                                    None, _lib.ptr(residual), residual.stride(0) if residual is not None else 0,
+                                    _lib.ptr(out), N, M, N, K, float(alpha), 0, _lib.stream_ptr())
+    _lib.check(rc, 'mvm_linear_tc_presplit')
+    return out
+
+
+def gemm_dx(dy, w, residual=None, alpha=1.0):
+    """Gradient w.r.t. the input of y = x @ w^T: dy [M, N_out] @ w [N_out, K_in] (+ residual) -> [M, K_in]."""
+    n_out, k_in = w.shape
+    w = w.detach().float().contiguous()
+    if k_in % 128 == 0 and n_out % 32 == 0:
+        _, hi, lo = transpose_split(w)
+        return linear_presplit(dy, hi, lo, residual=residual, alpha=alpha)
+    wt, _, _ = transpose_split(w, raw=True, planes=False)
+    return linear(dy, wt, residual=residual, alpha=alpha, tc_passes=0)
+
+
+def gemm_dw(dy, x, x2=None, alpha=1.0):
+    """Gradient w.r.t. the weight of y = [x | x2] @ w^T: dy^T [N_out, rows] @ [x | x2] [rows, K_in] -> [N_out, K_in]."""
+    rows, n_out = dy.shape
+    k1 = x.shape[1]
+    k_in = k1 + (x2.shape[1] if x2 is not None else 0)
+    dyt, _, _ = transpose_split(dy, raw=True, planes=False)
+    tc = k_in % 128 == 0 and rows % 32 == 0
+    dev = dy.device
+    if tc:
+        hi = torch.empty(k_in, rows, dtype=torch.float32, device=dev)
+        lo = torch.empty(k_in, rows, dtype=torch.float32, device=dev)
+        transpose_split(x, out=(None, hi[:k1], lo[:k1]))
+        if x2 is not None:
+            transpose_split(x2, out=(None, hi[k1:], lo[k1:]))
+        return linear_presplit(dyt, hi, lo, alpha=alpha)
+    xt = torch.empty(k_in, rows, dtype=torch.float32, device=dev)
+    transpose_split(x, out=(xt[:k1], None, None))
+    if x2 is not None:
+        transpose_split(x2, out=(xt[k1:], None, None))
+    return linear(dyt, xt, alpha=alpha, tc_passes=0)
+
+
+def colsum(x):
+    """x [rows, C] -> [C] column sums (bias gradient)."""
+    lib = _lib.lib()
+    rows, Cc = x.shape
+    out = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    ws = torch.empty(Cc, dtype=torch.float64, device=x.device)
+    _lib.check(lib.mvm_colsum(_lib.ptr(x), rows, Cc, x.stride(0), _lib.ptr(out), 0, _lib.ptr(ws), _lib.stream_ptr()),
+               'mvm_colsum')
+    return out
+
+
+def batchnorm_train(x, weight, bias, running_mean, running_var, momentum, eps, n_pad, n_valid, relu=True, groups=1,
+                    out=None, save=False):
+    """BatchNorm1d (+ReLU) in training mode on x [rows, C] -> (out (default: in place), stats [groups, 2C] or None)."""
+    lib = _lib.lib()
+    rows, Cc = x.shape
+    assert x.is_contiguous()
+    y = x if out is None else out
+    stats = torch.empty(groups, 2 * Cc, dtype=torch.float32, device=x.device) if save else None
+    ws = torch.empty(3 * Cc, dtype=torch.float64, device=x.device)
+    for g in range(groups):
+        _lib.check(lib.mvm_batchnorm_train(_lib.ptr(x), _lib.ptr(y), rows, Cc, x.stride(0), n_pad, n_valid, groups, g,
+                                           _lib.ptr(weight), _lib.ptr(bias), float(eps), int(relu), _lib.ptr(running_mean),
+                                           _lib.ptr(running_var), float(momentum),
+                                           _lib.ptr(stats[g]) if save else None, _lib.ptr(ws), _lib.stream_ptr()),
+                   'mvm_batchnorm_train')
+    return y, stats
+
+
+def batchnorm_train_backward(x, y, dy, weight, stats, n_pad, n_valid, relu=True):
+    """In place on dy (gradient w.r.t. y -> gradient w.r.t. x); -> (dgamma, dbeta)."""
+    lib = _lib.lib()
+    rows, Cc = x.shape
+    groups = stats.shape[0]
+    dg = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    db = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    ws = torch.empty(2 * Cc, dtype=torch.float64, device=x.device)
+    assert x.is_contiguous() and dy.is_contiguous() and y.is_contiguous()
+    for g in range(groups):
+        _lib.check(lib.mvm_batchnorm_train_backward(_lib.ptr(x), _lib.ptr(y), _lib.ptr(dy), rows, Cc, x.stride(0), n_pad,
+                                                    n_valid, groups, g, _lib.ptr(weight), _lib.ptr(stats[g]), int(relu),
+                                                    _lib.ptr(dg), _lib.ptr(db), int(g > 0), _lib.ptr(ws),
+                                                    _lib.stream_ptr()), 'mvm_batchnorm_train_backward')
+    return dg, db
+
+
+def attention_backward(qkv, out, dout, batch, n_views, counts, is_cross):
+    """qkv [V, n_pad, 768], out / dout [V, n_pad, 256] -> dqkv [V, n_pad, 768] (mvm_attention_backward)."""
+    lib = _lib.lib()
+    V, n_pad, _ = qkv.shape
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty(2 * V * 4 * n_pad, dtype=torch.float32, device=qkv.device)
+    cnt = (C.c_int * n_views)(*counts)
+    assert qkv.is_contiguous() and out.is_contiguous() and dout.is_contiguous()
+    _lib.check(lib.mvm_attention_backward(_lib.ptr(qkv), _lib.ptr(out), _lib.ptr(dout), _lib.ptr(dqkv), _lib.ptr(ws), batch,
+                                          n_views, n_pad, cnt, int(is_cross), _lib.stream_ptr()), 'mvm_attention_backward')
+    return dqkv
+
+
+def sinkhorn_train_forward(scores, alpha, iters):
+    """scores [B, m, n], alpha: device scalar tensor -> (couplings [B, m+1, n+1], potentials of every iteration)."""
+    lib = _lib.lib()
+    B, m, n = scores.shape
+    assert scores.is_contiguous() and alpha.dtype == torch.float32 and alpha.device == scores.device
+    Z = torch.empty(B, m + 1, n + 1, dtype=torch.float32, device=scores.device)
+    pot = torch.empty(lib.mvm_sinkhorn_train_pot_floats(B, m, n, iters), dtype=torch.float32, device=scores.device)
+    _lib.check(lib.mvm_sinkhorn_train_forward(_lib.ptr(scores), _lib.ptr(alpha), B, m, n, int(iters), _lib.ptr(Z),
+                                              _lib.ptr(pot), _lib.stream_ptr()), 'mvm_sinkhorn_train_forward')
+    return Z, pot
+
+
+def sinkhorn_train_backward(scores, alpha, pot, iters, grad_out):
+    """-> (dZ [B, m+1, n+1]: gradient w.r.t. the augmented score matrix, d_alpha: [1] float64)."""
+    lib = _lib.lib()
+    B, m, n = scores.shape
+    dZ = grad_out.detach().float().contiguous().clone()
+    d_alpha = torch.zeros(1, dtype=torch.float64, device=scores.device)
+    _lib.check(lib.mvm_sinkhorn_train_backward(_lib.ptr(scores), _lib.ptr(alpha), _lib.ptr(pot), B, m, n, int(iters),
+                                               _lib.ptr(dZ), _lib.ptr(d_alpha), _lib.stream_ptr()),
+               'mvm_sinkhorn_train_backward')
+    return dZ, d_alpha

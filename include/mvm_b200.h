@@ -358,16 +358,46 @@ int mvm_match_loss_forward(const float* log_p, const int64_t* gt_indices, const 
 int mvm_match_loss_backward(const int64_t* gt_indices, const float* gt_weights, const float* grad_loss, int bs, int ft,
                             float* grad_log_p, void* stream);
 
-/* BatchNorm1d in TRAINING mode on point-major activations x [rows, C] (row stride ld), in place, optionally followed by
- * ReLU -- the MLPs of the train branch (multi_view_matcher.py:8-22 with self.training).  Statistics over the rows whose
+/* BatchNorm1d in TRAINING mode on point-major activations x -> y [rows, C] (row stride ld; y may be x), optionally followed
+ * by ReLU -- the MLPs of the train branch (multi_view_matcher.py:8-22 with self.training).  Statistics over the rows whose
  * index inside their n_pad-row view slot is < n_valid, restricted to the slots s with s % slot_mod == slot_rem (1, 0 =
  * every slot; the pairwise train path normalises each view separately); biased variance for the normalisation,
  * running_mean / running_var (may both be NULL) updated with `momentum` and the unbiased variance like
- * torch.nn.BatchNorm1d.  ws: 3 C doubles. */
-int mvm_batchnorm_train(float* x, int rows, int C, int ld, int n_pad, int n_valid, int slot_mod, int slot_rem,
-                        const float* gamma,
-                        const float* beta, float eps, int relu, float* running_mean, float* running_var,
-                        float momentum, double* ws, void* stream);
+ * torch.nn.BatchNorm1d.  save_stats (may be NULL): [2 C] = mean | 1 / sqrt(var + eps) for the backward.  ws: 3 C doubles. */
+int mvm_batchnorm_train(const float* x, float* y, int rows, int C, int ld, int n_pad, int n_valid, int slot_mod,
+                        int slot_rem, const float* gamma, const float* beta, float eps, int relu, float* running_mean,
+                        float* running_var, float momentum, float* save_stats, double* ws, void* stream);
+/* its backward (what autograd computes for BatchNorm1d(+ReLU) in training mode): dy holds the gradient w.r.t. y on entry
+ * and the gradient w.r.t. x on return (rows outside the statistics are left untouched); x = the forward's input, y = its
+ * output (ReLU mask; may be NULL when relu == 0); dgamma / dbeta [C] are overwritten or, with accumulate != 0, added to.
+ * ws: 2 C doubles. */
+int mvm_batchnorm_train_backward(const float* x, const float* y, float* dy, int rows, int C, int ld, int n_pad, int n_valid,
+                                 int slot_mod, int slot_rem, const float* gamma, const float* save_stats, int relu,
+                                 float* dgamma, float* dbeta, int accumulate, double* ws, void* stream);
+/* out[c] (+)= sum_r x[r, c]: the bias gradient of a Conv1d(k=1) from the gradient of its output.  ws: C doubles. */
+int mvm_colsum(const float* x, int rows, int C, int ld, float* out, int accumulate, double* ws, void* stream);
+/* x [R, C] (row stride ld) -> transposed copies [C, R] (row stride ldo): raw (may be NULL) and / or the tf32 planes
+ * hi = rn_tf32(x), lo = rn_tf32(x - hi) (both or neither) that mvm_linear_tc_presplit takes as its W operand: the operand
+ * staging of the backward GEMMs (dX = dY W: W^T planes; dW = dY^T X: dY^T raw and X^T planes). */
+int mvm_transpose_split(const float* x, int R, int C, int ld, float* raw, float* hi, float* lo, long long ldo, void* stream);
+
+/* Backward of the multi-head attention with multi-view key segments (autograd of superglue.py:87-109 with the sources of
+ * multi_view_matcher.py:65-86): qkv [batch*n_views, n_pad, 768] (q | k | v, head-contiguous, as mvm_attention takes it),
+ * out = the forward's output and dout the gradient w.r.t. it, both [batch*n_views, n_pad, 256] -> dqkv like qkv.  Rows
+ * beyond counts[t] are masked (zero gradient).  ws: 2 * batch*n_views * 4 * n_pad floats.  Deterministic. */
+int mvm_attention_backward(const float* qkv, const float* out, const float* dout, float* dqkv, float* ws, int batch,
+                           int n_views, int n_pad, const int* counts, int is_cross, void* stream);
+
+/* log_optimal_transport for training (superglue.py:143-172): scores [batch, m, n] and the device scalar alpha
+ * (bin_score) -> couplings out [batch, m+1, n+1], keeping the potentials of every iteration in pot
+ * (mvm_sinkhorn_train_pot_floats floats); the backward turns dZ (gradient w.r.t. the couplings on entry) into the exact
+ * gradient of the unrolled iterations w.r.t. the augmented score matrix (inner block = d scores) and adds the dustbin
+ * entries to *d_alpha (device double, zeroed by the caller). */
+size_t mvm_sinkhorn_train_pot_floats(int batch, int m, int n, int iters);
+int mvm_sinkhorn_train_forward(const float* scores, const float* alpha, int batch, int m, int n, int iters, float* out,
+                               float* pot, void* stream);
+int mvm_sinkhorn_train_backward(const float* scores, const float* alpha, const float* pot, int batch, int m, int n,
+                                int iters, float* dZ, double* d_alpha, void* stream);
 
 /* compute_gt_matches_of_image_pair (helpers.py:121-203, with transform_kpts :115-119 and set_weight :205-213):
  * ground-truth assignment of an image pair from depth maps and poses, without the [bs, N, N] error matrix.

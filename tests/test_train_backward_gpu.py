@@ -1,0 +1,168 @@
+"""TRAINING-path kernels: every backward / staging kernel against the float64 torch stand-ins of
+tests/emul_ops.py on seeded inputs, then the whole training step (MatcherTrainFn forward + backward on the kernels, the
+CUDA match loss) against the gradients of the unmodified reference (tests/golden/train_backward_*.npz)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import emul_ops
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _rel(got, ref):
+    ref = ref.double()
+    return float((got.double().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('is_cross,counts', [(0, [128, 128]), (1, [128, 128, 128]), (1, [100, 100, 100, 100]), (0, [70, 128, 33]),
+                                             (1, [70, 128, 33])])
+def test_attention_backward_vs_torch(is_cross, counts):
+    from e2e_multi_view_matching_b200 import ops
+    g = torch.Generator().manual_seed(5 + is_cross + len(counts))
+    T, B, n_pad = len(counts), 2, 128
+    qkv = torch.randn(B * T, n_pad, 768, generator=g) * 1.5
+    dout = torch.randn(B * T, n_pad, 256, generator=g)
+    for v in range(B * T):
+        dout[v, counts[v % T]:] = 0          # the gradient of padding rows is zero by construction
+    out = emul_ops.attention(qkv, B, T, counts, is_cross)
+    ref = emul_ops.attention_backward(qkv, out, dout, B, T, counts, is_cross)
+    got = ops.attention_backward(qkv.cuda(), out.cuda(), dout.cuda(), B, T, counts, is_cross)
+    torch.cuda.synchronize()
+    for name, lo in (('dq', 0), ('dk', 256), ('dv', 512)):
+        e = _rel(got[:, :, lo:lo + 256], ref[:, :, lo:lo + 256])
+        print('attention backward', 'cross' if is_cross else 'self', counts, name, 'rel err %.2e' % e)
+        assert e < 2e-5, (name, e)
+    for v in range(B * T):
+        assert float(got[v, counts[v % T]:].abs().max()) == 0.0 if counts[v % T] < n_pad else True
+
+
+@pytest.mark.parametrize('groups,relu', [(1, True), (2, True), (1, False)])
+def test_batchnorm_train_forward_backward_vs_torch(groups, relu):
+    from e2e_multi_view_matching_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    n_pad, n_valid, slots, C = 128, 100, 6, 96
+    rows = slots * n_pad
+    x = torch.randn(rows, C, generator=g) * 3 + 1
+    w, b = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    dy = torch.randn(rows, C, generator=g)
+    dy.view(slots, n_pad, C)[:, n_valid:] = 0
+    rm, rv = torch.zeros(C), torch.ones(C)
+    y_ref, st_ref = emul_ops.batchnorm_train(x, w, b, rm, rv, 0.1, 1e-5, n_pad, n_valid, relu=relu, groups=groups,
+                                             out=torch.zeros_like(x), save=True)
+    dx_ref = dy.clone()
+    dg_ref, db_ref = emul_ops.batchnorm_train_backward(x, y_ref, dx_ref, w, st_ref, n_pad, n_valid, relu=relu)
+    rmc, rvc = torch.zeros(C).cuda(), torch.ones(C).cuda()
+    xc = x.cuda()
+    y, st = ops.batchnorm_train(xc, w.cuda(), b.cuda(), rmc, rvc, 0.1, 1e-5, n_pad, n_valid, relu=relu, groups=groups,
+                                out=torch.zeros_like(xc), save=True)
+    dx = dy.cuda()
+    dg, db = ops.batchnorm_train_backward(xc, y, dx, w.cuda(), st, n_pad, n_valid, relu=relu)
+    torch.cuda.synchronize()
+    assert _rel(y, y_ref) < 1e-5 and _rel(st, st_ref) < 1e-5
+    assert _rel(rmc, rm) < 1e-5 and _rel(rvc, rv) < 1e-5
+    assert _rel(dx, dx_ref) < 2e-5, _rel(dx, dx_ref)
+    assert _rel(dg, dg_ref) < 2e-5 and _rel(db, db_ref) < 2e-5
+
+
+@pytest.mark.parametrize('m,n,spread', [(64, 64, 3.0), (100, 100, 30.0), (37, 90, 10.0)])
+def test_sinkhorn_train_vs_autograd(m, n, spread):
+    from e2e_multi_view_matching_b200 import ops
+    g = torch.Generator().manual_seed(m + n)
+    B, iters = 3, 100
+    scores = torch.randn(B, m, n, generator=g) * spread
+    alpha = torch.tensor([1.3])
+    G = torch.randn(B, m + 1, n + 1, generator=g)
+    Z_ref, _ = emul_ops.sinkhorn_train_forward(scores, alpha, iters)
+    dZ_ref, da_ref = emul_ops.sinkhorn_train_backward(scores, alpha, None, iters, G)
+    Z, pot = ops.sinkhorn_train_forward(scores.cuda(), alpha.cuda(), iters)
+    dZ, da = ops.sinkhorn_train_backward(scores.cuda(), alpha.cuda(), pot, iters, G.cuda())
+    torch.cuda.synchronize()
+    ez = float((Z.cpu().double() - Z_ref.double()).abs().max())
+    eg = _rel(dZ[:, :m, :n], dZ_ref[:, :m, :n])
+    ea = abs(float(da) - float(da_ref)) / max(abs(float(da_ref)), 1e-12)
+    print('sinkhorn train %dx%d spread %.0f: couplings abs err %.2e, d scores rel err %.2e, d alpha rel err %.2e' % (m, n, spread, ez, eg, ea))
+    assert ez < 2e-4 * max(1.0, spread) and eg < 2e-4 and ea < 2e-4
+
+
+@pytest.mark.parametrize('rows,n_out,k_in,k2', [(384, 256, 256, 0), (896, 512, 256, 256), (384, 768, 256, 0), (384, 64, 32, 0),
+                                                (384, 32, 16, 0), (384, 256, 128, 0)])
+def test_backward_gemms_vs_fp64(rows, n_out, k_in, k2):
+    from e2e_multi_view_matching_b200 import ops
+    g = torch.Generator().manual_seed(rows + n_out)
+    dy = torch.randn(rows, n_out, generator=g) * 1e-3          # gradients are small: the 3xTF32 path keeps the fp32 range
+    x = torch.randn(rows, k_in, generator=g)
+    x2 = torch.randn(rows, k2, generator=g) if k2 else None
+    w = torch.randn(n_out, k_in + k2, generator=g) * 0.1
+    res = torch.randn(rows, k_in + k2, generator=g) * 1e-4
+    dx = ops.gemm_dx(dy.cuda(), w.cuda(), residual=res.cuda())
+    dw = ops.gemm_dw(dy.cuda(), x.cuda(), x2.cuda() if k2 else None)
+    torch.cuda.synchronize()
+    dx_ref = dy.double() @ w.double() + res.double()
+    dw_ref = dy.double().t() @ (torch.cat([x, x2], 1) if k2 else x).double()
+    assert _rel(dx, dx_ref) < 1e-5, _rel(dx, dx_ref)
+    assert _rel(dw, dw_ref) < 1e-5, _rel(dw, dw_ref)
+    cs = ops.colsum(dy.cuda())
+    assert _rel(cs, dy.double().sum(0)) < 1e-5
+
+
+def _golden_case(name):
+    from oracle.make_train_backward_golden import build
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    z = np.load(os.path.join(GOLDEN, 'train_backward_%s.npz' % name))
+    case = json.loads(str(z['meta']))
+    data_np, sd = build(case)
+    model = MultiViewMatcher({'multi_frame_matching': case['multi'], 'GNN_layers': case['layers'], 'conf_mlp': True,
+                              'full_output': False})
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    data = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
+    return z, case, model.cuda().train(), data
+
+
+def _loss(case, model, data):
+    from e2e_multi_view_matching_b200.training import compute_match_loss
+    result = model(data)
+    loss = 0.0
+    for b in range(case['views']):
+        for a in range(b):
+            key = '%d_%d' % (a, b)
+            loss = loss + compute_match_loss(result['scores_' + key], data['gt_indices_' + key], data['gt_weights_' + key])
+    return loss
+
+
+@pytest.mark.parametrize('name', ['mv3_64', 'mv4_100', 'pair_96'])
+def test_train_step_vs_reference_golden(name):
+    """loss.backward() through the kernels == the reference's autograd: every parameter gradient within 8x the
+    reference's own fp32-vs-fp64 deviation (+ 1e-4 of the gradient's scale) of the reference's fp64 run."""
+    from tests.test_train_host_logic import check_gradients
+    z, case, model, data = _golden_case(name)
+    loss = _loss(case, model, data)
+    noise = abs(float(z['loss_f32']) - float(z['loss_f64']))
+    assert abs(float(loss) - float(z['loss_f64'])) <= 8 * noise + 2e-5 * abs(float(z['loss_f64'])), (float(loss), float(z['loss_f64']))
+    loss.backward()
+    torch.cuda.synchronize()
+    worst = check_gradients(model, z, tol_noise=8.0, tol_rel=1e-4, what=name)
+    print(name, 'loss %.6f (reference fp64 %.6f, fp32 %.6f); worst gradient error / tolerance %.3f at %s'
+          % (float(loss), float(z['loss_f64']), float(z['loss_f32']), worst[0], worst[1]))
+
+
+def test_training_loop_reduces_the_loss():
+    """A few optimiser steps on one batch through model(data) / loss.backward() / torch.optim: the loss goes down and the
+    eval forward afterwards runs on the updated weights."""
+    z, case, model, data = _golden_case('mv3_64')
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        loss = _loss(case, model, data)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    print('match loss over 6 Adam steps:', ['%.1f' % v for v in losses])
+    assert losses[-1] < 0.9 * losses[0] and all(np.isfinite(losses))
+    out = model.eval()(data)
+    assert torch.isfinite(out['scores_0_1']).all()

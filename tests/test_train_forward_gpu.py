@@ -92,10 +92,13 @@ def test_train_forward_output_gating_and_eval_unchanged():
     model = _model(case, sd, full_output=False)
     data = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
     res = model(data)
-    assert sorted(res) == ['scores_0_1', 'scores_0_2', 'scores_1_2'] and not res['scores_0_1'].requires_grad
+    assert sorted(res) == ['scores_0_1', 'scores_0_2', 'scores_1_2'] and res['scores_0_1'].requires_grad   # MatcherTrainFn graph
+    with torch.no_grad():
+        assert not model(data)['scores_0_1'].requires_grad
     rm = model.kenc.encoder[1].running_mean.clone()
     before = model.eval()(data)['scores_0_1'].clone()
-    model.train()(data)                                              # second train step moves the statistics again
+    with torch.no_grad():
+        model.train()(data)                                          # another train-mode call moves the statistics again
     assert not torch.equal(rm, model.kenc.encoder[1].running_mean)
     after = model.eval()(data)['scores_0_1']
     assert not torch.equal(before, after)                            # the packed weights were rebuilt from the new buffers

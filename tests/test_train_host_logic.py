@@ -1,0 +1,96 @@
+"""Host-side orchestration of the TRAINING step (models/train_forward.py: MatcherTrainFn forward + backward) against the
+gradients of the unmodified reference (tests/golden/train_backward_*.npz, oracle/make_train_backward_golden.py), with the
+stage kernels replaced by the float64 torch stand-ins of tests/emul_ops.py -- runs without a GPU.  What it pins: which
+tensors are saved, the head permutation of q/k/v/merge and its inverse on the gradients, the concat / residual routing,
+the per-view BatchNorm groups of the pairwise path, the pair loops and the accumulation over pairs.  The kernels
+themselves are checked against the same stand-ins on the GPU (tests/test_train_backward_gpu.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import emul_ops
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+PATCHED = ['pack_views', 'linear', 'attention', 'attention_backward', 'transpose_split', 'linear_presplit', 'colsum',
+           'batchnorm_train', 'batchnorm_train_backward', 'sinkhorn_train_forward', 'sinkhorn_train_backward']
+
+
+def match_loss(log_p, idx, w):
+    """helpers.py:228-241 restated (the product's compute_match_loss is a CUDA kernel)."""
+    bs, ft, _ = log_p.shape
+    l0 = -log_p.reshape(bs * ft, ft)[range(bs * ft), idx[:, 0].reshape(-1)]
+    l1 = -log_p.transpose(1, 2).reshape(bs * ft, ft)[range(bs * ft), idx[:, 1].reshape(-1)]
+    return (torch.dot(l0, w[:, 0].reshape(-1)) + torch.dot(l1, w[:, 1].reshape(-1))) / bs
+
+
+def check_gradients(model, z, tol_noise, tol_rel, what):
+    from oracle.make_train_backward_golden import sample_index
+    names = [k[len('grad__'):] for k in z.files if k.startswith('grad__')]
+    params = dict(model.named_parameters())
+    assert sorted(n for n, p in params.items() if p.grad is not None) == sorted(names)
+    scale = max(float(np.abs(z['grad__' + k]).max()) for k in names)
+    worst = (0.0, None)
+    for k in names:
+        g = params[k].grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
+        ref = z['grad__' + k].astype(np.float64)
+        got = g[sample_index(k, g.size)]
+        tol = tol_noise * float(z['noise__' + k]) + tol_rel * max(float(np.abs(ref).max()), 1e-3 * scale)
+        err = float(np.abs(got - ref).max())
+        if err / tol > worst[0]:
+            worst = (err / tol, k)
+        assert err <= tol, (what, k, err, tol, float(z['noise__' + k]), float(np.abs(ref).max()))
+        norm = float(np.linalg.norm(g))
+        assert abs(norm - float(z['norm__' + k])) <= tol_noise * float(z['noise__' + k]) * np.sqrt(g.size) + 10 * tol_rel * max(float(z['norm__' + k]), 1e-3 * scale), k
+    return worst
+
+
+@pytest.mark.parametrize('name', ['mv3_64', 'mv4_100', 'pair_96'])
+def test_train_step_orchestration_vs_reference(name, monkeypatch):
+    from oracle.make_train_backward_golden import build
+    from e2e_multi_view_matching_b200 import ops, _lib
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    for f in PATCHED:
+        monkeypatch.setattr(ops, f, getattr(emul_ops, f))
+    monkeypatch.setattr(_lib, 'require_cuda', lambda device, what: None)
+    z = np.load(os.path.join(GOLDEN, 'train_backward_%s.npz' % name))
+    case = json.loads(str(z['meta']))
+    data_np, sd = build(case)
+    model = MultiViewMatcher({'multi_frame_matching': case['multi'], 'GNN_layers': case['layers'], 'conf_mlp': True,
+                              'full_output': False})
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model.train()
+    data = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
+    result = model(data)
+    assert sorted(result) == sorted('scores_%d_%d' % (a, b) for b in range(case['views']) for a in range(b))
+    loss = 0.0
+    for b in range(case['views']):
+        for a in range(b):
+            key = '%d_%d' % (a, b)
+            assert result['scores_' + key].requires_grad
+            loss = loss + match_loss(result['scores_' + key], data['gt_indices_' + key], data['gt_weights_' + key])
+    assert abs(float(loss) - float(z['loss_f64'])) <= 4 * abs(float(z['loss_f32']) - float(z['loss_f64'])) + 1e-6 * abs(float(z['loss_f64']))
+    loss.backward()
+    # the stand-ins compute in float64 and hand float32 tensors on: the error budget is the reference's own fp32 noise
+    worst = check_gradients(model, z, tol_noise=3.0, tol_rel=2e-5, what=name)
+    print(name, 'worst gradient error / tolerance: %.3f at %s' % worst)
+
+
+def test_no_grad_train_forward_has_no_graph(monkeypatch):
+    from oracle.make_train_backward_golden import build, CASES
+    from e2e_multi_view_matching_b200 import ops, _lib
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    for f in PATCHED:
+        monkeypatch.setattr(ops, f, getattr(emul_ops, f))
+    monkeypatch.setattr(_lib, 'require_cuda', lambda device, what: None)
+    case = CASES[0]
+    data_np, sd = build(case)
+    model = MultiViewMatcher({'multi_frame_matching': True, 'GNN_layers': case['layers'], 'conf_mlp': True, 'full_output': False})
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model.train()
+    data = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
+    with torch.no_grad():
+        res = model(data)
+    assert not res['scores_0_1'].requires_grad
