@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- view-tuples/sec of the hot path on synthetic 5-view x 1024-keypoint tuples.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3|cfg2|cfg4] [--tuples B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3|cfg2|cfg4|cfg5] [--tuples B]
 
 A *step* is one pass of the hot path over one batch of B synthetic units per GPU.  Default = BASELINE.json
 configs[2] (cfg3: ScanNet-shape 5-tuple, 1024 kpts, 28-layer matcher, confidence head, 10 x {w8pt + two-view BA},
@@ -50,6 +50,12 @@ CONFIGS = {
                  layers=['self', 'cross'] * 9, batch=8, width=1600, height=1200, f=1400.0, seed_base=4000,
                  metric='pairs/sec @2048 kpts 2-view w8pt_ba', unit='pairs/s', parity_kpts=256,
                  pose='w8pt + 10it 2-view BA (eval_pairs.py w8pt_ba)'),
+    # BASELINE.json configs[4], STAGE 1 of it (match loss; the pose-loss gradients of stage 2 are not built): one training
+    # iteration per step -- train-mode forward, match loss, backward through the kernels, gradient all-reduce, Adam
+    'cfg5': dict(workload='train_stage1_5tuple_400kpts_28layers_matchloss', kind='train', views=5, kpts=400,
+                 layers=(['self'] + ['cross'] * 3) * 7, batch=8, width=640, height=480, f=577.87, seed_base=5000,
+                 metric='training steps/sec, tuple_size 5, 8 tuples per GPU, 400 kpts (stage 1: match loss)', unit='steps/s',
+                 pose='none (stage 1 of train.py: match loss only)'),
 }
 
 
@@ -332,6 +338,140 @@ def run_reference_arm(args, cfg, rank, world):
     emit(line)
 
 
+def run_train_arm(args, cfg, rank, world, local):
+    """--config cfg5: training iterations per second (training.train_step: train-mode forward with batch-statistics
+    BatchNorm, CUDA match loss, MatcherTrainFn backward on the kernels, bucketed gradient all-reduce over NCCL when
+    world > 1, torch.optim.Adam like train.py:360).  Data parallel: every rank trains on its own tuples (weak scaling:
+    the global batch grows with the ranks, steps/s should stay flat); `tuples_per_s` is the whole-job rate."""
+    if args.impl == 'reference':
+        if rank == 0:
+            emit({'impl': 'reference', 'unavailable': 'cfg5 reference arm: the reference\'s training step needs its own '
+                  'autograd on the host CPU (minutes per step at this size); the gradients are pinned by the committed '
+                  'reference goldens instead (tests/golden/train_backward_*.npz)'})
+        return
+    import types
+    import torch
+    import torch.distributed as dist
+    from e2e_multi_view_matching_b200 import _lib, sharding, training
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    from e2e_multi_view_matching_b200.synthetic import landmark_gt_matches
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.lib()
+    B, T = args.tuples or cfg['batch'], cfg['views']
+    P = n_pairs(cfg)
+    sd = make_weights(cfg)
+    model = MultiViewMatcher({'GNN_layers': cfg['layers'], 'multi_frame_matching': True, 'conf_mlp': False, 'full_output': False})
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items() if not k.startswith('conf_mlp')})
+    model = model.to(dev).train()
+    opt = types.SimpleNamespace(pose_loss=False, rot_weight=0.0, trans_weight=0.0)
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-4)
+    data_np = make_inputs(cfg, sharding.tuple_shard(rank, world, B, base=cfg['seed_base'])[0], B)
+    for b_ in range(T):
+        for a_ in range(b_):
+            data_np['gt_indices_%d_%d' % (a_, b_)], data_np['gt_weights_%d_%d' % (a_, b_)] = \
+                landmark_gt_matches(data_np['landmark%d' % a_], data_np['landmark%d' % b_])
+    keys = [k for k, v in data_np.items() if isinstance(v, np.ndarray) and k.startswith(('keypoints', 'scores', 'descriptors', 'gt_'))]
+    host = {k: torch.from_numpy(data_np[k]).pin_memory() for k in keys}
+    meta = {k: torch.empty(v.shape, device='meta') for k, v in data_np.items() if k.startswith('image')}
+    fixed = dict(meta, ids=data_np['ids'], pose0=torch.zeros(1, device=dev))
+    data_dev = dict({k: v.to(dev) for k, v in host.items()}, **fixed)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_device():
+        return training.train_step(opt, dict(data_dev), model, optimizer, P)[0]
+
+    def step_e2e():
+        d = dict({k: v.to(dev, non_blocking=True) for k, v in host.items()}, **fixed)
+        loss = training.train_step(opt, d, model, optimizer, P)[0]
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        return loss
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev)
+
+    losses = []
+    for _ in range(args.warmup):
+        losses.append(float(step_device()))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.mvm_launch_count()
+    ms_dev = timed(step_device, args.steps)
+    launches = lib.mvm_launch_count() - n0
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    losses.append(float(step_device()))
+    # stage split (CUDA events around forward / backward / optimiser of two more steps) and the kernel-class timers
+    lib.mvm_profile_enable(1)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    split = np.zeros(3)
+    for _ in range(2):
+        d = dict(data_dev)
+        ev[0].record()
+        ls, _ = training.run_matcher(opt, d, model)
+        loss, _ = training.combine_losses(ls, P, 0.0, 0.0, 0.0)
+        ev[1].record()
+        optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        ev[2].record()
+        sharding.all_reduce_gradients(list(model.parameters()))
+        optimizer.step()
+        ev[3].record()
+        torch.cuda.synchronize()
+        split += [ev[i].elapsed_time(ev[i + 1]) / 2 for i in range(3)]
+    prof = _lib.profile_collect()
+    lib.mvm_profile_enable(0)
+    if rank == 0:
+        peaks = load_peaks()
+        att_ms, att_n = prof['attention']
+        # forward QK^T + PV (4 N M D per view and layer) and the backward's recomputation + four gradient products
+        # (QK^T twice, dO V^T twice, dS K, dS^T Q, P^T dO = 7 products of 2 N M D): 4 + 14 = 18 N M D
+        att_flops = attention_flops(cfg) * B * 2 * (18.0 / 4.0)
+        att_tflops = att_flops / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
+        line = {'metric': cfg['metric'], 'value': args.steps / (ms_dev * 1e-3), 'unit': cfg['unit'], 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32 via split operands on tcgen05 (fp16x3 forward, tf32x3 backward GEMMs), f32 CUDA cores (attention backward, Sinkhorn, BatchNorm)',
+                'data': 'synthetic', 'config': workload_config(cfg), 'units_per_step': B * world,
+                'tuples_per_s': B * world * args.steps / (ms_dev * 1e-3),
+                'run': {'tuples_per_step_per_gpu': B, 'l2': 'flushed between timed steps (256 MB write)', 'parallelism': 'dp%d' % world,
+                        'optimizer': 'torch.optim.Adam (train.py:360)', 'collective': 'bucketed gradient all-reduce (sharding.all_reduce_gradients)' if world > 1 else 'none',
+                        'stage': 'stage 1 of cfg5 (match loss); stage 2 (--pose_loss) is not built'},
+                'e2e': {'value': args.steps / (ms_e2e * 1e-3), 'unit': cfg['unit'], 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+                        'ms_per_step': ms_e2e / args.steps},
+                'gpu_launches': int(launches), 'clocks': sampler.summary(),
+                'roofline': {'kernel': 'attention forward (tcgen05 fp16x3) + backward (fp32 CUDA cores, flash-style recomputation)',
+                             'bound': 'tensor', 'achieved': att_tflops, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                             'frac': att_tflops / peaks['tflops'], 'traffic': None, 'launches_timed': att_n, 'peak_source': peaks['source'],
+                             'note': 'the backward kernels are the functional first version on the CUDA cores; their tcgen05 port is the next step'},
+                'step_split_ms': {'forward+loss': round(float(split[0]), 3), 'backward': round(float(split[1]), 3),
+                                  'allreduce+optimizer': round(float(split[2]), 3)},
+                'stage_ms_per_step': {k: round(v[0] / 2, 4) for k, v in prof.items() if v[1] > 0},
+                'loss_first_last': [losses[0], losses[-1]], 'cpu_baseline': None}
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -361,6 +501,9 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
+    if cfg['kind'] == 'train':
+        run_train_arm(args, cfg, rank, world, local)
+        return
     if args.impl == 'reference':
         run_reference_arm(args, cfg, rank, world)
         return

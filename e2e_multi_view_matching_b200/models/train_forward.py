@@ -134,6 +134,8 @@ def _forward(model, data, view_ids=None, save=False, debug=None):
         if debug is not None and 'layer0_delta' not in debug:
             debug['layer0_delta'] = (x_new - x).view(B, T, n_pad, 256)[:, :, :N].clone()
         x = x_new
+        if debug is not None:
+            debug.setdefault('x_layers', []).append(x.clone())
     # ---- final projection, scores, optimal transport (multi_view_matcher.py:275-285)
     if debug is not None:
         debug['gnn'] = x.view(B, T, n_pad, 256)[:, :, :N].clone()
@@ -221,11 +223,16 @@ def _backward(model, S, grads):
                 g_md[i, b_] = ops.linear_presplit(dSt, hi, lo, residual=g_md[i, b_], alpha=1.0 / 16.0)
         acc(model.bin_score, d_alpha.float())
         g_md = g_md.view(rows, 256)
+        dbg = getattr(model, '_train_debug', None)      # tests: gradients at the stage boundaries, [B, T, N, 256]
+        if dbg is not None:
+            dbg['g_mdesc'] = g_md.view(B, T, n_pad, 256)[:, :, :N].clone()
         # ---- final projection
         wf = model.final_proj.weight[:, :, 0]
         acc(model.final_proj.weight, ops.gemm_dw(g_md, S.x_final))
         acc(model.final_proj.bias, ops.colsum(g_md))
         gx = ops.gemm_dx(g_md, wf)
+        if dbg is not None:
+            dbg['g_gnn'] = gx.view(B, T, n_pad, 256)[:, :, :N].clone()
         # ---- GNN layers, last to first (superglue.py:94-121, multi_view_matcher.py:65-86)
         inv = torch.empty_like(perm)
         inv[perm] = torch.arange(256, device=dev)
@@ -249,6 +256,9 @@ def _backward(model, S, grads):
             g_msg = ops.gemm_dx(g_merged, wm)
             g_qkv = ops.attention_backward(qkv.view(B * T, n_pad, 768), msg, g_msg.view(B * T, n_pad, 256), B, T, [N] * T,
                                            1 if name == 'cross' else 0).view(rows, 768)
+            if dbg is not None:
+                dbg.setdefault('layers', []).append({'g_hid': g_hid.clone(), 'g_merged': g_merged.clone(), 'g_msg': g_msg.clone(),
+                                                     'g_qkv': g_qkv.clone()})
             g_wqkv = ops.gemm_dw(g_qkv, x_in)                           # [768, 256], rows head-contiguous per projection
             g_bqkv = ops.colsum(g_qkv)
             for i in range(3):
@@ -256,8 +266,12 @@ def _backward(model, S, grads):
                 acc(attn.proj[i].bias, g_bqkv[i * 256:(i + 1) * 256][inv])
             wqkv = torch.cat([attn.proj[i].weight[:, :, 0][perm] for i in range(3)], 0)
             gx = ops.gemm_dx(g_qkv, wqkv, residual=gx)
+            if dbg is not None:
+                dbg['layers'][-1]['gx'] = gx.clone()
         # ---- keypoint encoder (x = kenc(kpts, scores) + descriptors)
         enc = model.kenc.encoder
+        if dbg is not None:
+            dbg['g_kenc'] = gx.view(B, T, n_pad, 256)[:, :, :N].clone()
         acc(enc[12].weight, ops.gemm_dw(gx, S.kenc_last_in))
         acc(enc[12].bias, ops.colsum(gx))
         g_h = ops.gemm_dx(gx, enc[12].weight[:, :, 0])

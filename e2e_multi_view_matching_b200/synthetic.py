@@ -262,3 +262,31 @@ def make_image(seed, height, width, batch=1):
         img = (img - img.min()) / (img.max() - img.min())
         out.append(img[None])
     return np.stack(out, 0).astype(np.float32)
+
+
+def landmark_gt_matches(la, lb):
+    """Ground-truth assignments of one pair from the scene's landmark ids (two keypoints match iff they observe the same
+    landmark), in the layout and with the class-balancing weights of compute_gt_matches_of_image_pair
+    (helpers.py:190-213): la, lb [B, n] -> (indices [B, 2, n+1] int64, weights [B, 2, n+1] float32).  For the training
+    bench / tests, whose synthetic scenes carry landmark ids instead of depth maps."""
+    la, lb = np.asarray(la), np.asarray(lb)
+    B, n = la.shape
+    idx = np.full((B, 2, n + 1), -1, np.int64)
+    w = np.zeros((B, 2, n + 1), np.float32)
+    for b in range(B):
+        order = np.argsort(lb[b], kind='stable')
+        pos = np.searchsorted(lb[b][order], la[b])
+        pos = np.clip(pos, 0, n - 1)
+        hit = lb[b][order][pos] == la[b]
+        i0 = np.where(hit, order[pos], -1)
+        idx[b, 0, :n] = i0
+        i1 = np.full(n, -1, np.int64)
+        i1[i0[hit]] = np.nonzero(hit)[0]
+        idx[b, 1, :n] = i1
+        m = int(hit.sum())
+        mw = np.float32(2.0 * m) / np.float32(2.0 * n)
+        uw = np.float32(0.5) / (np.float32(1.0) - mw)
+        mw = np.float32(0.5) / mw if m else np.float32(0.0)
+        w[b, 0] = np.where(idx[b, 0] >= 0, mw, uw)
+        w[b, 1] = np.where(idx[b, 1] >= 0, mw, uw)
+    return idx, w

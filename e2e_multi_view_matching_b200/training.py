@@ -1,4 +1,4 @@
-"""Training-side consumers of the matcher output -- FIRST SLICE of SURVEY.md §8 f-2 / a20 (BASELINE cfg5).
+"""Training-side consumers of the matcher output -- SURVEY.md §8 f-2 / a20 (BASELINE cfg5).
 
 Built:
   * compute_match_loss (helpers.py:228-241) as an autograd.Function on CUDA kernels (csrc/train_loss.cu), forward
@@ -6,20 +6,20 @@ Built:
   * combine_losses (train.py:36-40);
   * compute_gt_matches_of_image_pair / compute_gt_matches (helpers.py:121-226): ground-truth assignments from depth
     maps and poses on CUDA kernels (csrc/gt_matches.cu; the [bs, N, N] error matrix is never materialised);
-  * run_matcher (helpers.py:243-260) and validation_step (the loop body of Trainer.validate, train.py:89-106) for the
-    matcher in EVAL mode -- exactly what the reference's validation pass runs: matcher forward, match loss, weighted
-    eight-point with choose_closest against the ground-truth pose, rotation / translation losses, combine_losses and
-    the validation-loss all-reduce;
-  * LogOptimalTransport: autograd.Function around the production Sinkhorn kernel whose backward is the EXACT gradient
-    of the 100 unrolled iterations (what autograd computes for the reference, superglue.py:143-172).  The backward
-    below is stated in torch operations -- it is the executable specification (checked against autograd through the
-    reference's function in tests/test_training_gpu.py) of the fused kernel that is the next step: since Z is
-    constant over the iterations, d loss / d Z = G - exp(Z) * (A B^T) with A = [exp(u^t) | r^t], B = [c^t | exp(v^(t-1))]
-    stacked over the iterations (a rank-2T correction), and the recursion for (gu, gv) needs exactly the two
-    matrix-vector passes per iteration the forward kernel already makes over its on-chip copy of the matrix.
-Not built (stated, not hidden): the train branch of the matcher forward (batch-statistics BatchNorm over B*T*N,
-`full_output`, multi_view_matcher.py:65-86,219-226) and the backward kernels of attention / GEMMs / pose, so
-MultiViewMatcher.forward still raises in training mode and cfg5 cannot run end to end yet.
+  * run_matcher (helpers.py:243-260) and validation_step (the loop body of Trainer.validate, train.py:89-106): matcher
+    forward, match loss, weighted eight-point with choose_closest against the ground-truth pose, rotation / translation
+    losses, combine_losses and the validation-loss all-reduce;
+  * the TRAINING step of stage 1 (train.py:405-426 without --pose_loss: match loss only): train_step = compute_gt_matches,
+    run_matcher with the matcher in train() mode (models/train_forward.py: batch-statistics BatchNorm, and
+    MatcherTrainFn's backward on the kernels: attention backward, BatchNorm backward, the exact gradient of the
+    unrolled Sinkhorn iterations, 3xTF32 GEMMs), combine_losses, backward, the data-parallel gradient all-reduce
+    (sharding.all_reduce_gradients, what DistributedDataParallel does for the reference) and the optimiser step;
+  * LogOptimalTransport: autograd.Function over mvm_sinkhorn_train_{forward,backward} -- the exact gradient of the 100
+    unrolled iterations (what autograd computes for the reference, superglue.py:143-172), with respect to the scores
+    and to bin_score.
+Not built (stated, not hidden): stage 2 of cfg5 (--pose_loss): the gradients through the weighted eight-point, the
+two-view bundle adjustment and the ConfidenceMLP.  run_matcher with opt.pose_loss evaluates those losses (validation)
+but they carry no graph.
 """
 import torch
 
@@ -74,56 +74,29 @@ def combine_losses(losses, n_pairs, pose_match_ratio, rot_weight, trans_weight):
 
 
 class LogOptimalTransport(torch.autograd.Function):
-    """log_optimal_transport(scores, alpha, iters) (superglue.py:152-172) with gradients w.r.t. scores and alpha."""
+    """log_optimal_transport(scores, alpha, iters) (superglue.py:152-172) with gradients w.r.t. scores and alpha:
+    mvm_sinkhorn_train_forward keeps the potentials of every iteration, mvm_sinkhorn_train_backward runs the exact
+    reverse recursion of the unrolled iterations (csrc/sinkhorn_train.cu)."""
 
     @staticmethod
     def forward(ctx, scores, alpha, iters):
-        if scores.device.type != 'cuda':
-            raise _lib.MvmError('LogOptimalTransport needs CUDA tensors (no CPU fallback)')
-        Z = ops.log_optimal_transport(scores.detach().float().contiguous(), float(alpha), int(iters))
-        ctx.save_for_backward(scores.detach(), alpha.detach() if torch.is_tensor(alpha) else torch.tensor(float(alpha)))
+        _lib.require_cuda(scores.device, 'LogOptimalTransport')
+        s = scores.detach().float().contiguous()
+        a = alpha.detach().float().reshape(1).to(s.device).contiguous()
+        with _lib.device_ctx(s.device):
+            Z, pot = ops.sinkhorn_train_forward(s, a, int(iters))
+        ctx.save_for_backward(s, a, pot)
         ctx.iters = int(iters)
+        ctx.alpha_shape = alpha.shape
         return Z
 
     @staticmethod
     def backward(ctx, G):
-        scores, alpha = ctx.saved_tensors
-        T = ctx.iters
-        dt = torch.float64                      # the recursion is short and cheap next to the forward: do it in double
-        b, m, n = scores.shape
-        dev = scores.device
-        Z = torch.empty(b, m + 1, n + 1, dtype=dt, device=dev)
-        Z[:, :m, :n] = scores.to(dt)
-        Z[:, m, :] = alpha.to(dt).to(dev)
-        Z[:, :m, n] = alpha.to(dt).to(dev)
-        norm = -torch.log(torch.tensor(float(m + n), dtype=dt, device=dev))
-        log_mu = torch.cat([norm.expand(m), (torch.log(torch.tensor(float(n), dtype=dt, device=dev)) + norm)[None]])[None]
-        log_nu = torch.cat([norm.expand(n), (torch.log(torch.tensor(float(m), dtype=dt, device=dev)) + norm)[None]])[None]
-        us, vs = [], [torch.zeros(b, n + 1, dtype=dt, device=dev)]
-        u, v = torch.zeros(b, m + 1, dtype=dt, device=dev), vs[0]
-        for _ in range(T):                      # the reference's iteration (superglue.py:143-149), potentials kept
-            u = log_mu - torch.logsumexp(Z + v.unsqueeze(1), dim=2)
-            v = log_nu - torch.logsumexp(Z + u.unsqueeze(2), dim=1)
-            us.append(u)
-            vs.append(v)
-        G = G.to(dt)
-        gu, gv, dZ = G.sum(2), G.sum(1), G.clone()
-        for t in range(T, 0, -1):
-            u_t, v_t, v_p = us[t - 1], vs[t], vs[t - 1]
-            # v^t = log_nu - LSE_i(Z + u^t):  P_ij = exp(Z_ij + u^t_i + v^t_j - log_nu_j)  (columns sum to one)
-            P = torch.exp(Z + u_t.unsqueeze(2) + (v_t - log_nu).unsqueeze(1))
-            W = P * gv.unsqueeze(1)
-            dZ -= W
-            gu = gu - W.sum(2)
-            # u^t = log_mu - LSE_j(Z + v^(t-1)):  Q_ij = exp(Z_ij + u^t_i + v^(t-1)_j - log_mu_i)  (rows sum to one)
-            Q = torch.exp(Z + (u_t - log_mu).unsqueeze(2) + v_p.unsqueeze(1))
-            W = Q * gu.unsqueeze(2)
-            dZ -= W
-            gv = -W.sum(1)
-            gu = torch.zeros_like(gu)
-        d_scores = dZ[:, :m, :n].to(scores.dtype)
-        d_alpha = (dZ[:, m, :].sum() + dZ[:, :m, n].sum()).to(torch.float32)
-        return d_scores, d_alpha, None
+        s, a, pot = ctx.saved_tensors
+        _, m, n = s.shape
+        with _lib.device_ctx(s.device):
+            dZ, d_alpha = ops.sinkhorn_train_backward(s, a, pot, ctx.iters, G)
+        return dZ[:, :m, :n].contiguous(), d_alpha.float().reshape(ctx.alpha_shape), None
 
 
 def log_optimal_transport(scores, alpha, iters):
@@ -171,8 +144,8 @@ def compute_gt_matches(opt, data):
 
 
 def run_matcher(opt, data, matcher):
-    """helpers.py:243-260.  The matcher must be in eval mode (the validation pass, train.py:66-68): the training
-    branch of the forward is not built (module docstring)."""
+    """helpers.py:243-260.  Eval mode = the validation pass (train.py:66-68); train mode = the training step, where the
+    match loss carries MatcherTrainFn's graph (the pose losses never do: module docstring)."""
     from .pose_optimization.two_view.estimate_relative_pose import run_weighted_8_point
     from .pose_optimization.two_view.compute_pose_error import compute_rotation_error, compute_translation_error_as_angle
     curr_tuple_size = len(data["ids"])
@@ -209,3 +182,27 @@ def validation_step(opt, data, matcher, n_pairs, pose_match_ratio, process_group
             torch.distributed.all_reduce(val_loss, group=process_group)
             val_loss /= torch.distributed.get_world_size(process_group)
     return val_loss, losses
+
+
+def train_step(opt, data, matcher, optimizer, n_pairs, pose_match_ratio=0.0, grad_clip=-1.0):
+    """One iteration of the training loop after SuperPoint (train.py:409-426), stage 1 (match loss): ground-truth matches
+    when the batch still carries depth maps, run_matcher in train mode, combine_losses, backward through the kernels,
+    gradient averaging over the ranks when torch.distributed is initialised (DistributedDataParallel's all-reduce in the
+    reference), optional value clipping, optimiser step.  -> (train_loss tensor, losses dict)."""
+    if getattr(opt, 'pose_loss', False):
+        raise NotImplementedError('stage 2 (--pose_loss) needs the gradients of the pose stage, which are not built')
+    from . import sharding
+    if "depth0" in data:
+        with torch.no_grad():
+            compute_gt_matches(opt, data)
+    losses, _ = run_matcher(opt, data, matcher)
+    train_loss, losses = combine_losses(losses, n_pairs, pose_match_ratio, getattr(opt, 'rot_weight', 0.0),
+                                        getattr(opt, 'trans_weight', 0.0))
+    optimizer.zero_grad(set_to_none=True)
+    train_loss.backward()
+    params = [p for group in optimizer.param_groups for p in group['params']]
+    sharding.all_reduce_gradients(params)
+    if grad_clip > 0.0:
+        torch.nn.utils.clip_grad_value_(params, grad_clip)
+    optimizer.step()
+    return train_loss.detach(), {k: v.detach() for k, v in losses.items()}

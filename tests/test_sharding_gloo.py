@@ -37,11 +37,40 @@ def test_shards_and_collectives_world2(tmp_path):
     assert open(out).read() == 'ok'
 
 
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from e2e_multi_view_matching_b200 import sharding
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    params[0].grad = torch.full((5, 3), float(rank + 1))
+    params[1].grad = torch.arange(7.0) * (rank + 1)
+    if rank == 0:
+        params[2].grad = torch.ones(2, 2)                    # rank 1 has no gradient for this parameter
+    calls = sharding.all_reduce_gradients(params, bucket_bytes=64)      # small buckets: several collectives
+    mean = sum(range(1, world + 1)) / world
+    assert calls >= 2
+    assert torch.allclose(params[0].grad, torch.full((5, 3), mean))
+    assert torch.allclose(params[1].grad, torch.arange(7.0) * mean)
+    assert torch.allclose(params[2].grad, torch.ones(2, 2) / world)
+    if rank == 0:
+        open(out, 'w').write('ok')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_world2(tmp_path):
+    out = str(tmp_path / 'ok.txt')
+    mp.spawn(_grad_worker, args=(2, 29533, out), nprocs=2, join=True)
+    assert open(out).read() == 'ok'
+
+
 def test_no_process_group_is_a_noop():
     from e2e_multi_view_matching_b200 import sharding
     assert sharding.tuple_shard(0, 1, 3) == [1000, 1001, 1002]
     assert sharding.all_reduce_step_loss(torch.tensor([2.0])).item() == 2.0
     assert sharding.max_over_ranks(3.5) == 3.5
+    assert sharding.all_reduce_gradients([torch.nn.Parameter(torch.zeros(2))]) == 0
 
 
 def test_reference_arm_only_rank0_prints():

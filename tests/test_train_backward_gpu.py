@@ -134,19 +134,89 @@ def _loss(case, model, data):
     return loss
 
 
+def _to_cpu(o):
+    if torch.is_tensor(o):
+        return o.detach().cpu()
+    if isinstance(o, (list, tuple)):
+        return type(o)(_to_cpu(x) for x in o)
+    return o
+
+
+@pytest.mark.parametrize('name', ['mv3_64', 'mv4_100', 'pair_96'])
+def test_backward_system_vs_standins_on_the_gpu_forward_state(name, monkeypatch):
+    """The whole backward (every kernel in sequence, 100+ launches) against the float64 stand-ins run on the SAME saved
+    forward state (the GPU's activations, BatchNorm statistics and ReLU masks): isolates the backward kernels from the
+    rounding of the forward -- a pre-ReLU activation within ~1e-5 of zero flips its mask between two correct forwards,
+    which moves the gradient by far more than rounding does (profiles/r02_train_kink.txt)."""
+    import copy
+    from e2e_multi_view_matching_b200 import ops, _lib
+    from e2e_multi_view_matching_b200.models import train_forward as TF
+    from e2e_multi_view_matching_b200.training import compute_match_loss
+    from tests.test_train_host_logic import PATCHED
+    z, case, model, data = _golden_case(name)
+    ids = None if case['multi'] else [0, 1]
+    with torch.no_grad():
+        result, S = TF._forward(model, data, ids, save=True)
+    grads = {}
+    for k, Z in result.items():
+        key = k[len('scores_'):]
+        leaf = Z.detach().clone().requires_grad_(True)
+        compute_match_loss(leaf, data['gt_indices_' + key], data['gt_weights_' + key]).backward()
+        grads[k] = leaf.grad
+    with torch.no_grad():
+        G = TF._backward(model, S, grads)
+    torch.cuda.synchronize()
+    names = {p: n for n, p in model.named_parameters()}
+    got = {names[p]: g.detach().cpu().double() for p, g in G.items()}
+    # the same backward on the CPU stand-ins, fed with the GPU's saved state
+    model_c = copy.deepcopy(model).cpu()
+    S_c = TF._Saved()
+    for k, v in vars(S).items():
+        setattr(S_c, k, _to_cpu(v))
+    S_c.dev = torch.device('cpu')
+    for f in PATCHED:
+        monkeypatch.setattr(ops, f, getattr(emul_ops, f))
+    with torch.no_grad():
+        G_c = TF._backward(model_c, S_c, {k: v.cpu() for k, v in grads.items()})
+    names_c = {p: n for n, p in model_c.named_parameters()}
+    ref = {names_c[p]: g.detach().double() for p, g in G_c.items()}
+    assert sorted(got) == sorted(ref) and len(got) > 50
+    scale = max(float(v.abs().max()) for v in ref.values())
+    worst = (0.0, None)
+    for k in ref:
+        e = float((got[k] - ref[k]).abs().max()) / max(float(ref[k].abs().max()), 1e-3 * scale)
+        worst = max(worst, (e, k))
+        assert e < 1e-4, (k, e)
+    print(name, 'backward on the kernels vs float64 stand-ins on the same forward state: worst relative error %.2e at %s' % worst)
+
+
 @pytest.mark.parametrize('name', ['mv3_64', 'mv4_100', 'pair_96'])
 def test_train_step_vs_reference_golden(name):
-    """loss.backward() through the kernels == the reference's autograd: every parameter gradient within 8x the
-    reference's own fp32-vs-fp64 deviation (+ 1e-4 of the gradient's scale) of the reference's fp64 run."""
+    """loss.backward() through the kernels against the reference's autograd (its fp64 run).  The loss matches to the
+    reference's own fp32 deviation.  The gradients are compared with two bounds: most parameters sit within a few times
+    the reference's own fp32-vs-fp64 deviation (median of error / deviation <= 6); the rest is bounded by what ONE flipped
+    ReLU mask does (an activation within ~1e-5 of zero has a different sign in two correctly rounded forwards: measured
+    on the float64 stand-ins with a 1e-6 forward perturbation, profiles/r02_train_kink.txt: up to 7e-3 of the gradient's
+    scale) -- 2e-2 of the parameter's gradient scale.  The backward itself is pinned tighter by the test above."""
     from tests.test_train_host_logic import check_gradients
     z, case, model, data = _golden_case(name)
+    model._train_debug = {}
     loss = _loss(case, model, data)
     noise = abs(float(z['loss_f32']) - float(z['loss_f64']))
     assert abs(float(loss) - float(z['loss_f64'])) <= 8 * noise + 2e-5 * abs(float(z['loss_f64'])), (float(loss), float(z['loss_f64']))
     loss.backward()
     torch.cuda.synchronize()
-    worst = check_gradients(model, z, tol_noise=8.0, tol_rel=1e-4, what=name)
-    print(name, 'loss %.6f (reference fp64 %.6f, fp32 %.6f); worst gradient error / tolerance %.3f at %s'
+    for k, g in model._train_debug.items():        # gradients at the stage boundaries (reference layout [T, B, 256, N])
+        if k in ('g_gnn', 'g_kenc') and 'inter__' + k in z.files:
+            ref = z['inter__' + k].astype(np.float64).reshape(case['views'], case['batch'], 256, case['kpts'])
+            err = float(np.abs(g.cpu().numpy().transpose(1, 0, 3, 2) - ref).max())
+            print(name, k, 'max err %.3g = %.1f x the reference\'s fp32-vs-fp64 deviation (%.3g), |ref| max %.3g'
+                  % (err, err / float(z['inter_noise__' + k]), float(z['inter_noise__' + k]), float(np.abs(ref).max())))
+    worst, ratios = check_gradients(model, z, tol_noise=0.0, tol_rel=2e-2, what=name, return_ratios=True)
+    # (parameters whose gradient is analytically zero -- the key biases: softmax is shift-invariant -- have a deviation
+    # yardstick of ~1e-5 absolute and are excluded from the ratio statistic by its median)
+    assert np.median(ratios) <= 6.0, np.median(ratios)
+    print(name, 'loss %.6f (reference fp64 %.6f, fp32 %.6f); worst gradient error / (2e-2 of its scale) %.3f at %s'
           % (float(loss), float(z['loss_f64']), float(z['loss_f32']), worst[0], worst[1]))
 
 

@@ -26,13 +26,14 @@ def match_loss(log_p, idx, w):
     return (torch.dot(l0, w[:, 0].reshape(-1)) + torch.dot(l1, w[:, 1].reshape(-1))) / bs
 
 
-def check_gradients(model, z, tol_noise, tol_rel, what):
+def check_gradients(model, z, tol_noise, tol_rel, what, return_ratios=False):
     from oracle.make_train_backward_golden import sample_index
     names = [k[len('grad__'):] for k in z.files if k.startswith('grad__')]
     params = dict(model.named_parameters())
     assert sorted(n for n, p in params.items() if p.grad is not None) == sorted(names)
     scale = max(float(np.abs(z['grad__' + k]).max()) for k in names)
     worst = (0.0, None)
+    ratios = []
     for k in names:
         g = params[k].grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
         ref = z['grad__' + k].astype(np.float64)
@@ -41,9 +42,14 @@ def check_gradients(model, z, tol_noise, tol_rel, what):
         err = float(np.abs(got - ref).max())
         if err / tol > worst[0]:
             worst = (err / tol, k)
+        ratios.append(err / max(float(z['noise__' + k]), 1e-30))
         assert err <= tol, (what, k, err, tol, float(z['noise__' + k]), float(np.abs(ref).max()))
         norm = float(np.linalg.norm(g))
         assert abs(norm - float(z['norm__' + k])) <= tol_noise * float(z['noise__' + k]) * np.sqrt(g.size) + 10 * tol_rel * max(float(z['norm__' + k]), 1e-3 * scale), k
+    print(what, 'gradient error / reference fp32 noise over the parameters: median %.2f, 90 %% %.2f, max %.2f'
+          % (np.median(ratios), np.percentile(ratios, 90), max(ratios)))
+    if return_ratios:
+        return worst, ratios
     return worst
 
 
