@@ -6,8 +6,12 @@
 //               Q = exp(Z + u^t - log_mu + v^(t-1)) (rows sum to 1):   W = Q gu_i;  dZ -= W;  gv_j = -sum_i W;  gu = 0
 //             d scores = dZ[:m, :n],  d alpha = sum of dZ over the dustbin row and column
 // (Z is the augmented matrix; every exponent above is <= 0, so nothing overflows however far the scores of an untrained
-// network spread.)  One CTA per problem; the matrix and dZ stay in L2 (0.64 MB each at 400 keypoints); row-direction
-// reductions by a warp per row, column-direction reductions by a thread per column (coalesced across the warp).
+// network spread.)  One CTA per problem, every pair of a training step in ONE launch; the matrix and dZ stay in L2
+// (0.64 MB each at 400 keypoints).  Row-direction reductions: a warp per row.  Column-direction reductions: every warp
+// walks its rows with per-lane accumulators for the columns lane + 32 k (coalesced 128-byte row segments, KC independent
+// chains per thread), then the 32 per-warp partials of a column are merged through shared memory in fixed order
+// (deterministic) -- a thread-per-column loop over all rows was a 400-deep dependent chain on 13 warps (290 ms per
+// cfg5 step before).  expf on the conditional-rescale online log-sum-exp: ~1 exponential per element.
 #include "../../include/mvm_b200.h"
 #include "common.cuh"
 #include "kernels.cuh"
@@ -27,145 +31,200 @@ __device__ __forceinline__ float zin(const float* __restrict__ sc, int i, int j,
   return (i < m && j < n) ? sc[(long long)i * n + j] : alpha;
 }
 
+constexpr int CH = 416;   // columns merged per shared-memory round (13 x 32)
+
+// online log-sum-exp update with one exponential in the common case
+__device__ __forceinline__ void lse_push(float& mx, float& s, float x) {
+  if (x > mx) { s = s * expf(mx - x) + 1.f; mx = x; }
+  else s += expf(x - mx);
+}
+__device__ __forceinline__ void lse_merge(float& mx, float& s, float mo, float so) {
+  if (mo == -INFINITY) return;
+  if (mo > mx) { s = s * expf(mx - mo) + so; mx = mo; }
+  else s += so * expf(mo - mx);
+}
+
+template <int KC>
 __global__ void __launch_bounds__(1024) sinkhorn_train_fwd_kernel(const SkArgs g) {
   extern __shared__ float sm[];
   const int m = g.m, n = g.n, b = blockIdx.x;
-  float* u = sm;               // m + 1
-  float* v = u + (m + 1);      // n + 1
+  float* u = sm;                 // m + 1
+  float* v = u + (m + 1);        // n + 1
+  float* pmx = v + (n + 1);      // [32][CH] per-warp column partials
+  float* psm = pmx + 32 * CH;
   const float* sc = g.scores + (long long)b * m * n;
   const float alpha = *g.alpha_p;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float norm = -logf((float)(m + n));
   const float log_mu_bin = logf((float)n) + norm, log_nu_bin = logf((float)m) + norm;
-  for (int j = tid; j <= n; j += blockDim.x) v[j] = 0.f;
+  for (int j = tid; j <= n; j += 1024) v[j] = 0.f;
   __syncthreads();
   for (int it = 0; it < g.iters; ++it) {
     float* pot = g.pot + ((long long)b * g.iters + it) * (m + n + 2);
-    for (int i = warp; i <= m; i += nwarps) {
+    // rows: u_i = log_mu_i - LSE_j(Z_ij + v_j)
+    for (int i = warp; i <= m; i += 32) {
       float mx = -INFINITY, s = 0.f;
-      for (int j = lane; j <= n; j += 32) {
-        const float x = zin(sc, i, j, m, n, alpha) + v[j];
-        const float mn = fmaxf(mx, x);
-        s = s * expf(mx - mn) + expf(x - mn);
-        mx = mn;
-      }
+      for (int j = lane; j <= n; j += 32) lse_push(mx, s, zin(sc, i, j, m, n, alpha) + v[j]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const float mo = __shfl_xor_sync(0xffffffffu, mx, o), so = __shfl_xor_sync(0xffffffffu, s, o);
-        const float mn = fmaxf(mx, mo);
-        s = (mx == -INFINITY ? 0.f : s * expf(mx - mn)) + (mo == -INFINITY ? 0.f : so * expf(mo - mn));
-        mx = mn;
+        lse_merge(mx, s, mo, so);
       }
       if (lane == 0) { const float r = (i < m ? norm : log_mu_bin) - (logf(s) + mx); u[i] = r; pot[i] = r; }
     }
     __syncthreads();
-    for (int j = tid; j <= n; j += blockDim.x) {
-      float mx = -INFINITY, s = 0.f;
-      for (int i = 0; i <= m; ++i) {
-        const float x = zin(sc, i, j, m, n, alpha) + u[i];
-        const float mn = fmaxf(mx, x);
-        s = s * expf(mx - mn) + expf(x - mn);
-        mx = mn;
+    // columns: v_j = log_nu_j - LSE_i(Z_ij + u_i)
+    float cmx[KC], csm[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) { cmx[k] = -INFINITY; csm[k] = 0.f; }
+    for (int i = warp; i <= m; i += 32) {
+      const float ui = u[i];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int j = lane + 32 * k;
+        if (j <= n) lse_push(cmx[k], csm[k], zin(sc, i, j, m, n, alpha) + ui);
       }
-      const float r = (j < n ? norm : log_nu_bin) - (logf(s) + mx);
-      v[j] = r;
-      pot[m + 1 + j] = r;
     }
-    __syncthreads();
+    for (int c0 = 0; c0 <= n; c0 += CH) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int j = lane + 32 * k;
+        if (j >= c0 && j < c0 + CH) { pmx[warp * CH + j - c0] = cmx[k]; psm[warp * CH + j - c0] = csm[k]; }
+      }
+      __syncthreads();
+      for (int jj = tid; jj < CH && c0 + jj <= n; jj += 1024) {
+        float mx = -INFINITY, s = 0.f;
+        for (int w = 0; w < 32; ++w) lse_merge(mx, s, pmx[w * CH + jj], psm[w * CH + jj]);
+        const int j = c0 + jj;
+        const float r = (j < n ? norm : log_nu_bin) - (logf(s) + mx);
+        v[j] = r;
+        pot[m + 1 + j] = r;
+      }
+      __syncthreads();
+    }
   }
   float* out = g.out + (long long)b * (m + 1) * (n + 1);
-  for (int i = warp; i <= m; i += nwarps)
+  for (int i = warp; i <= m; i += 32)
     for (int j = lane; j <= n; j += 32) out[(long long)i * (n + 1) + j] = zin(sc, i, j, m, n, alpha) + u[i] + v[j] - norm;
 }
 
+template <int KC>
 __global__ void __launch_bounds__(1024) sinkhorn_train_bwd_kernel(const SkArgs g) {
   extern __shared__ float sm[];
   const int m = g.m, n = g.n, b = blockIdx.x, ld = n + 1;
   float* u = sm;                // m + 1   u^t
-  float* v = u + (m + 1);       // n + 1   v^t
+  float* v = u + (m + 1);       // n + 1   v^t - log_nu
   float* vp = v + (n + 1);      // n + 1   v^(t-1)
   float* gu = vp + (n + 1);     // m + 1
   float* gv = gu + (m + 1);     // n + 1
+  float* part = gv + (n + 1);   // [32][CH] per-warp column partial sums
   __shared__ double red[32];
   const float* sc = g.scores + (long long)b * m * n;
   float* dZ = g.out + (long long)b * (m + 1) * ld;
   const float alpha = *g.alpha_p;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float norm = -logf((float)(m + n));
   const float log_mu_bin = logf((float)n) + norm, log_nu_bin = logf((float)m) + norm;
+  float acc[KC];
+  // merges the per-warp column partials `acc` into gv_j = sign * sum (fixed order)
+  auto merge_columns = [&](float sign) {
+    for (int c0 = 0; c0 <= n; c0 += CH) {
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int j = lane + 32 * k;
+        if (j >= c0 && j < c0 + CH) part[warp * CH + j - c0] = acc[k];
+      }
+      __syncthreads();
+      for (int jj = tid; jj < CH && c0 + jj <= n; jj += 1024) {
+        float s = 0.f;
+        for (int w = 0; w < 32; ++w) s += part[w * CH + jj];
+        gv[c0 + jj] = sign * s;
+      }
+      __syncthreads();
+    }
+  };
   // gu = row sums of G, gv = column sums of G (dZ already holds G)
-  for (int i = warp; i <= m; i += nwarps) {
+#pragma unroll
+  for (int k = 0; k < KC; ++k) acc[k] = 0.f;
+  for (int i = warp; i <= m; i += 32) {
     float s = 0.f;
-    for (int j = lane; j <= n; j += 32) s += dZ[(long long)i * ld + j];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int j = lane + 32 * k;
+      if (j <= n) { const float x = dZ[(long long)i * ld + j]; s += x; acc[k] += x; }
+    }
     s = warp_sum(s);
     if (lane == 0) gu[i] = s;
   }
-  for (int j = tid; j <= n; j += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f;
-    int i = 0;
-    for (; i + 1 <= m; i += 2) { s0 += dZ[(long long)i * ld + j]; s1 += dZ[(long long)(i + 1) * ld + j]; }
-    if (i <= m) s0 += dZ[(long long)i * ld + j];
-    gv[j] = s0 + s1;
-  }
-  __syncthreads();
+  merge_columns(1.f);
   for (int t = g.iters; t >= 1; --t) {
     const float* pot = g.pot + ((long long)b * g.iters + (t - 1)) * (m + n + 2);
-    for (int i = tid; i <= m; i += blockDim.x) u[i] = pot[i];
-    for (int j = tid; j <= n; j += blockDim.x) {
+    for (int i = tid; i <= m; i += 1024) u[i] = pot[i];
+    for (int j = tid; j <= n; j += 1024) {
       v[j] = pot[m + 1 + j] - (j < n ? norm : log_nu_bin);          // v^t - log_nu
       vp[j] = t > 1 ? (pot - (m + n + 2))[m + 1 + j] : 0.f;         // v^(t-1)
     }
     __syncthreads();
-    // pass A (rows): W = exp(Z + u^t + v^t - log_nu) gv_j
-    for (int i = warp; i <= m; i += nwarps) {
+    // pass A (rows): W = exp(Z + u^t + v^t - log_nu) gv_j;  dZ -= W;  gu_i -= sum_j W
+    for (int i = warp; i <= m; i += 32) {
       const float ui = u[i];
-      float acc = 0.f;
-      for (int j = lane; j <= n; j += 32) {
-        const float w = expf(zin(sc, i, j, m, n, alpha) + ui + v[j]) * gv[j];
-        dZ[(long long)i * ld + j] -= w;
-        acc += w;
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int j = lane + 32 * k;
+        if (j <= n) {
+          const float w = expf(zin(sc, i, j, m, n, alpha) + ui + v[j]) * gv[j];
+          dZ[(long long)i * ld + j] -= w;
+          a += w;
+        }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) gu[i] -= acc;
+      a = warp_sum(a);
+      if (lane == 0) gu[i] -= a;
     }
     __syncthreads();
-    // pass B (columns): W = exp(Z + u^t - log_mu + v^(t-1)) gu_i;  u is shifted by -log_mu in place first
-    for (int i = tid; i <= m; i += blockDim.x) u[i] -= (i < m ? norm : log_mu_bin);
-    __syncthreads();
-    for (int j = tid; j <= n; j += blockDim.x) {
-      const float vj = vp[j];
-      float a0 = 0.f, a1 = 0.f;
-      int i = 0;
-      for (; i + 1 <= m; i += 2) {
-        const float w0 = expf(zin(sc, i, j, m, n, alpha) + u[i] + vj) * gu[i];
-        const float w1 = expf(zin(sc, i + 1, j, m, n, alpha) + u[i + 1] + vj) * gu[i + 1];
-        dZ[(long long)i * ld + j] -= w0;
-        dZ[(long long)(i + 1) * ld + j] -= w1;
-        a0 += w0; a1 += w1;
+    // pass B (columns): W = exp(Z + u^t - log_mu + v^(t-1)) gu_i;  dZ -= W;  gv_j = -sum_i W;  gu = 0
+#pragma unroll
+    for (int k = 0; k < KC; ++k) acc[k] = 0.f;
+    for (int i = warp; i <= m; i += 32) {
+      const float ui = u[i] - (i < m ? norm : log_mu_bin), gi = gu[i];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int j = lane + 32 * k;
+        if (j <= n) {
+          const float w = expf(zin(sc, i, j, m, n, alpha) + ui + vp[j]) * gi;
+          dZ[(long long)i * ld + j] -= w;
+          acc[k] += w;
+        }
       }
-      if (i <= m) {
-        const float w0 = expf(zin(sc, i, j, m, n, alpha) + u[i] + vj) * gu[i];
-        dZ[(long long)i * ld + j] -= w0;
-        a0 += w0;
-      }
-      gv[j] = -(a0 + a1);
     }
-    __syncthreads();
-    for (int i = tid; i <= m; i += blockDim.x) gu[i] = 0.f;
+    merge_columns(-1.f);          // (its barriers also order pass B's reads of gu before the reset below)
+    for (int i = tid; i <= m; i += 1024) gu[i] = 0.f;
     __syncthreads();
   }
   // d alpha: dustbin row and column
   double s = 0.0;
-  for (int j = tid; j <= n; j += blockDim.x) s += (double)dZ[(long long)m * ld + j];
-  for (int i = tid; i < m; i += blockDim.x) s += (double)dZ[(long long)i * ld + n];
+  for (int j = tid; j <= n; j += 1024) s += (double)dZ[(long long)m * ld + j];
+  for (int i = tid; i < m; i += 1024) s += (double)dZ[(long long)i * ld + n];
   s = warp_sum_d(s);
   if (lane == 0) red[warp] = s;
   __syncthreads();
   if (warp == 0) {
-    s = lane < nwarps ? red[lane] : 0.0;
+    s = red[lane];
     s = warp_sum_d(s);
     if (lane == 0) atomicAdd(g.d_alpha, s);
   }
+}
+
+constexpr int SK_MAX_N = 1055;    // KC = 33 covers n + 1 <= 1056 columns
+inline int fwd_smem(int m, int n) { return (m + n + 2 + 2 * 32 * CH) * 4; }
+inline int bwd_smem(int m, int n) { return (2 * (m + 1) + 3 * (n + 1) + 32 * CH) * 4; }
+void set_attrs() {
+  mvm_once_per_device(MVM_ONCE_SINKHORN_TRAIN, [&] {
+    cudaFuncSetAttribute(sinkhorn_train_fwd_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(SK_MAX_N, SK_MAX_N));
+    cudaFuncSetAttribute(sinkhorn_train_fwd_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(SK_MAX_N, SK_MAX_N));
+    cudaFuncSetAttribute(sinkhorn_train_bwd_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem(SK_MAX_N, SK_MAX_N));
+    cudaFuncSetAttribute(sinkhorn_train_bwd_kernel<33>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem(SK_MAX_N, SK_MAX_N));
+  });
 }
 
 }  // namespace
@@ -176,17 +235,15 @@ extern "C" size_t mvm_sinkhorn_train_pot_floats(int batch, int m, int n, int ite
 
 extern "C" int mvm_sinkhorn_train_forward(const float* scores, const float* alpha, int batch, int m, int n, int iters,
                                           float* out, float* pot, void* stream) {
-  MVM_REQUIRE(scores && alpha && out && pot && batch >= 1 && m >= 1 && n >= 1 && iters >= 1 && m <= 8192 && n <= 8192);
+  MVM_REQUIRE(scores && alpha && out && pot && batch >= 1 && m >= 1 && n >= 1 && iters >= 1 && m <= SK_MAX_N && n <= SK_MAX_N);
   SkArgs g;
   g.scores = scores; g.out = out; g.pot = pot; g.alpha_p = alpha; g.d_alpha = nullptr; g.m = m; g.n = n; g.iters = iters;
-  const int smem = (m + n + 2) * 4;
-  mvm_once_per_device(MVM_ONCE_SINKHORN_TRAIN, [&] {
-    cudaFuncSetAttribute(sinkhorn_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8194 * 4);
-    cudaFuncSetAttribute(sinkhorn_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 8194 * 4);
-  });
+  const int smem = fwd_smem(m, n);
+  set_attrs();
   cudaStream_t s = (cudaStream_t)stream;
   MvmProfScope prof__(MVM_TAG_SINKHORN, s);
-  sinkhorn_train_fwd_kernel<<<batch, 1024, smem, s>>>(g);
+  if (n + 1 <= 13 * 32) sinkhorn_train_fwd_kernel<13><<<batch, 1024, smem, s>>>(g);
+  else sinkhorn_train_fwd_kernel<33><<<batch, 1024, smem, s>>>(g);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }
@@ -195,18 +252,16 @@ extern "C" int mvm_sinkhorn_train_forward(const float* scores, const float* alph
 // on return (its inner block is d scores); d_alpha (one double, zeroed by the caller) += the dustbin entries.
 extern "C" int mvm_sinkhorn_train_backward(const float* scores, const float* alpha, const float* pot, int batch, int m, int n,
                                            int iters, float* dZ, double* d_alpha, void* stream) {
-  MVM_REQUIRE(scores && alpha && pot && dZ && d_alpha && batch >= 1 && m >= 1 && n >= 1 && iters >= 1 && m <= 8192 && n <= 8192);
+  MVM_REQUIRE(scores && alpha && pot && dZ && d_alpha && batch >= 1 && m >= 1 && n >= 1 && iters >= 1 && m <= SK_MAX_N && n <= SK_MAX_N);
   SkArgs g;
   g.scores = scores; g.out = dZ; g.pot = const_cast<float*>(pot); g.alpha_p = alpha; g.d_alpha = d_alpha;
   g.m = m; g.n = n; g.iters = iters;
-  const int smem = (2 * (m + 1) + 3 * (n + 1)) * 4;
-  mvm_once_per_device(MVM_ONCE_SINKHORN_TRAIN, [&] {
-    cudaFuncSetAttribute(sinkhorn_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8194 * 4);
-    cudaFuncSetAttribute(sinkhorn_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 8194 * 4);
-  });
+  const int smem = bwd_smem(m, n);
+  set_attrs();
   cudaStream_t s = (cudaStream_t)stream;
   MvmProfScope prof__(MVM_TAG_SINKHORN, s);
-  sinkhorn_train_bwd_kernel<<<batch, 1024, smem, s>>>(g);
+  if (n + 1 <= 13 * 32) sinkhorn_train_bwd_kernel<13><<<batch, 1024, smem, s>>>(g);
+  else sinkhorn_train_bwd_kernel<33><<<batch, 1024, smem, s>>>(g);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }

@@ -145,23 +145,28 @@ def _forward(model, data, view_ids=None, save=False, debug=None):
     slot = {v: s for s, v in enumerate(ids)}
     alpha = model.bin_score.detach().float().reshape(1).contiguous()
     iters = int(cfg['sinkhorn_iterations'])
+    # score matrices of every pair, then ONE optimal-transport launch over all (pair, tuple) problems.  The log-domain
+    # training kernel keeps the potentials of every iteration; couplings of an untrained / early-training network span
+    # thousands of nats, beyond the range of the scaling-domain kernels of the eval path.
+    pair_list = [(id0, id1) for id1 in ids for id0 in ids if id0 < id1]
+    raws = []
+    for id0, id1 in pair_list:
+        a, b_ = slot[id0], slot[id1]
+        for i in range(B):
+            raws.append(_lin(md[i, a, :N], md[i, b_, :N], None, alpha=1.0 / 16.0))                    # [N, N]
+    raw_all = torch.stack(raws, 0)                                                                    # [P * B, N, N]
+    with _lib.device_ctx(dev):
+        Z_all, pot_all = ops.sinkhorn_train_forward(raw_all, alpha, iters)
     pairs_saved = []
-    for id1 in ids:
-        for id0 in ids:
-            if id0 >= id1:
-                continue
+    for p_, (id0, id1) in enumerate(pair_list):
             a, b_ = slot[id0], slot[id1]
-            m0 = md[:, a, :N].contiguous()                                    # [B, N, 256]
+            m0 = md[:, a, :N].contiguous()
             m1 = md[:, b_, :N].contiguous()
-            raw = torch.stack([_lin(m0[i], m1[i], None, alpha=1.0 / 16.0) for i in range(B)], 0)      # [B, N, N]
-            # log-domain kernel that keeps the potentials of every iteration: couplings of an untrained / early-training
-            # network span thousands of nats, beyond the range of the scaling-domain kernels of the eval path
-            with _lib.device_ctx(dev):
-                Z, pot = ops.sinkhorn_train_forward(raw, alpha, iters)
+            Z = Z_all[p_ * B:(p_ + 1) * B]
             key = '{}_{}'.format(id0, id1)
             result['scores_' + key] = Z
             if save:
-                pairs_saved.append((key, a, b_, raw, pot))
+                pairs_saved.append((key, a, b_))
             if not full:
                 continue
             i0, i1, s0, s1 = ops.extract_matches(Z, model.match_threshold)
@@ -189,6 +194,7 @@ def _forward(model, data, view_ids=None, save=False, debug=None):
         S.dims = (B, T, N, n_pad, rows, g_bn)
         S.inp, S.kenc, S.kenc_last_in, S.layers, S.x_final, S.md = inp, kenc_saved, h, layers_saved, x, md
         S.pairs, S.alpha, S.iters, S.perm, S.dev = pairs_saved, alpha, iters, perm, dev
+        S.raw_all, S.pot_all = raw_all, pot_all
     return result, S
 
 
@@ -205,15 +211,17 @@ def _backward(model, S, grads):
     with _lib.device_ctx(dev):
         # ---- optimal transport and the score products (multi_view_matcher.py:275-285)
         g_md = torch.zeros(B, T, n_pad, 256, dtype=torch.float32, device=dev)
-        d_alpha = torch.zeros(1, dtype=torch.float64, device=dev)
-        for key, a, b_, raw, pot in S.pairs:
+        G_all = torch.zeros(len(S.pairs) * B, N + 1, N + 1, dtype=torch.float32, device=dev)
+        for p_, (key, a, b_) in enumerate(S.pairs):
             go = grads.get('scores_' + key)
-            if go is None:
+            if go is not None:
+                G_all[p_ * B:(p_ + 1) * B] = go
+        dZ_all, d_alpha = ops.sinkhorn_train_backward(S.raw_all, S.alpha, S.pot_all, S.iters, G_all)      # ONE launch
+        for p_, (key, a, b_) in enumerate(S.pairs):
+            if grads.get('scores_' + key) is None:
                 continue
-            dZ, da = ops.sinkhorn_train_backward(raw, S.alpha, pot, S.iters, go)
-            d_alpha += da
             dS = torch.zeros(B, n_pad, n_pad, dtype=torch.float32, device=dev)
-            dS[:, :N, :N] = dZ[:, :N, :N]
+            dS[:, :N, :N] = dZ_all[p_ * B:(p_ + 1) * B, :N, :N]
             for i in range(B):
                 # scores = m0 m1^T / 16:  d m0 = dS m1 / 16,  d m1 = dS^T m0 / 16
                 _, hi, lo = ops.transpose_split(S.md[i, b_])
