@@ -93,6 +93,10 @@ def lib():
     L.mvm_transpose_split.argtypes = [_fp, I, I, I, _fp, _fp, _fp, C.c_longlong, _fp]
     L.mvm_attention_backward.restype = I
     L.mvm_attention_backward.argtypes = [_fp, _fp, _fp, _fp, _fp, I, I, I, C.POINTER(C.c_int), I, _fp]
+    L.mvm_linear_tc_presplit_splitk.restype = I
+    L.mvm_linear_tc_presplit_splitk.argtypes = [_fp, I, _fp, _fp, I, _fp, I, I, I, I, F, I, _fp, _fp]
+    L.mvm_debug_set_attention_backward_variant.restype = I
+    L.mvm_debug_set_attention_backward_variant.argtypes = [I]
     L.mvm_sinkhorn_train_pot_floats.restype = C.c_size_t
     L.mvm_sinkhorn_train_pot_floats.argtypes = [I, I, I, I]
     L.mvm_sinkhorn_train_forward.restype = I

@@ -67,6 +67,10 @@ struct PArgs {
   // KLO, VT and VTLO
   __half* KH16; __half* KL16; __half* VH16; __half* VL16;
   int tiles_m, tiles_n;
+  // split-K (weight-gradient GEMMs: few output tiles, a very long contraction): K is cut into `ksplit` slices, slice s is
+  // an extra group of row tiles writing its partial product to rows [s * tiles_m * BM, ...) of C (a slab buffer that a
+  // small kernel sums afterwards, in fixed order).  1 = off.
+  int ksplit;
 };
 
 // SCORE mode: one launch computes every (pair, tuple) score matrix  scores = mdesc_a . mdesc_b^T * alpha  into the
@@ -127,13 +131,15 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = g.K / BK;
+  const int nk = SCORE ? g.K / BK : g.K / BK / g.ksplit;       // k-blocks per tile (per K slice)
   const int per_prob = g.tiles_m * g.tiles_n;
-  const int n_tiles = SCORE ? per_prob * st.n_pairs * st.batch : per_prob;
+  const int n_tiles = SCORE ? per_prob * st.n_pairs * st.batch : per_prob * g.ksplit;
   // tile -> output tile origin (m0, n0) and the rows the A / W boxes start at
   auto decode = [&](int tile, int& m0, int& n0, int& a_row, int& w_row, int& prob) {
     if (!SCORE) {
-      m0 = (tile / g.tiles_n) * BM; n0 = (tile % g.tiles_n) * BN; a_row = m0; w_row = n0; prob = 0;
+      const int r = tile % per_prob;
+      prob = tile / per_prob;                                   // K slice (0 without split-K)
+      m0 = (r / g.tiles_n) * BM; n0 = (r % g.tiles_n) * BN; a_row = m0; w_row = n0;
     } else {
       prob = tile / per_prob;
       const int r = tile % per_prob;
@@ -176,7 +182,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (tc::elect_one()) {
           tc::mbar_arrive_expect_tx(full + s, STAGE_BYTES);
           uint8_t* sp = smem + s * STAGE_BYTES;
-          const int k = kt * BK;
+          const int k = kt * BK + (SCORE ? 0 : prob * nk * BK);
           if (k < g.K1) tc::tma_load_2d(sp, &tmA, full + s, k, a_row);
           else tc::tma_load_2d(sp, &tmA2, full + s, k - g.K1, a_row);
           if (F16) {   // second [128 x 32] fp32 box of the 64-wide k-block (K1 is a multiple of 64: same side of the concat)
@@ -429,7 +435,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int j = 0; j < 8; ++j) so[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           tc::fence_proxy_async();
           __syncwarp();
-          if (tc::elect_one()) { tc::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, nb, m0 + q * 32); tc::tma_store_commit(); }
+          const int c_row = m0 + q * 32 + (SCORE ? 0 : prob * g.tiles_m * BM);     // split-K: slab of this K slice
+          if (tc::elect_one()) { tc::tma_store_2d(&tmC, stg + sbuf * STG_BYTES, nb, c_row); tc::tma_store_commit(); }
           sbuf ^= 1;
         }
       }
@@ -449,7 +456,11 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 // Requirements (checked by the dispatcher in gemm_tc.cu): pre-split W planes, N % 128 == 0, K % 32 == 0,
 // K1 % 32 == 0, 16-byte aligned rows.
 int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO,
-                           cudaStream_t stream, const HalfPlanes* hp) {
+                           cudaStream_t stream, const HalfPlanes* hp, int ksplit, float* slabs) {
+  // split-K: partial products of the K slices go to slabs [ksplit, M, N] (M a multiple of the tile height), summed by
+  // launch_splitk_reduce afterwards; no bias / residual / activation / concat in that mode
+  MVM_REQUIRE(ksplit >= 1 && (ksplit == 1 || (slabs && d.M % BM == 0 && d.K % (32 * ksplit) == 0 && !d.Whi16 && !d.bias && !d.R && !d.A2 &&
+                                               !d.relu && !VT && !KLO && !hp)));
   mvm_once_per_device(MVM_ONCE_GEMM_PERSIST, [&] {
     cudaFuncSetAttribute(gemm_tc_persist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(gemm_tc_persist_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -461,7 +472,7 @@ int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad,
   const CUtensorMap* tA2 = d.A2 ? mvm_get_tmap_2d(d.A2, d.M, d.K - d.K1, d.lda2, BM) : tA;
   const CUtensorMap* tWhi = f16 ? mvm_get_tmap_2d_f16(d.Whi16, d.N, d.K, d.ldw, BN) : mvm_get_tmap_2d(d.Whi, d.N, d.K, d.ldw, BN);
   const CUtensorMap* tWlo = f16 ? mvm_get_tmap_2d_f16(d.Wlo16, d.N, d.K, d.ldw, BN) : mvm_get_tmap_2d(d.Wlo, d.N, d.K, d.ldw, BN);
-  const CUtensorMap* tC = mvm_get_tmap_2d(d.C, d.M, d.N, d.ldc, 32);
+  const CUtensorMap* tC = ksplit > 1 ? mvm_get_tmap_2d(slabs, (long long)ksplit * d.M, d.N, d.N, 32) : mvm_get_tmap_2d(d.C, d.M, d.N, d.ldc, 32);
   const CUtensorMap* tK = KLO ? mvm_get_tmap_2d(KLO, d.M, 256, 256, 32) : tC;
   const CUtensorMap* tKH = hp ? mvm_get_tmap_2d_f16_store(hp->kh, d.M, 256, 256) : tC;
   const CUtensorMap* tKL = hp ? mvm_get_tmap_2d_f16_store(hp->kl, d.M, 256, 256) : tC;
@@ -469,18 +480,42 @@ int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad,
   const CUtensorMap* tVL = hp ? mvm_get_tmap_2d_f16_store(hp->vl, d.M, 256, 256) : tC;
   if (!tA || !tA2 || !tWhi || !tWlo || !tC || !tK || !tKH || !tKL || !tVH || !tVL) return MVM_ERR_LAUNCH;
   PArgs g;
-  g.bias = d.bias; g.R = d.R; g.ldr = d.ldr; g.C = d.C; g.ldc = d.ldc; g.M = d.M; g.N = d.N; g.K = d.K;
+  g.bias = d.bias; g.R = d.R; g.ldr = d.ldr; g.C = ksplit > 1 ? slabs : d.C; g.ldc = ksplit > 1 ? d.N : d.ldc; g.M = d.M; g.N = d.N; g.K = d.K;
   g.K1 = d.K1; g.alpha = f16 ? d.alpha / d.wscale : d.alpha; g.relu = d.relu; g.VT = VT; g.vt_col0 = vt_col0; g.n_pad = n_pad;
   g.KLO = KLO; g.VTLO = VTLO;
   g.KH16 = hp ? (__half*)hp->kh : nullptr; g.KL16 = hp ? (__half*)hp->kl : nullptr;
   g.VH16 = hp ? (__half*)hp->vh : nullptr; g.VL16 = hp ? (__half*)hp->vl : nullptr;
   g.tiles_m = mvm_div_up(d.M, BM); g.tiles_n = d.N / BN;
-  const int n_tiles = g.tiles_m * g.tiles_n;
+  g.ksplit = ksplit;
+  const int n_tiles = g.tiles_m * g.tiles_n * ksplit;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   ScoreTab none;
   none.n_pairs = 0; none.batch = 0; none.n_views = 0; none.n_pad = 0;
   if (f16) gemm_tc_persist_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, *tKH, *tKL, *tVH, *tVL, g, none);
   else gemm_tc_persist_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*tA, *tA2, *tWhi, *tWlo, *tC, *tK, *tKH, *tKL, *tVH, *tVL, g, none);
+  MVM_CHECK_LAUNCH();
+  return MVM_OK;
+}
+
+namespace {
+// C[m, n] = sum_s slabs[s][m][n] (fixed order: deterministic)
+__global__ void splitk_reduce_kernel(const float4* __restrict__ slabs, float* __restrict__ C, int M, int N4, int ldc, int S) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N4) return;
+  const int m = (int)(i / N4), n4 = (int)(i % N4);
+  float4 a = slabs[i];
+  for (int s = 1; s < S; ++s) {
+    const float4 b = slabs[(long long)s * M * N4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  *reinterpret_cast<float4*>(C + (long long)m * ldc + 4 * n4) = a;
+}
+}  // namespace
+
+int launch_splitk_reduce(const float* slabs, float* C, int M, int N, int ldc, int ksplit, cudaStream_t stream) {
+  MVM_REQUIRE(N % 4 == 0 && ldc % 4 == 0);
+  const long long n = (long long)M * (N / 4);
+  splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(slabs), C, M, N / 4, ldc, ksplit);
   MVM_CHECK_LAUNCH();
   return MVM_OK;
 }
@@ -527,7 +562,7 @@ int launch_score_gemm_tc(const float* mdesc, float* hi, float* lo, int n_pad, co
   }
   PArgs g;
   memset(&g, 0, sizeof(g));
-  g.K = 256; g.K1 = 256; g.alpha = alpha;
+  g.K = 256; g.K1 = 256; g.alpha = alpha; g.ksplit = 1;
   g.tiles_m = mvm_div_up(max_m, BM); g.tiles_n = mvm_div_up(max_n, BN);
   const long long n_tiles = (long long)g.tiles_m * g.tiles_n * tab.n_pairs * batch;
   const int grid = n_tiles < n_sm ? (int)n_tiles : n_sm;

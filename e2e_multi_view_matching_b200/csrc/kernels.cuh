@@ -39,7 +39,8 @@ int mvm_default_gemm_persistent();
 // launch_attention_h3 instead of the fp32 / tf32 buffers (kh, kl, vh, vl: all [rows, 256], as __half; V stays key-major)
 struct HalfPlanes { void* kh; void* kl; void* vh; void* vl; };
 int launch_gemm_tc_persist(const GemmDesc& d, float* VT, int vt_col0, int n_pad, float* KLO, float* VTLO,
-                           cudaStream_t stream, const HalfPlanes* hp = nullptr);
+                           cudaStream_t stream, const HalfPlanes* hp = nullptr, int ksplit = 1, float* slabs = nullptr);
+int launch_splitk_reduce(const float* slabs, float* C, int M, int N, int ldc, int ksplit, cudaStream_t stream);
 // every (pair, tuple) score matrix in one launch of the persistent kernel (3xTF32); hi / lo: scratch [rows, 256]
 struct PairTable;
 int launch_score_gemm_tc(const float* mdesc, float* hi, float* lo, int n_pad, const PairTable& tab, int batch,

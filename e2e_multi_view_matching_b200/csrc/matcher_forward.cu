@@ -324,6 +324,18 @@ int mvm_linear_tc_presplit(const float* A, int lda, const float* A2, int lda2, i
   return launch_gemm_tc(g, 3, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
+int mvm_linear_tc_presplit_splitk(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, float* C, int ldc,
+                                  int M, int N, int K, float alpha, int ksplit, float* ws, void* stream) {
+  MVM_REQUIRE(A && W_hi && W_lo && C && ws && ksplit >= 2 && M % 128 == 0 && N % 128 == 0 && K % (32 * ksplit) == 0);
+  MVM_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && ldc % 4 == 0);
+  GemmDesc g = make_gemm(A, lda, W_hi, K, nullptr, C, ldc, M, N, 0);
+  g.ldw = ldw; g.alpha = alpha; g.Whi = W_hi; g.Wlo = W_lo;
+  MvmProfScope prof__(MVM_TAG_GEMM, (cudaStream_t)stream);
+  int rc = launch_gemm_tc_persist(g, nullptr, 0, 0, nullptr, nullptr, (cudaStream_t)stream, nullptr, ksplit, ws);
+  if (rc != MVM_OK) return rc;
+  return launch_splitk_reduce(ws, C, M, N, ldc, ksplit, (cudaStream_t)stream);
+}
+
 int mvm_linear_tc_h16(const float* A, int lda, const float* A2, int lda2, int K1, const void* W16_hi, const void* W16_lo,
                       float wscale, int ldw, const float* bias, const float* R, int ldr, float* C, int ldc, int M, int N, int K,
                       float alpha, int relu, void* stream) {

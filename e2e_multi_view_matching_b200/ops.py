@@ -200,6 +200,20 @@ def linear_presplit(a, w_hi, w_lo, residual=None, alpha=1.0):
     return out
 
 
+def linear_presplit_splitk(a, w_hi, w_lo, ksplit, alpha=1.0):
+    """linear_presplit for few output tiles and a very long contraction: K cut into `ksplit` slices computed by different
+    CTAs of the persistent kernel and summed in fixed order (mvm_linear_tc_presplit_splitk)."""
+    lib = _lib.lib()
+    M, K = a.shape
+    N = w_hi.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    ws = torch.empty(ksplit * M * N, dtype=torch.float32, device=a.device)
+    _lib.check(lib.mvm_linear_tc_presplit_splitk(_lib.ptr(a), a.stride(0), _lib.ptr(w_hi), _lib.ptr(w_lo), w_hi.stride(0),
+                                                 _lib.ptr(out), N, M, N, K, float(alpha), int(ksplit), _lib.ptr(ws),
+                                                 _lib.stream_ptr()), 'mvm_linear_tc_presplit_splitk')
+    return out
+
+
 def gemm_dx(dy, w, residual=None, alpha=1.0):
     """Gradient w.r.t. the input of y = x @ w^T: dy [M, N_out] @ w [N_out, K_in] (+ residual) -> [M, K_in]."""
     n_out, k_in = w.shape
@@ -225,6 +239,12 @@ def gemm_dw(dy, x, x2=None, alpha=1.0):
         transpose_split(x, out=(None, hi[:k1], lo[:k1]))
         if x2 is not None:
             transpose_split(x2, out=(None, hi[k1:], lo[k1:]))
+        # few output tiles, a very long contraction: cut K = rows into slices for different CTAs (split-K)
+        tiles = (n_out // 128) * (k_in // 128) if n_out % 128 == 0 else 0
+        kb = rows // 32
+        ks = max([s_ for s_ in range(1, 65) if kb % s_ == 0 and kb // s_ >= 8 and tiles * s_ <= 148] or [1]) if tiles else 1
+        if ks >= 2:
+            return linear_presplit_splitk(dyt, hi, lo, ks, alpha=alpha)
         return linear_presplit(dyt, hi, lo, alpha=alpha)
     xt = torch.empty(k_in, rows, dtype=torch.float32, device=dev)
     transpose_split(x, out=(xt[:k1], None, None))

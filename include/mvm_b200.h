@@ -157,6 +157,12 @@ int mvm_linear_tc_presplit(const float* A, int lda, const float* A2, int lda2, i
                            const float* W_lo, int ldw, const float* bias, const float* R, int ldr, float* C,
                            int ldc, int M, int N, int K, float alpha, int relu, void* stream);
 
+/* mvm_linear_tc_presplit for GEMMs with few output tiles and a very long contraction (the weight gradients of training:
+ * M, N <= 768, K = all points of the batch): K is cut into ksplit slices computed by different CTAs of the persistent
+ * kernel into ws [ksplit, M, N] and summed in fixed order.  M, N multiples of 128, K of 32 * ksplit; no bias / residual. */
+int mvm_linear_tc_presplit_splitk(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, float* C, int ldc,
+                                  int M, int N, int K, float alpha, int ksplit, float* ws, void* stream);
+
 /* fp16x3 on the persistent kernel: W16_hi / W16_lo = fp16 planes of wscale * W (hi = fp16(wscale W), lo = fp16(wscale W - hi));
  * K and K1 multiples of 64, N of 128. */
 int mvm_linear_tc_h16(const float* A, int lda, const float* A2, int lda2, int K1, const void* W16_hi, const void* W16_lo,
@@ -387,6 +393,9 @@ int mvm_transpose_split(const float* x, int R, int C, int ld, float* raw, float*
  * beyond counts[t] are masked (zero gradient).  ws: 2 * batch*n_views * 4 * n_pad floats.  Deterministic. */
 int mvm_attention_backward(const float* qkv, const float* out, const float* dout, float* dqkv, float* ws, int batch,
                            int n_views, int n_pad, const int* counts, int is_cross, void* stream);
+/* process default of its kernels: 1 = tile products on the tensor cores (mma.sync TF32 x 3 split passes, default),
+ * 0 = fp32 CUDA cores (cross-check) */
+int mvm_debug_set_attention_backward_variant(int variant);
 
 /* log_optimal_transport for training (superglue.py:143-172): scores [batch, m, n] and the device scalar alpha
  * (bin_score) -> couplings out [batch, m+1, n+1], keeping the potentials of every iteration in pot

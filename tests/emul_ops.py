@@ -83,6 +83,10 @@ def linear_presplit(a, w_hi, w_lo, residual=None, alpha=1.0):
     return y.float()
 
 
+def linear_presplit_splitk(a, w_hi, w_lo, ksplit, alpha=1.0):
+    return linear_presplit(a, w_hi, w_lo, alpha=alpha)
+
+
 def colsum(x):
     return x.to(D).sum(0).float()
 

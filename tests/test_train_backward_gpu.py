@@ -19,10 +19,12 @@ def _rel(got, ref):
     return float((got.double().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
 
 
+@pytest.mark.parametrize('variant', [1, 0])       # 1 = mma.sync TF32x3 (default), 0 = fp32 CUDA cores
 @pytest.mark.parametrize('is_cross,counts', [(0, [128, 128]), (1, [128, 128, 128]), (1, [100, 100, 100, 100]), (0, [70, 128, 33]),
                                              (1, [70, 128, 33])])
-def test_attention_backward_vs_torch(is_cross, counts):
-    from e2e_multi_view_matching_b200 import ops
+def test_attention_backward_vs_torch(is_cross, counts, variant):
+    from e2e_multi_view_matching_b200 import ops, _lib
+    _lib.lib().mvm_debug_set_attention_backward_variant(variant)
     g = torch.Generator().manual_seed(5 + is_cross + len(counts))
     T, B, n_pad = len(counts), 2, 128
     qkv = torch.randn(B * T, n_pad, 768, generator=g) * 1.5
@@ -31,11 +33,14 @@ def test_attention_backward_vs_torch(is_cross, counts):
         dout[v, counts[v % T]:] = 0          # the gradient of padding rows is zero by construction
     out = emul_ops.attention(qkv, B, T, counts, is_cross)
     ref = emul_ops.attention_backward(qkv, out, dout, B, T, counts, is_cross)
-    got = ops.attention_backward(qkv.cuda(), out.cuda(), dout.cuda(), B, T, counts, is_cross)
-    torch.cuda.synchronize()
+    try:
+        got = ops.attention_backward(qkv.cuda(), out.cuda(), dout.cuda(), B, T, counts, is_cross)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().mvm_debug_set_attention_backward_variant(1)
     for name, lo in (('dq', 0), ('dk', 256), ('dv', 512)):
         e = _rel(got[:, :, lo:lo + 256], ref[:, :, lo:lo + 256])
-        print('attention backward', 'cross' if is_cross else 'self', counts, name, 'rel err %.2e' % e)
+        print('attention backward variant', variant, 'cross' if is_cross else 'self', counts, name, 'rel err %.2e' % e)
         assert e < 2e-5, (name, e)
     for v in range(B * T):
         assert float(got[v, counts[v % T]:].abs().max()) == 0.0 if counts[v % T] < n_pad else True
@@ -90,7 +95,8 @@ def test_sinkhorn_train_vs_autograd(m, n, spread):
 
 
 @pytest.mark.parametrize('rows,n_out,k_in,k2', [(384, 256, 256, 0), (896, 512, 256, 256), (384, 768, 256, 0), (384, 64, 32, 0),
-                                                (384, 32, 16, 0), (384, 256, 128, 0)])
+                                                (384, 32, 16, 0), (384, 256, 128, 0), (17920, 256, 256, 0), (8960, 512, 256, 256),
+                                                (4480, 768, 256, 0)])     # the last three: split-K weight gradients
 def test_backward_gemms_vs_fp64(rows, n_out, k_in, k2):
     from e2e_multi_view_matching_b200 import ops
     g = torch.Generator().manual_seed(rows + n_out)
