@@ -100,9 +100,12 @@ def lib():
     L.mvm_sinkhorn_train_pot_floats.restype = C.c_size_t
     L.mvm_sinkhorn_train_pot_floats.argtypes = [I, I, I, I]
     L.mvm_sinkhorn_train_forward.restype = I
-    L.mvm_sinkhorn_train_forward.argtypes = [_fp, _fp, I, I, I, I, _fp, _fp, _fp]
+    L.mvm_sinkhorn_train_forward.argtypes = [_fp, C.c_longlong, C.c_longlong, _fp, I, I, I, I, _fp, _fp, _fp]
     L.mvm_sinkhorn_train_backward.restype = I
-    L.mvm_sinkhorn_train_backward.argtypes = [_fp, _fp, _fp, I, I, I, I, _fp, _fp, _fp]
+    L.mvm_sinkhorn_train_backward.argtypes = [_fp, C.c_longlong, C.c_longlong, _fp, _fp, I, I, I, I, _fp, _fp, _fp]
+    L.mvm_pair_scores.restype = I
+    L.mvm_pair_scores.argtypes = [_fp, _fp, _fp, I, I, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I),
+                                  C.POINTER(C.c_void_p), F, _fp]
     L.mvm_pack_views.restype = C.c_int
     L.mvm_pack_views.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int),
                                  C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]

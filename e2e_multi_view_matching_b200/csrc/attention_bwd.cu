@@ -292,19 +292,29 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const __grid_constant
 
 // ======================================================================================================================
 // Tensor-core variant (default): the same two kernels with the 64 x 64 x 64 products on mma.sync m16n8k8 TF32, every
-// product as three MMAs on split operands (x = hi + lo, hi = rn_tf32(x), lo = rn_tf32(x - hi); lo.lo dropped) with fp32
+// product as three MMAs on split operands (x = hi + lo, hi = x truncated to tf32, lo = x - hi; lo.lo dropped) with fp32
 // accumulation -- fp32-faithful like the 3xTF32 GEMMs.  8 warps: warp w owns rows (w & 3) * 16 .. + 16 and columns
 // (w >> 2) * 32 .. + 32 of a tile product; a thread holds rows gid, gid + 8 and columns 2 tig, 2 tig + 1 of each of its
 // four 8-column blocks (gid = lane / 4, tig = lane % 4).
 // ======================================================================================================================
-__device__ __forceinline__ uint32_t tf32_bits(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return u;
+constexpr int LDM = 72;             // row pitch of the tensor-core variant's tiles (conflict-free for every fragment pattern below)
+constexpr int TILE_M = BT * LDM;
+
+__device__ __forceinline__ void load_tile_m(float* s, const float* g, long long ld, int nvalid, int tid) {
+  for (int i = tid; i < 64 * 16; i += 256) {
+    const int r = i >> 4, c4 = (i & 15) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nvalid) x = *reinterpret_cast<const float4*>(g + (long long)r * ld + c4);
+    *reinterpret_cast<float4*>(s + r * LDM + c4) = x;
+  }
 }
+
+// x = hi + lo with hi = x truncated to tf32 (one logic op) and lo = x - hi (exact; the tensor core reads its upper 19
+// bits).  The ncu capture of the first version (cvt.rna on both parts: 3 conversions / subtractions per fragment element
+// in the inner loop) had the ALU pipe as its top pipe at 51 %, the tensor pipe at 36-42 %.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = tf32_bits(x);
-  lo = tf32_bits(x - __uint_as_float(hi));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -315,18 +325,25 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 // acc[nt][.] += A(16 rows m0.. x 64) * B(64 x 8 columns n0 + 8 nt ..), nt = 0..3.
 //   A_T == false: A stored [m][k] (row-major),  A_T == true: A stored [k][m]
 //   B_T == true:  B stored [n][k] ("NT" product, both operands contraction-contiguous),  B_T == false: B stored [k][n]
+// NT products relabel the contraction index inside a k-step (fragment slots k = tig / tig + 4 read the memory columns
+// 2 tig / 2 tig + 1 of BOTH operands), so that every fragment pair is one 64-bit shared-memory load.
 template <bool A_T, bool B_T>
 __device__ __forceinline__ void warp_mma(float (&acc)[4][4], const float* __restrict__ A, const float* __restrict__ B,
                                          int m0, int n0, int gid, int tig) {
+  constexpr bool PAIR = !A_T && B_T;
 #pragma unroll 2
   for (int k0 = 0; k0 < 64; k0 += 8) {
     float af[4];
-    if (!A_T) {
-      af[0] = A[(m0 + gid) * LD + k0 + tig];      af[1] = A[(m0 + gid + 8) * LD + k0 + tig];
-      af[2] = A[(m0 + gid) * LD + k0 + tig + 4];  af[3] = A[(m0 + gid + 8) * LD + k0 + tig + 4];
+    if (PAIR) {
+      const float2 x = *reinterpret_cast<const float2*>(A + (m0 + gid) * LDM + k0 + 2 * tig);
+      const float2 y = *reinterpret_cast<const float2*>(A + (m0 + gid + 8) * LDM + k0 + 2 * tig);
+      af[0] = x.x; af[2] = x.y; af[1] = y.x; af[3] = y.y;
+    } else if (!A_T) {
+      af[0] = A[(m0 + gid) * LDM + k0 + tig];      af[1] = A[(m0 + gid + 8) * LDM + k0 + tig];
+      af[2] = A[(m0 + gid) * LDM + k0 + tig + 4];  af[3] = A[(m0 + gid + 8) * LDM + k0 + tig + 4];
     } else {
-      af[0] = A[(k0 + tig) * LD + m0 + gid];      af[1] = A[(k0 + tig) * LD + m0 + gid + 8];
-      af[2] = A[(k0 + tig + 4) * LD + m0 + gid];  af[3] = A[(k0 + tig + 4) * LD + m0 + gid + 8];
+      af[0] = A[(k0 + tig) * LDM + m0 + gid];      af[1] = A[(k0 + tig) * LDM + m0 + gid + 8];
+      af[2] = A[(k0 + tig + 4) * LDM + m0 + gid];  af[3] = A[(k0 + tig + 4) * LDM + m0 + gid + 8];
     }
     uint32_t ahi[4], alo[4];
 #pragma unroll
@@ -335,8 +352,9 @@ __device__ __forceinline__ void warp_mma(float (&acc)[4][4], const float* __rest
     for (int nt = 0; nt < 4; ++nt) {
       const int n = n0 + nt * 8 + gid;
       float bf[2];
-      if (B_T) { bf[0] = B[n * LD + k0 + tig]; bf[1] = B[n * LD + k0 + tig + 4]; }
-      else     { bf[0] = B[(k0 + tig) * LD + n]; bf[1] = B[(k0 + tig + 4) * LD + n]; }
+      if (PAIR) { const float2 x = *reinterpret_cast<const float2*>(B + n * LDM + k0 + 2 * tig); bf[0] = x.x; bf[1] = x.y; }
+      else if (B_T) { bf[0] = B[n * LDM + k0 + tig]; bf[1] = B[n * LDM + k0 + tig + 4]; }
+      else     { bf[0] = B[(k0 + tig) * LDM + n]; bf[1] = B[(k0 + tig + 4) * LDM + n]; }
       uint32_t bhi[2], blo[2];
       split_tf32(bf[0], bhi[0], blo[0]);
       split_tf32(bf[1], bhi[1], blo[1]);
@@ -350,10 +368,10 @@ __device__ __forceinline__ void warp_mma(float (&acc)[4][4], const float* __rest
 __global__ void __launch_bounds__(256) attn_bwd_dq_mma_kernel(const __grid_constant__ BwdArgs g) {
   extern __shared__ __align__(16) float smem[];
   float* Qs = smem;
-  float* dOs = Qs + TILE;
-  float* Ks = dOs + TILE;
-  float* Vs = Ks + TILE;
-  float* Ss = Vs + TILE;
+  float* dOs = Qs + TILE_M;
+  float* Ks = dOs + TILE_M;
+  float* Vs = Ks + TILE_M;
+  float* Ss = Vs + TILE_M;
   __shared__ float Lsm[64], Dsm[64], Pm[2][64], Pl[2][64];
   const int q0 = blockIdx.x * BT, h = blockIdx.y, v = blockIdx.z;
   const int T = g.segs.n_views, t = v % T, b = v / T, n_pad = g.n_pad;
@@ -372,15 +390,15 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_mma_kernel(const __grid_const
     return;
   }
   const int nvq = min(64, cnt_q - q0);
-  load_tile(Qs, g.qkv + ((long long)v * n_pad + q0) * QKV_LD + h * 64, QKV_LD, nvq, tid);
-  load_tile(dOs, g.dout + ((long long)v * n_pad + q0) * O_LD + h * 64, O_LD, nvq, tid);
-  load_tile(Ks, g.out + ((long long)v * n_pad + q0) * O_LD + h * 64, O_LD, nvq, tid);
+  load_tile_m(Qs, g.qkv + ((long long)v * n_pad + q0) * QKV_LD + h * 64, QKV_LD, nvq, tid);
+  load_tile_m(dOs, g.dout + ((long long)v * n_pad + q0) * O_LD + h * 64, O_LD, nvq, tid);
+  load_tile_m(Ks, g.out + ((long long)v * n_pad + q0) * O_LD + h * 64, O_LD, nvq, tid);
   __syncthreads();
   {   // D_i = dO_i . O_i : four threads per row
     const int r = tid >> 2, p = tid & 3;
     float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) s = fmaf(dOs[r * LD + p * 16 + d], Ks[r * LD + p * 16 + d], s);
+    for (int d = 0; d < 16; ++d) s = fmaf(dOs[r * LDM + p * 16 + d], Ks[r * LDM + p * 16 + d], s);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     if (p == 0) Dsm[r] = s;
@@ -393,7 +411,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_mma_kernel(const __grid_const
     const long long vs = (long long)b * T + s;
     for (int k0 = 0; k0 < cnt; k0 += BT) {
       __syncthreads();
-      load_tile(Ks, g.qkv + (vs * n_pad + k0) * QKV_LD + 256 + h * 64, QKV_LD, min(64, cnt - k0), tid);
+      load_tile_m(Ks, g.qkv + (vs * n_pad + k0) * QKV_LD + 256 + h * 64, QKV_LD, min(64, cnt - k0), tid);
       __syncthreads();
       float acc[4][4];
       zero16(acc);
@@ -446,8 +464,8 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_mma_kernel(const __grid_const
     const long long vs = (long long)b * T + s;
     for (int k0 = 0; k0 < cnt; k0 += BT) {
       __syncthreads();
-      load_tile(Ks, g.qkv + (vs * n_pad + k0) * QKV_LD + 256 + h * 64, QKV_LD, min(64, cnt - k0), tid);
-      load_tile(Vs, g.qkv + (vs * n_pad + k0) * QKV_LD + 512 + h * 64, QKV_LD, min(64, cnt - k0), tid);
+      load_tile_m(Ks, g.qkv + (vs * n_pad + k0) * QKV_LD + 256 + h * 64, QKV_LD, min(64, cnt - k0), tid);
+      load_tile_m(Vs, g.qkv + (vs * n_pad + k0) * QKV_LD + 512 + h * 64, QKV_LD, min(64, cnt - k0), tid);
       __syncthreads();
       float sc[4][4], dp[4][4];
       zero16(sc);
@@ -466,7 +484,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_mma_kernel(const __grid_const
             if (k0 + col < cnt) ds.x = expf(sc[nt][2 * r] * SCALE - L) * (dp[nt][2 * r] - D) * SCALE;
             if (k0 + col + 1 < cnt) ds.y = expf(sc[nt][2 * r + 1] * SCALE - L) * (dp[nt][2 * r + 1] - D) * SCALE;
           }
-          *reinterpret_cast<float2*>(Ss + row * LD + col) = ds;
+          *reinterpret_cast<float2*>(Ss + row * LDM + col) = ds;
         }
       }
       __syncthreads();
@@ -484,11 +502,11 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_mma_kernel(const __grid_const
 __global__ void __launch_bounds__(256) attn_bwd_dkv_mma_kernel(const __grid_constant__ BwdArgs g) {
   extern __shared__ __align__(16) float smem[];
   float* Ks = smem;
-  float* Vs = Ks + TILE;
-  float* Qs = Vs + TILE;
-  float* dOs = Qs + TILE;
-  float* Ps = dOs + TILE;
-  float* dSs = Ps + TILE;
+  float* Vs = Ks + TILE_M;
+  float* Qs = Vs + TILE_M;
+  float* dOs = Qs + TILE_M;
+  float* Ps = dOs + TILE_M;
+  float* dSs = Ps + TILE_M;
   __shared__ float Lsm[64], Dsm[64];
   const int k0 = blockIdx.x * BT, h = blockIdx.y, v = blockIdx.z;
   const int T = g.segs.n_views, t = v % T, b = v / T, n_pad = g.n_pad;
@@ -502,8 +520,8 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_mma_kernel(const __grid_cons
   zero16(dv);
   if (k0 < cnt_k) {
     const int nvk = min(64, cnt_k - k0);
-    load_tile(Ks, g.qkv + ((long long)v * n_pad + k0) * QKV_LD + 256 + h * 64, QKV_LD, nvk, tid);
-    load_tile(Vs, g.qkv + ((long long)v * n_pad + k0) * QKV_LD + 512 + h * 64, QKV_LD, nvk, tid);
+    load_tile_m(Ks, g.qkv + ((long long)v * n_pad + k0) * QKV_LD + 256 + h * 64, QKV_LD, nvk, tid);
+    load_tile_m(Vs, g.qkv + ((long long)v * n_pad + k0) * QKV_LD + 512 + h * 64, QKV_LD, nvk, tid);
     for (int s = 0; s < T; ++s) {
       if (!attends(g.is_cross, s, t)) continue;     // query view s attends to key view t
       const int cnt_q = g.segs.counts[s];
@@ -511,8 +529,8 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_mma_kernel(const __grid_cons
       for (int q0 = 0; q0 < cnt_q; q0 += BT) {
         const int nvq = min(64, cnt_q - q0);
         __syncthreads();
-        load_tile(Qs, g.qkv + (vq * n_pad + q0) * QKV_LD + h * 64, QKV_LD, nvq, tid);
-        load_tile(dOs, g.dout + (vq * n_pad + q0) * O_LD + h * 64, O_LD, nvq, tid);
+        load_tile_m(Qs, g.qkv + (vq * n_pad + q0) * QKV_LD + h * 64, QKV_LD, nvq, tid);
+        load_tile_m(dOs, g.dout + (vq * n_pad + q0) * O_LD + h * 64, O_LD, nvq, tid);
         if (tid < 64) {
           Lsm[tid] = g.lse[(vq * 4 + h) * n_pad + q0 + tid];
           Dsm[tid] = g.dsum[(vq * 4 + h) * n_pad + q0 + tid];
@@ -535,8 +553,8 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_mma_kernel(const __grid_cons
               if (col < nvk) p.x = expf(sc[nt][2 * r] * SCALE - L);
               if (col + 1 < nvk) p.y = expf(sc[nt][2 * r + 1] * SCALE - L);
             }
-            *reinterpret_cast<float2*>(Ps + row * LD + col) = p;
-            *reinterpret_cast<float2*>(dSs + row * LD + col) =
+            *reinterpret_cast<float2*>(Ps + row * LDM + col) = p;
+            *reinterpret_cast<float2*>(dSs + row * LDM + col) =
                 make_float2(p.x * (dp[nt][2 * r] - D) * SCALE, p.y * (dp[nt][2 * r + 1] - D) * SCALE);
           }
         }
@@ -559,6 +577,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_mma_kernel(const __grid_cons
 int g_attn_bwd_variant = 1;    // 1 = mma.sync TF32x3 (default), 0 = fp32 CUDA cores (cross-check)
 
 constexpr int SMEM_DQ = 5 * TILE * 4, SMEM_DKV = 6 * TILE * 4;
+constexpr int SMEM_DQ_M = 5 * TILE_M * 4, SMEM_DKV_M = 6 * TILE_M * 4;
 
 }  // namespace
 
@@ -578,16 +597,16 @@ extern "C" int mvm_attention_backward(const float* qkv, const float* out, const 
   mvm_once_per_device(MVM_ONCE_ATTN_BWD, [&] {
     cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ);
     cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV);
-    cudaFuncSetAttribute(attn_bwd_dq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ);
-    cudaFuncSetAttribute(attn_bwd_dkv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV);
+    cudaFuncSetAttribute(attn_bwd_dq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ_M);
+    cudaFuncSetAttribute(attn_bwd_dkv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV_M);
   });
   cudaStream_t s = (cudaStream_t)stream;
   MvmProfScope prof__(MVM_TAG_ATTN, s);
   const dim3 grid(n_pad / 64, 4, (unsigned)V);
-  if (g_attn_bwd_variant == 1) attn_bwd_dq_mma_kernel<<<grid, 256, SMEM_DQ, s>>>(g);
+  if (g_attn_bwd_variant == 1) attn_bwd_dq_mma_kernel<<<grid, 256, SMEM_DQ_M, s>>>(g);
   else attn_bwd_dq_kernel<<<grid, 256, SMEM_DQ, s>>>(g);
   MVM_CHECK_LAUNCH();
-  if (g_attn_bwd_variant == 1) attn_bwd_dkv_mma_kernel<<<grid, 256, SMEM_DKV, s>>>(g);
+  if (g_attn_bwd_variant == 1) attn_bwd_dkv_mma_kernel<<<grid, 256, SMEM_DKV_M, s>>>(g);
   else attn_bwd_dkv_kernel<<<grid, 256, SMEM_DKV, s>>>(g);
   MVM_CHECK_LAUNCH();
   return MVM_OK;

@@ -324,6 +324,21 @@ int mvm_linear_tc_presplit(const float* A, int lda, const float* A2, int lda2, i
   return launch_gemm_tc(g, 3, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
+int mvm_pair_scores(const float* mdesc, float* hi, float* lo, int batch, int n_views, int n_pad, int n_pairs, const int* pa,
+                    const int* pb, const int* m, const int* n, float* const* scores, float alpha, void* stream) {
+  MVM_REQUIRE(mdesc && hi && lo && pa && pb && m && n && scores && batch >= 1 && n_views >= 2 && n_views <= MVM_MAX_VIEWS);
+  MVM_REQUIRE(n_pairs >= 1 && n_pairs <= MVM_MAX_PAIRS && n_pad >= 64 && n_pad % 64 == 0);
+  PairTable tab;
+  memset(&tab, 0, sizeof(tab));
+  tab.n_pairs = n_pairs; tab.n_views = n_views;
+  for (int p = 0; p < n_pairs; ++p) {
+    MVM_REQUIRE(pa[p] >= 0 && pa[p] < n_views && pb[p] >= 0 && pb[p] < n_views && scores[p]);
+    MVM_REQUIRE(m[p] >= 1 && m[p] <= n_pad && n[p] >= 1 && n[p] <= n_pad);
+    tab.a[p] = pa[p]; tab.b[p] = pb[p]; tab.m[p] = m[p]; tab.n[p] = n[p]; tab.scores[p] = scores[p];
+  }
+  return launch_score_gemm_tc(mdesc, hi, lo, n_pad, tab, batch, alpha, (cudaStream_t)stream);
+}
+
 int mvm_linear_tc_presplit_splitk(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, float* C, int ldc,
                                   int M, int N, int K, float alpha, int ksplit, float* ws, void* stream) {
   MVM_REQUIRE(A && W_hi && W_lo && C && ws && ksplit >= 2 && M % 128 == 0 && N % 128 == 0 && K % (32 * ksplit) == 0);

@@ -19,7 +19,9 @@
 namespace {
 
 struct SkArgs {
-  const float* scores;   // [B, m, n]
+  const float* scores;   // problem b: rows of n scores, row stride sld, at scores + b * sstride ([B, m, n] packed, or the
+                         // inner block of [B, m+1, n+1] buffers as the score GEMM of the matcher writes them)
+  long long sld, sstride;
   float* out;            // forward: couplings [B, m+1, n+1];  backward: dZ [B, m+1, n+1] (holds G on entry)
   float* pot;            // [B, iters, m + n + 2]  (u^t | v^t)
   const float* alpha_p;  // device scalar (bin_score)
@@ -27,9 +29,10 @@ struct SkArgs {
   int m, n, iters;
 };
 
-__device__ __forceinline__ float zin(const float* __restrict__ sc, int i, int j, int m, int n, float alpha) {
-  return (i < m && j < n) ? sc[(long long)i * n + j] : alpha;
+__device__ __forceinline__ float zin_(const float* __restrict__ sc, long long sld, int i, int j, int m, int n, float alpha) {
+  return (i < m && j < n) ? sc[(long long)i * sld + j] : alpha;
 }
+#define zin(sc, i, j, m, n, alpha) zin_(sc, sld, i, j, m, n, alpha)
 
 constexpr int CH = 416;   // columns merged per shared-memory round (13 x 32)
 
@@ -52,7 +55,8 @@ __global__ void __launch_bounds__(1024) sinkhorn_train_fwd_kernel(const SkArgs g
   float* v = u + (m + 1);        // n + 1
   float* pmx = v + (n + 1);      // [32][CH] per-warp column partials
   float* psm = pmx + 32 * CH;
-  const float* sc = g.scores + (long long)b * m * n;
+  const float* sc = g.scores + (long long)b * g.sstride;
+  const long long sld = g.sld;
   const float alpha = *g.alpha_p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float norm = -logf((float)(m + n));
@@ -119,7 +123,8 @@ __global__ void __launch_bounds__(1024) sinkhorn_train_bwd_kernel(const SkArgs g
   float* gv = gu + (m + 1);     // n + 1
   float* part = gv + (n + 1);   // [32][CH] per-warp column partial sums
   __shared__ double red[32];
-  const float* sc = g.scores + (long long)b * m * n;
+  const float* sc = g.scores + (long long)b * g.sstride;
+  const long long sld = g.sld;
   float* dZ = g.out + (long long)b * (m + 1) * ld;
   const float alpha = *g.alpha_p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -233,11 +238,12 @@ extern "C" size_t mvm_sinkhorn_train_pot_floats(int batch, int m, int n, int ite
   return (size_t)batch * (size_t)iters * (size_t)(m + n + 2);
 }
 
-extern "C" int mvm_sinkhorn_train_forward(const float* scores, const float* alpha, int batch, int m, int n, int iters,
-                                          float* out, float* pot, void* stream) {
+extern "C" int mvm_sinkhorn_train_forward(const float* scores, long long scores_ld, long long scores_stride, const float* alpha,
+                                          int batch, int m, int n, int iters, float* out, float* pot, void* stream) {
+  MVM_REQUIRE(scores_ld >= n && scores_stride >= 0);
   MVM_REQUIRE(scores && alpha && out && pot && batch >= 1 && m >= 1 && n >= 1 && iters >= 1 && m <= SK_MAX_N && n <= SK_MAX_N);
   SkArgs g;
-  g.scores = scores; g.out = out; g.pot = pot; g.alpha_p = alpha; g.d_alpha = nullptr; g.m = m; g.n = n; g.iters = iters;
+  g.scores = scores; g.sld = scores_ld; g.sstride = scores_stride; g.out = out; g.pot = pot; g.alpha_p = alpha; g.d_alpha = nullptr; g.m = m; g.n = n; g.iters = iters;
   const int smem = fwd_smem(m, n);
   set_attrs();
   cudaStream_t s = (cudaStream_t)stream;
@@ -250,11 +256,13 @@ extern "C" int mvm_sinkhorn_train_forward(const float* scores, const float* alph
 
 // dZ: [B, m+1, n+1], holds the gradient w.r.t. the couplings on entry and the gradient w.r.t. the augmented score matrix
 // on return (its inner block is d scores); d_alpha (one double, zeroed by the caller) += the dustbin entries.
-extern "C" int mvm_sinkhorn_train_backward(const float* scores, const float* alpha, const float* pot, int batch, int m, int n,
-                                           int iters, float* dZ, double* d_alpha, void* stream) {
+extern "C" int mvm_sinkhorn_train_backward(const float* scores, long long scores_ld, long long scores_stride, const float* alpha,
+                                           const float* pot, int batch, int m, int n, int iters, float* dZ, double* d_alpha,
+                                           void* stream) {
+  MVM_REQUIRE(scores_ld >= n && scores_stride >= 0);
   MVM_REQUIRE(scores && alpha && pot && dZ && d_alpha && batch >= 1 && m >= 1 && n >= 1 && iters >= 1 && m <= SK_MAX_N && n <= SK_MAX_N);
   SkArgs g;
-  g.scores = scores; g.out = dZ; g.pot = const_cast<float*>(pot); g.alpha_p = alpha; g.d_alpha = d_alpha;
+  g.scores = scores; g.sld = scores_ld; g.sstride = scores_stride; g.out = dZ; g.pot = const_cast<float*>(pot); g.alpha_p = alpha; g.d_alpha = d_alpha;
   g.m = m; g.n = n; g.iters = iters;
   const int smem = bwd_smem(m, n);
   set_attrs();

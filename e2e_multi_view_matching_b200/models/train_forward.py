@@ -145,18 +145,14 @@ def _forward(model, data, view_ids=None, save=False, debug=None):
     slot = {v: s for s, v in enumerate(ids)}
     alpha = model.bin_score.detach().float().reshape(1).contiguous()
     iters = int(cfg['sinkhorn_iterations'])
-    # score matrices of every pair, then ONE optimal-transport launch over all (pair, tuple) problems.  The log-domain
+    # score matrices of every pair in one launch (score mode of the persistent GEMM, as the eval path), then ONE
+    # optimal-transport launch over all (pair, tuple) problems.  The log-domain
     # training kernel keeps the potentials of every iteration; couplings of an untrained / early-training network span
     # thousands of nats, beyond the range of the scaling-domain kernels of the eval path.
     pair_list = [(id0, id1) for id1 in ids for id0 in ids if id0 < id1]
-    raws = []
-    for id0, id1 in pair_list:
-        a, b_ = slot[id0], slot[id1]
-        for i in range(B):
-            raws.append(_lin(md[i, a, :N], md[i, b_, :N], None, alpha=1.0 / 16.0))                    # [N, N]
-    raw_all = torch.stack(raws, 0)                                                                    # [P * B, N, N]
     with _lib.device_ctx(dev):
-        Z_all, pot_all = ops.sinkhorn_train_forward(raw_all, alpha, iters)
+        raw_all = ops.pair_scores(md, [(slot[id0], slot[id1]) for id0, id1 in pair_list], N)          # [P * B, N+1, N+1]
+        Z_all, pot_all = ops.sinkhorn_train_forward(raw_all, alpha, iters, augmented=True)
     pairs_saved = []
     for p_, (id0, id1) in enumerate(pair_list):
             a, b_ = slot[id0], slot[id1]
@@ -216,7 +212,7 @@ def _backward(model, S, grads):
             go = grads.get('scores_' + key)
             if go is not None:
                 G_all[p_ * B:(p_ + 1) * B] = go
-        dZ_all, d_alpha = ops.sinkhorn_train_backward(S.raw_all, S.alpha, S.pot_all, S.iters, G_all)      # ONE launch
+        dZ_all, d_alpha = ops.sinkhorn_train_backward(S.raw_all, S.alpha, S.pot_all, S.iters, G_all, augmented=True)      # ONE launch
         for p_, (key, a, b_) in enumerate(S.pairs):
             if grads.get('scores_' + key) is None:
                 continue

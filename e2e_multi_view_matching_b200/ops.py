@@ -312,25 +312,50 @@ def attention_backward(qkv, out, dout, batch, n_views, counts, is_cross):
     return dqkv
 
 
-def sinkhorn_train_forward(scores, alpha, iters):
-    """scores [B, m, n], alpha: device scalar tensor -> (couplings [B, m+1, n+1], potentials of every iteration)."""
+def pair_scores(md, pairs, N, alpha=1.0 / 16.0):
+    """md [B, T, n_pad, 256] matching descriptors, pairs [(slot a, slot b)] -> score buffers [P * B, N + 1, N + 1] whose
+    inner blocks hold md_a md_b^T * alpha (pair-major; the dustbin row / column are left unset): one launch of the
+    persistent tcgen05 GEMM's score mode (mvm_pair_scores)."""
     lib = _lib.lib()
-    B, m, n = scores.shape
+    B, T, n_pad, _ = md.shape
+    P = len(pairs)
+    assert md.is_contiguous()
+    out = torch.empty(P * B, N + 1, N + 1, dtype=torch.float32, device=md.device)
+    hi, lo = torch.empty_like(md), torch.empty_like(md)
+    I = C.c_int * P
+    ptrs = (C.c_void_p * P)(*[out[p * B].data_ptr() for p in range(P)])
+    _lib.check(lib.mvm_pair_scores(_lib.ptr(md), _lib.ptr(hi), _lib.ptr(lo), B, T, n_pad, P, I(*[a for a, _ in pairs]),
+                                   I(*[b for _, b in pairs]), I(*([N] * P)), I(*([N] * P)), ptrs, float(alpha),
+                                   _lib.stream_ptr()), 'mvm_pair_scores')
+    return out
+
+
+def _sk_layout(scores, augmented):
+    B, r, c = scores.shape
+    m, n = (r - 1, c - 1) if augmented else (r, c)
+    return B, m, n, c, r * c
+
+
+def sinkhorn_train_forward(scores, alpha, iters, augmented=False):
+    """scores [B, m, n] (or, augmented, the [B, m+1, n+1] buffers of pair_scores whose inner blocks hold the scores),
+    alpha: device scalar tensor -> (couplings [B, m+1, n+1], potentials of every iteration)."""
+    lib = _lib.lib()
+    B, m, n, ld, stride = _sk_layout(scores, augmented)
     assert scores.is_contiguous() and alpha.dtype == torch.float32 and alpha.device == scores.device
     Z = torch.empty(B, m + 1, n + 1, dtype=torch.float32, device=scores.device)
     pot = torch.empty(lib.mvm_sinkhorn_train_pot_floats(B, m, n, iters), dtype=torch.float32, device=scores.device)
-    _lib.check(lib.mvm_sinkhorn_train_forward(_lib.ptr(scores), _lib.ptr(alpha), B, m, n, int(iters), _lib.ptr(Z),
+    _lib.check(lib.mvm_sinkhorn_train_forward(_lib.ptr(scores), ld, stride, _lib.ptr(alpha), B, m, n, int(iters), _lib.ptr(Z),
                                               _lib.ptr(pot), _lib.stream_ptr()), 'mvm_sinkhorn_train_forward')
     return Z, pot
 
 
-def sinkhorn_train_backward(scores, alpha, pot, iters, grad_out):
+def sinkhorn_train_backward(scores, alpha, pot, iters, grad_out, augmented=False):
     """-> (dZ [B, m+1, n+1]: gradient w.r.t. the augmented score matrix, d_alpha: [1] float64)."""
     lib = _lib.lib()
-    B, m, n = scores.shape
+    B, m, n, ld, stride = _sk_layout(scores, augmented)
     dZ = grad_out.detach().float().contiguous().clone()
     d_alpha = torch.zeros(1, dtype=torch.float64, device=scores.device)
-    _lib.check(lib.mvm_sinkhorn_train_backward(_lib.ptr(scores), _lib.ptr(alpha), _lib.ptr(pot), B, m, n, int(iters),
-                                               _lib.ptr(dZ), _lib.ptr(d_alpha), _lib.stream_ptr()),
+    _lib.check(lib.mvm_sinkhorn_train_backward(_lib.ptr(scores), ld, stride, _lib.ptr(alpha), _lib.ptr(pot), B, m, n,
+                                               int(iters), _lib.ptr(dZ), _lib.ptr(d_alpha), _lib.stream_ptr()),
                'mvm_sinkhorn_train_backward')
     return dZ, d_alpha

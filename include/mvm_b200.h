@@ -397,16 +397,26 @@ int mvm_attention_backward(const float* qkv, const float* out, const float* dout
  * 0 = fp32 CUDA cores (cross-check) */
 int mvm_debug_set_attention_backward_variant(int variant);
 
-/* log_optimal_transport for training (superglue.py:143-172): scores [batch, m, n] and the device scalar alpha
+/* Every (pair, tuple) score matrix of a call in one launch of the persistent tcgen05 GEMM (3xTF32):
+ * scores[p][bi] inner [m_p, n_p] block = mdesc[view a_p of tuple bi] . mdesc[view b_p of tuple bi]^T * alpha, written
+ * into buffers laid out [batch, m_p + 1, n_p + 1] (multi_view_matcher.py:278-280; the dustbin row / column are not
+ * touched).  mdesc: [batch * n_views * n_pad, 256] point-major; hi / lo: scratch of the same size; pa / pb / m / n and
+ * scores: host arrays of n_pairs entries (scores: device pointers). */
+int mvm_pair_scores(const float* mdesc, float* hi, float* lo, int batch, int n_views, int n_pad, int n_pairs, const int* pa,
+                    const int* pb, const int* m, const int* n, float* const* scores, float alpha, void* stream);
+
+/* log_optimal_transport for training (superglue.py:143-172): problem b reads its m x n scores at
+ * scores + b * scores_stride with row stride scores_ld (packed [batch, m, n]: ld = n, stride = m n; the inner block of
+ * the [batch, m+1, n+1] buffers mvm_pair_scores fills: ld = n + 1, stride = (m+1)(n+1)); alpha = device scalar
  * (bin_score) -> couplings out [batch, m+1, n+1], keeping the potentials of every iteration in pot
  * (mvm_sinkhorn_train_pot_floats floats); the backward turns dZ (gradient w.r.t. the couplings on entry) into the exact
  * gradient of the unrolled iterations w.r.t. the augmented score matrix (inner block = d scores) and adds the dustbin
- * entries to *d_alpha (device double, zeroed by the caller). */
+ * entries to *d_alpha (device double, zeroed by the caller).  m, n <= 1055. */
 size_t mvm_sinkhorn_train_pot_floats(int batch, int m, int n, int iters);
-int mvm_sinkhorn_train_forward(const float* scores, const float* alpha, int batch, int m, int n, int iters, float* out,
-                               float* pot, void* stream);
-int mvm_sinkhorn_train_backward(const float* scores, const float* alpha, const float* pot, int batch, int m, int n,
-                                int iters, float* dZ, double* d_alpha, void* stream);
+int mvm_sinkhorn_train_forward(const float* scores, long long scores_ld, long long scores_stride, const float* alpha, int batch,
+                               int m, int n, int iters, float* out, float* pot, void* stream);
+int mvm_sinkhorn_train_backward(const float* scores, long long scores_ld, long long scores_stride, const float* alpha,
+                                const float* pot, int batch, int m, int n, int iters, float* dZ, double* d_alpha, void* stream);
 
 /* compute_gt_matches_of_image_pair (helpers.py:121-203, with transform_kpts :115-119 and set_weight :205-213):
  * ground-truth assignment of an image pair from depth maps and poses, without the [bs, N, N] error matrix.

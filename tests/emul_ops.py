@@ -152,11 +152,23 @@ def _ot(scores, alpha, iters):
     return Z + u.unsqueeze(2) + v.unsqueeze(1) - norm
 
 
-def sinkhorn_train_forward(scores, alpha, iters):
+def pair_scores(md, pairs, N, alpha=1.0 / 16.0):
+    B = md.shape[0]
+    out = torch.zeros(len(pairs) * B, N + 1, N + 1)
+    for p, (a, b) in enumerate(pairs):
+        out[p * B:(p + 1) * B, :N, :N] = (alpha * (md[:, a, :N].to(D) @ md[:, b, :N].to(D).transpose(1, 2))).float()
+    return out
+
+
+def sinkhorn_train_forward(scores, alpha, iters, augmented=False):
+    if augmented:
+        scores = scores[:, :-1, :-1]
     return _ot(scores.to(D), alpha.to(D).reshape(()), iters).float(), None
 
 
-def sinkhorn_train_backward(scores, alpha, pot, iters, grad_out):
+def sinkhorn_train_backward(scores, alpha, pot, iters, grad_out, augmented=False):
+    if augmented:
+        scores = scores[:, :-1, :-1]
     """-> (dZ [B, m+1, n+1] with d scores in its inner block (the dustbin entries are folded into d_alpha), d_alpha [1])."""
     with torch.enable_grad():
         s = scores.to(D).clone().requires_grad_(True)

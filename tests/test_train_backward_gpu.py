@@ -140,6 +140,28 @@ def _loss(case, model, data):
     return loss
 
 
+def test_pair_scores_and_augmented_sinkhorn_layout():
+    """Score matrices of every (pair, tuple) in one launch (score mode of the persistent GEMM) into [B, N+1, N+1] buffers,
+    read in place by the Sinkhorn training kernels."""
+    from e2e_multi_view_matching_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, T, N, n_pad = 2, 3, 100, 128
+    md = torch.randn(B, T, n_pad, 256, generator=g)
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    ref = emul_ops.pair_scores(md, pairs, N)
+    got = ops.pair_scores(md.cuda(), pairs, N)
+    assert _rel(got[:, :N, :N], ref[:, :N, :N]) < 2e-6
+    alpha = torch.tensor([0.7])
+    Z_ref, _ = emul_ops.sinkhorn_train_forward(ref, alpha, 100, augmented=True)
+    Z, pot = ops.sinkhorn_train_forward(got, alpha.cuda(), 100, augmented=True)
+    G = torch.randn(Z_ref.shape, generator=g)
+    dZ_ref, da_ref = emul_ops.sinkhorn_train_backward(ref, alpha, None, 100, G, augmented=True)
+    dZ, da = ops.sinkhorn_train_backward(got, alpha.cuda(), pot, 100, G.cuda(), augmented=True)
+    torch.cuda.synchronize()
+    assert float((Z.cpu().double() - Z_ref.double()).abs().max()) < 5e-4
+    assert _rel(dZ[:, :N, :N], dZ_ref[:, :N, :N]) < 2e-4 and abs(float(da) - float(da_ref)) <= 2e-4 * abs(float(da_ref)) + 1e-6
+
+
 def _to_cpu(o):
     if torch.is_tensor(o):
         return o.detach().cpu()

@@ -14,7 +14,7 @@ import torch
 from tests import emul_ops
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-PATCHED = ['pack_views', 'linear', 'attention', 'attention_backward', 'transpose_split', 'linear_presplit', 'linear_presplit_splitk', 'colsum',
+PATCHED = ['pack_views', 'pair_scores', 'linear', 'attention', 'attention_backward', 'transpose_split', 'linear_presplit', 'linear_presplit_splitk', 'colsum',
            'batchnorm_train', 'batchnorm_train_backward', 'sinkhorn_train_forward', 'sinkhorn_train_backward']
 
 
