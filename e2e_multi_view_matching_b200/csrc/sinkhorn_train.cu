@@ -35,8 +35,10 @@ __device__ __forceinline__ float zin_(const float* __restrict__ sc, long long sl
 #define zin(sc, i, j, m, n, alpha) zin_(sc, sld, i, j, m, n, alpha)
 
 constexpr int CH = 416;   // columns merged per shared-memory round (13 x 32)
+constexpr int KB = 7;     // columns per thread whose loads are issued together
 
-// online log-sum-exp update with one exponential in the common case
+// online log-sum-exp update with one exponential in the common case.  Every exponent in this file is <= 0 (a difference
+// to a running maximum, or a log-probability): __expf (ex2.approx of x log2 e) is accurate to ~1e-7 relative there.
 __device__ __forceinline__ void lse_push(float& mx, float& s, float x) {
   if (x > mx) { s = s * expf(mx - x) + 1.f; mx = x; }
   else s += expf(x - mx);
@@ -67,8 +69,23 @@ __global__ void __launch_bounds__(1024) sinkhorn_train_fwd_kernel(const SkArgs g
     float* pot = g.pot + ((long long)b * g.iters + it) * (m + n + 2);
     // rows: u_i = log_mu_i - LSE_j(Z_ij + v_j)
     for (int i = warp; i <= m; i += 32) {
+      // chunks of KB columns in two phases: the loads of a chunk are in flight together before the dependent
+      // log-sum-exp chain consumes them (a load -> push -> load loop serialised 13 L2 latencies per row)
       float mx = -INFINITY, s = 0.f;
-      for (int j = lane; j <= n; j += 32) lse_push(mx, s, zin(sc, i, j, m, n, alpha) + v[j]);
+#pragma unroll
+      for (int k0 = 0; k0 < KC; k0 += KB) {
+        float z[KB];
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+          const int j = lane + 32 * (k0 + kk);
+          z[kk] = (k0 + kk < KC && j <= n) ? zin(sc, i, j, m, n, alpha) : 0.f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+          const int j = lane + 32 * (k0 + kk);
+          if (k0 + kk < KC && j <= n) lse_push(mx, s, z[kk] + v[j]);
+        }
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const float mo = __shfl_xor_sync(0xffffffffu, mx, o), so = __shfl_xor_sync(0xffffffffu, s, o);
@@ -84,9 +101,18 @@ __global__ void __launch_bounds__(1024) sinkhorn_train_fwd_kernel(const SkArgs g
     for (int i = warp; i <= m; i += 32) {
       const float ui = u[i];
 #pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const int j = lane + 32 * k;
-        if (j <= n) lse_push(cmx[k], csm[k], zin(sc, i, j, m, n, alpha) + ui);
+      for (int k0 = 0; k0 < KC; k0 += KB) {
+        float z[KB];
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+          const int j = lane + 32 * (k0 + kk);
+          z[kk] = (k0 + kk < KC && j <= n) ? zin(sc, i, j, m, n, alpha) : 0.f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+          const int j = lane + 32 * (k0 + kk);
+          if (k0 + kk < KC && j <= n) lse_push(cmx[k0 + kk], csm[k0 + kk], z[kk] + ui);
+        }
       }
     }
     for (int c0 = 0; c0 <= n; c0 += CH) {
@@ -174,13 +200,26 @@ __global__ void __launch_bounds__(1024) sinkhorn_train_bwd_kernel(const SkArgs g
     for (int i = warp; i <= m; i += 32) {
       const float ui = u[i];
       float a = 0.f;
+      // chunks of KB columns: all loads of a chunk first (the stores to dZ would otherwise order every later load behind
+      // them: the compiler cannot prove that dZ and the scores do not alias), then the exponentials, then the stores
 #pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const int j = lane + 32 * k;
-        if (j <= n) {
-          const float w = expf(zin(sc, i, j, m, n, alpha) + ui + v[j]) * gv[j];
-          dZ[(long long)i * ld + j] -= w;
-          a += w;
+      for (int k0 = 0; k0 < KC; k0 += KB) {
+        float z[KB], d[KB];
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+          const int j = lane + 32 * (k0 + kk);
+          const bool ok = k0 + kk < KC && j <= n;
+          z[kk] = ok ? zin(sc, i, j, m, n, alpha) : 0.f;
+          d[kk] = ok ? dZ[(long long)i * ld + j] : 0.f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+          const int j = lane + 32 * (k0 + kk);
+          if (k0 + kk < KC && j <= n) {
+            const float w = expf(z[kk] + ui + v[j]) * gv[j];
+            dZ[(long long)i * ld + j] = d[kk] - w;
+            a += w;
+          }
         }
       }
       a = warp_sum(a);
@@ -193,12 +232,23 @@ __global__ void __launch_bounds__(1024) sinkhorn_train_bwd_kernel(const SkArgs g
     for (int i = warp; i <= m; i += 32) {
       const float ui = u[i] - (i < m ? norm : log_mu_bin), gi = gu[i];
 #pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const int j = lane + 32 * k;
-        if (j <= n) {
-          const float w = expf(zin(sc, i, j, m, n, alpha) + ui + vp[j]) * gi;
-          dZ[(long long)i * ld + j] -= w;
-          acc[k] += w;
+      for (int k0 = 0; k0 < KC; k0 += KB) {
+        float z[KB], d[KB];
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+          const int j = lane + 32 * (k0 + kk);
+          const bool ok = k0 + kk < KC && j <= n;
+          z[kk] = ok ? zin(sc, i, j, m, n, alpha) : 0.f;
+          d[kk] = ok ? dZ[(long long)i * ld + j] : 0.f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < KB; ++kk) {
+          const int j = lane + 32 * (k0 + kk);
+          if (k0 + kk < KC && j <= n) {
+            const float w = expf(z[kk] + ui + vp[j]) * gi;
+            dZ[(long long)i * ld + j] = d[kk] - w;
+            acc[k0 + kk] += w;
+          }
         }
       }
     }

@@ -57,6 +57,20 @@ def test_eight_gpu_line_scales():
     assert eight['value'] > 0.95 * 8 * one['value']
 
 
+def test_training_line_cfg5():
+    """bench.py --config cfg5: training iterations per second (stage 1 of BASELINE configs[4])."""
+    d = _load('bench_r02_cfg5_e.json')
+    for k in REQUIRED:
+        assert k in d, k
+    assert d['unit'] == 'steps/s' and d['scaling'] == 'weak' and d['config']['workload'].startswith('train_stage1')
+    assert d['warmup'] >= 3 and d['gpu_launches'] > 1000 and d['value'] > 6.0
+    assert abs(d['value'] * d['ms_per_step'] - 1000.0) < 1.0 and d['tuples_per_s'] == d['value'] * d['units_per_step']
+    assert d['loss_first_last'][1] < 0.2 * d['loss_first_last'][0]              # the optimiser steps really train
+    assert d['e2e']['h2d_bytes_per_step'] > 1e7 and 'not built' in d['run']['stage']
+    first = _load('bench_r02_cfg5_a.json')
+    assert d['value'] > 3.0 * first['value']                                    # 2.1 -> 7.1 steps/s over the round
+
+
 def test_pair_config_lines():
     for name, unit_min in (('bench_r02_v14_cfg2.json', 2000), ('bench_r02_v14_cfg4.json', 400)):
         d = _load(name)

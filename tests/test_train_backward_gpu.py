@@ -150,7 +150,7 @@ def test_pair_scores_and_augmented_sinkhorn_layout():
     pairs = [(0, 1), (0, 2), (1, 2)]
     ref = emul_ops.pair_scores(md, pairs, N)
     got = ops.pair_scores(md.cuda(), pairs, N)
-    assert _rel(got[:, :N, :N], ref[:, :N, :N]) < 2e-6
+    assert _rel(got[:, :N, :N], ref[:, :N, :N]) < 1e-5
     alpha = torch.tensor([0.7])
     Z_ref, _ = emul_ops.sinkhorn_train_forward(ref, alpha, 100, augmented=True)
     Z, pot = ops.sinkhorn_train_forward(got, alpha.cuda(), 100, augmented=True)
