@@ -466,10 +466,18 @@ def run_train_arm(args, cfg, rank, world, local):
                                   'allreduce+optimizer': round(float(split[2]), 3)},
                 'stage_ms_per_step': {k: round(v[0] / 2, 4) for k, v in prof.items() if v[1] > 0},
                 'loss_first_last': [losses[0], losses[-1]], 'cpu_baseline': None}
-        emit(line)
-    if world > 1:
+        if world == 1:
+            emit(line)
+    if world > 1:       # the JSON line last: the other ranks tear their communicators down (and NCCL logs that) first
         dist.barrier()
-        dist.destroy_process_group()
+        if rank != 0:
+            dist.destroy_process_group()
+        else:
+            time.sleep(2.0)
+            dist.destroy_process_group()
+            emit(line)
+            if os.environ.get('NCCL_DEBUG', '').upper() in ('INFO', 'TRACE'):
+                os._exit(0)
 
 
 # ---------------------------------------------------------------------------------------------
