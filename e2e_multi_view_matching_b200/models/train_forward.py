@@ -315,11 +315,12 @@ def train_forward(model, data, view_ids=None, debug=None):
     """Result dict of the train branch.  With autograd enabled (and parameters that require grad) the `scores_*` tensors
     carry the graph of MatcherTrainFn; under torch.no_grad() this is a plain forward."""
     params = [p for p in model.parameters() if p.requires_grad]
-    if debug is None and torch.is_grad_enabled() and params:
-        holder = {}
-        outs = MatcherTrainFn.apply(model, data, view_ids, holder, *params)
-        result = dict(zip(holder.pop('__keys__'), outs))
-        result.update(holder)
-        return result
-    with torch.no_grad():
-        return _forward(model, data, view_ids, save=False, debug=debug)[0]
+    with _lib.device_ctx(data['keypoints0'].device):      # every launch of the call on the device of the inputs
+        if debug is None and torch.is_grad_enabled() and params:
+            holder = {}
+            outs = MatcherTrainFn.apply(model, data, view_ids, holder, *params)
+            result = dict(zip(holder.pop('__keys__'), outs))
+            result.update(holder)
+            return result
+        with torch.no_grad():
+            return _forward(model, data, view_ids, save=False, debug=debug)[0]

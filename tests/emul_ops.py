@@ -178,3 +178,20 @@ def sinkhorn_train_backward(scores, alpha, pot, iters, grad_out, augmented=False
     dZ = torch.zeros(b, m + 1, n + 1)
     dZ[:, :m, :n] = gs.float()
     return dZ, ga.reshape(1)
+
+
+def extract_matches(Z, match_threshold=0.0):
+    """multi_view_matcher.py:288-300 restated."""
+    inner = Z[:, :-1, :-1]
+    max0, max1 = inner.max(2), inner.max(1)
+    i0, i1 = max0.indices, max1.indices
+    ar0 = torch.arange(i0.shape[1])[None]
+    ar1 = torch.arange(i1.shape[1])[None]
+    mutual0 = ar0 == i1.gather(1, i0)
+    mutual1 = ar1 == i0.gather(1, i1)
+    zero = inner.new_tensor(0)
+    s0 = torch.where(mutual0, max0.values.exp(), zero)
+    s1 = torch.where(mutual1, s0.gather(1, i1), zero)
+    v0 = mutual0 & (s0 > match_threshold)
+    v1 = mutual1 & v0.gather(1, i1)
+    return torch.where(v0, i0, i0.new_tensor(-1)), torch.where(v1, i1, i1.new_tensor(-1)), s0, s1

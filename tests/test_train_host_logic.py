@@ -100,3 +100,54 @@ def test_no_grad_train_forward_has_no_graph(monkeypatch):
     with torch.no_grad():
         res = model(data)
     assert not res['scores_0_1'].requires_grad
+
+
+@pytest.mark.parametrize('name', ['mv3_64', 'pair_128'])
+def test_train_forward_full_output_orchestration_vs_reference(name, monkeypatch):
+    """The train-mode forward with `full_output` (match extraction + ConfidenceMLP with batch-statistics BatchNorm, the
+    per-view BatchNorm groups of the pairwise path, running statistics) on the stand-ins against the unmodified reference
+    in .train() (tests/golden/train_forward_*.npz)."""
+    from oracle.make_train_forward_golden import build, STATS
+    from tests.util import stable_rows
+    from e2e_multi_view_matching_b200 import ops, _lib
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    for f in PATCHED + ['extract_matches']:
+        monkeypatch.setattr(ops, f, getattr(emul_ops, f))
+    monkeypatch.setattr(_lib, 'require_cuda', lambda device, what: None)
+    z = np.load(os.path.join(GOLDEN, 'train_forward_%s.npz' % name))
+    case = json.loads(str(z['meta']))
+    sd, data_np = build(case)
+    model = MultiViewMatcher({'multi_frame_matching': case['multi'], 'GNN_layers': case['layers'], 'conf_mlp': True, 'full_output': True})
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model.train()
+    data = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
+    with torch.no_grad():
+        res = model(data)
+    keys = [k[5:] for k in z.files if k.startswith('f64__') and '__stat__' not in k and '__inter__' not in k]
+    assert sorted(k for k, v in res.items() if v is not None) == sorted(keys)
+    for k in sorted(keys):
+        r32, r64 = z['f32__' + k], z['f64__' + k]
+        got = res[k].numpy()
+        assert got.shape == r64.shape, k
+        if k.startswith('scores_'):
+            noise = float(np.abs(r32.astype(np.float64) - r64).max())
+            assert np.abs(got - r64).max() <= 3 * noise + 1e-5, (k, float(np.abs(got - r64).max()), noise)
+        elif k.startswith('matches'):
+            pair = k.split('_', 1)[1]
+            first = k[len('matches'):].split('_')[0] == pair.split('_')[0]
+            Z64, Z32 = z['f64__scores_' + pair], z['f32__scores_' + pair]
+            st0, st1 = stable_rows(Z64, 10.0 * float(np.abs(Z32.astype(np.float64) - Z64).max()))
+            st = st0 if first else st1
+            assert np.array_equal(got[st], r64[st]), (k, int((got[st] != r64[st]).sum()))
+        elif k.startswith('conf_scores'):
+            pair = k[len('conf_scores_'):]
+            same = res['matches%s_%s' % (pair.split('_')[0], pair)].numpy() == z['f64__matches%s_%s' % (pair.split('_')[0], pair)]
+            noise = float(np.abs(r32.astype(np.float64) - r64)[..., 0][same].max())
+            assert np.abs(got.astype(np.float64) - r64)[..., 0][same].max() <= 3 * noise + 1e-5, k
+    state = dict(model.state_dict())
+    for k in STATS:
+        st, r32, r64 = state[k].numpy(), z['f32__stat__' + k], z['f64__stat__' + k]
+        if k.endswith('num_batches_tracked'):
+            assert int(st) == int(r64), k
+        else:
+            assert np.abs(st.astype(np.float64) - r64).max() <= 3 * float(np.abs(r32.astype(np.float64) - r64).max()) + 1e-6, k
