@@ -449,7 +449,7 @@ def run_train_arm(args, cfg, rank, world, local):
         line = {'metric': cfg['metric'], 'value': args.steps / (ms_dev * 1e-3), 'unit': cfg['unit'], 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32 via split operands on tcgen05 (fp16x3 forward, tf32x3 backward GEMMs), f32 CUDA cores (attention backward, Sinkhorn, BatchNorm)',
+                'dtype': 'f32 via split operands on the tensor cores (fp16x3 forward, tf32x3 backward GEMMs and attention backward), f32 CUDA cores (Sinkhorn, BatchNorm)',
                 'data': 'synthetic', 'config': workload_config(cfg), 'units_per_step': B * world,
                 'tuples_per_s': B * world * args.steps / (ms_dev * 1e-3),
                 'run': {'tuples_per_step_per_gpu': B, 'l2': 'flushed between timed steps (256 MB write)', 'parallelism': 'dp%d' % world,
@@ -458,10 +458,10 @@ def run_train_arm(args, cfg, rank, world, local):
                 'e2e': {'value': args.steps / (ms_e2e * 1e-3), 'unit': cfg['unit'], 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                         'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': int(launches), 'clocks': sampler.summary(),
-                'roofline': {'kernel': 'attention forward (tcgen05 fp16x3) + backward (fp32 CUDA cores, flash-style recomputation)',
+                'roofline': {'kernel': 'attention forward (tcgen05 fp16x3) + backward (mma.sync TF32 x 3 split passes, flash-style recomputation)',
                              'bound': 'tensor', 'achieved': att_tflops, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
                              'frac': att_tflops / peaks['tflops'], 'traffic': None, 'launches_timed': att_n, 'peak_source': peaks['source'],
-                             'note': 'the backward kernels are the functional first version on the CUDA cores; their tcgen05 port is the next step'},
+                             'note': 'the backward runs on the legacy mma.sync path with register fragments; its tcgen05 port is the next step'},
                 'step_split_ms': {'forward+loss': round(float(split[0]), 3), 'backward': round(float(split[1]), 3),
                                   'allreduce+optimizer': round(float(split[2]), 3)},
                 'stage_ms_per_step': {k: round(v[0] / 2, 4) for k, v in prof.items() if v[1] > 0},

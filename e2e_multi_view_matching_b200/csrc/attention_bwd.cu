@@ -348,6 +348,7 @@ __device__ __forceinline__ void warp_mma(float (&acc)[4][4], const float* __rest
     uint32_t ahi[4], alo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) split_tf32(af[i], ahi[i], alo[i]);
+    uint32_t bhi[4][2], blo[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int n = n0 + nt * 8 + gid;
@@ -355,13 +356,18 @@ __device__ __forceinline__ void warp_mma(float (&acc)[4][4], const float* __rest
       if (PAIR) { const float2 x = *reinterpret_cast<const float2*>(B + n * LDM + k0 + 2 * tig); bf[0] = x.x; bf[1] = x.y; }
       else if (B_T) { bf[0] = B[n * LDM + k0 + tig]; bf[1] = B[n * LDM + k0 + tig + 4]; }
       else     { bf[0] = B[(k0 + tig) * LDM + n]; bf[1] = B[(k0 + tig + 4) * LDM + n]; }
-      uint32_t bhi[2], blo[2];
-      split_tf32(bf[0], bhi[0], blo[0]);
-      split_tf32(bf[1], bhi[1], blo[1]);
-      mma_tf32(acc[nt], alo, bhi);
-      mma_tf32(acc[nt], ahi, blo);
-      mma_tf32(acc[nt], ahi, bhi);
+      split_tf32(bf[0], bhi[nt][0], blo[nt][0]);
+      split_tf32(bf[1], bhi[nt][1], blo[nt][1]);
     }
+    // the three passes of a product go to the same accumulator: issue them pass-major, so that four independent MMAs sit
+    // between two dependent ones (the ncu capture of the nt-major order had `wait` -- fixed-latency dependencies -- as its
+    // top stall reason)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], alo, bhi[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ahi, blo[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ahi, bhi[nt]);
   }
 }
 
