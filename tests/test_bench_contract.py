@@ -59,16 +59,18 @@ def test_eight_gpu_line_scales():
 
 def test_training_line_cfg5():
     """bench.py --config cfg5: training iterations per second (stage 1 of BASELINE configs[4])."""
-    d = _load('bench_r02_cfg5_e.json')
+    d = _load('bench_r02_cfg5_h.json')
     for k in REQUIRED:
         assert k in d, k
     assert d['unit'] == 'steps/s' and d['scaling'] == 'weak' and d['config']['workload'].startswith('train_stage1')
-    assert d['warmup'] >= 3 and d['gpu_launches'] > 1000 and d['value'] > 6.0
+    assert d['warmup'] >= 3 and d['gpu_launches'] > 1000 and d['value'] > 7.0
     assert abs(d['value'] * d['ms_per_step'] - 1000.0) < 1.0 and d['tuples_per_s'] == d['value'] * d['units_per_step']
     assert d['loss_first_last'][1] < 0.2 * d['loss_first_last'][0]              # the optimiser steps really train
     assert d['e2e']['h2d_bytes_per_step'] > 1e7 and 'not built' in d['run']['stage']
     first = _load('bench_r02_cfg5_a.json')
-    assert d['value'] > 3.0 * first['value']                                    # 2.1 -> 7.1 steps/s over the round
+    assert d['value'] > 3.0 * first['value']                                    # 2.1 -> 7.4 steps/s over the round
+    two = _load('bench_r02_cfg5_2gpu.json')                                     # data parallel, gradient all-reduce over NCCL
+    assert two['n_gpus'] == 2 and two['tuples_per_s'] > 1.9 * d['tuples_per_s'] and 'all-reduce' in two['run']['collective']
 
 
 def test_pair_config_lines():
