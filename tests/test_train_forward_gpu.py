@@ -103,3 +103,18 @@ def test_train_forward_output_gating_and_eval_unchanged():
     assert not torch.equal(rm, model.kenc.encoder[1].running_mean)
     after = model.eval()(data)['scores_0_1']
     assert not torch.equal(before, after)                            # the packed weights were rebuilt from the new buffers
+
+
+def test_full_output_with_autograd_on_the_kernels():
+    """`full_output` + autograd: couplings with MatcherTrainFn's graph, match / confidence outputs beside them; backward
+    fills every matcher parameter's gradient with finite values."""
+    from oracle.make_train_forward_golden import build, CASES
+    case = CASES[0]
+    sd, data_np = build(case)
+    model = _model(case, sd, full_output=True)
+    data = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
+    res = model(data)
+    assert res['scores_0_1'].requires_grad and not res['conf_scores_0_1'].requires_grad and res['matches0_0_1'].dtype == torch.int64
+    sum(res['scores_%s' % k].square().mean() for k in ('0_1', '0_2', '1_2')).backward()
+    named = dict(model.named_parameters())
+    assert all(named[k].grad is not None and torch.isfinite(named[k].grad).all() for k in named if not k.startswith('conf_mlp'))

@@ -151,3 +151,29 @@ def test_train_forward_full_output_orchestration_vs_reference(name, monkeypatch)
             assert int(st) == int(r64), k
         else:
             assert np.abs(st.astype(np.float64) - r64).max() <= 3 * float(np.abs(r32.astype(np.float64) - r64).max()) + 1e-6, k
+
+
+def test_full_output_with_autograd_keeps_the_extra_outputs(monkeypatch):
+    """`full_output` with autograd enabled: the couplings carry MatcherTrainFn's graph, the match / confidence outputs come
+    back beside them without one, and the backward still reaches every matcher parameter."""
+    from oracle.make_train_backward_golden import build, CASES
+    from e2e_multi_view_matching_b200 import ops, _lib
+    from e2e_multi_view_matching_b200.models.multi_view_matcher import MultiViewMatcher
+    for f in PATCHED + ['extract_matches']:
+        monkeypatch.setattr(ops, f, getattr(emul_ops, f))
+    monkeypatch.setattr(_lib, 'require_cuda', lambda device, what: None)
+    case = CASES[0]
+    data_np, sd = build(case)
+    model = MultiViewMatcher({'multi_frame_matching': True, 'GNN_layers': case['layers'], 'conf_mlp': True, 'full_output': True})
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model.train()
+    data = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in data_np.items()}
+    res = model(data)
+    assert res['scores_0_1'].requires_grad and not res['conf_scores_0_1'].requires_grad
+    assert res['matches0_0_1'].dtype == torch.int64 and res['matching_scores2_0_2'].shape == res['matches2_0_2'].shape
+    assert sorted(k.split('_')[0] for k in res) == sorted(['scores'] * 3 + ['matches0', 'matches1', 'matches0', 'matches2', 'matches1', 'matches2'] +
+                                                           ['matching'] * 6 + ['conf'] * 3)
+    sum(res['scores_%s' % k].sum() for k in ('0_1', '0_2', '1_2')).backward()
+    named = dict(model.named_parameters())
+    assert all(named[k].grad is not None for k in named if not k.startswith('conf_mlp'))
+    assert all(named[k].grad is None for k in named if k.startswith('conf_mlp'))        # no graph through the confidences
