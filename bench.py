@@ -442,9 +442,11 @@ def run_train_arm(args, cfg, rank, world, local):
     if rank == 0:
         peaks = load_peaks()
         att_ms, att_n = prof['attention']
-        # forward QK^T + PV (4 N M D per view and layer) and the backward's recomputation + four gradient products
-        # (QK^T twice, dO V^T twice, dS K, dS^T Q, P^T dO = 7 products of 2 N M D): 4 + 14 = 18 N M D
-        att_flops = attention_flops(cfg) * B * 2 * (18.0 / 4.0)
+        # algorithmic work: forward QK^T + PV (4 N M D per view and layer) + the five products of a memory-efficient
+        # backward (S recomputed once, dP = dO V^T, dQ = dS K, dK = dS^T Q, dV = P^T dO: 10 N M D) = 14 N M D.  The two
+        # backward kernels EXECUTE eight (S three times, dP twice); the lines committed as profiles/bench_r02_cfg5_*.json
+        # were taken with 18 N M D in this place.
+        att_flops = attention_flops(cfg) * B * 2 * (14.0 / 4.0)
         att_tflops = att_flops / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
         line = {'metric': cfg['metric'], 'value': args.steps / (ms_dev * 1e-3), 'unit': cfg['unit'], 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
