@@ -177,3 +177,17 @@ def test_full_output_with_autograd_keeps_the_extra_outputs(monkeypatch):
     named = dict(model.named_parameters())
     assert all(named[k].grad is not None for k in named if not k.startswith('conf_mlp'))
     assert all(named[k].grad is None for k in named if k.startswith('conf_mlp'))        # no graph through the confidences
+
+
+def test_landmark_gt_matches_equals_the_golden_generator():
+    """synthetic.landmark_gt_matches (ground truth of the training bench) == the per-item construction the reference goldens
+    were generated with (oracle/make_validation_golden.gt_from_landmarks: helpers.py:190-213 weights)."""
+    from e2e_multi_view_matching_b200.synthetic import landmark_gt_matches, make_scene_tuple_inputs
+    from oracle.make_validation_golden import gt_from_landmarks
+    d = make_scene_tuple_inputs(3, n_views=3, n_kpts=100, batch=2)
+    for a, b in ((0, 1), (0, 2), (1, 2)):
+        idx, w = landmark_gt_matches(d['landmark%d' % a], d['landmark%d' % b])
+        for i in range(2):
+            ri, rw = gt_from_landmarks(d['landmark%d' % a][i], d['landmark%d' % b][i])
+            assert np.array_equal(ri, idx[i]) and np.allclose(rw, w[i], rtol=1e-6)
+        assert idx.dtype == np.int64 and w.dtype == np.float32 and (idx[:, :, -1] == -1).all()
