@@ -1,5 +1,5 @@
 """TRAINING-path kernels: every backward / staging kernel against the float64 torch stand-ins of
-tests/emul_ops.py on seeded inputs, then the whole training step (MatcherTrainFn forward + backward on the kernels, the
+oracle/train_ops.py on seeded inputs, then the whole training step (MatcherTrainFn forward + backward on the kernels, the
 CUDA match loss) against the gradients of the unmodified reference (tests/golden/train_backward_*.npz)."""
 import json
 import os

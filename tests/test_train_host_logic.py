@@ -1,6 +1,6 @@
 """Host-side orchestration of the TRAINING step (models/train_forward.py: MatcherTrainFn forward + backward) against the
 gradients of the unmodified reference (tests/golden/train_backward_*.npz, oracle/make_train_backward_golden.py), with the
-stage kernels replaced by the float64 torch stand-ins of tests/emul_ops.py -- runs without a GPU.  What it pins: which
+stage kernels replaced by the float64 torch stand-ins of oracle/train_ops.py -- runs without a GPU.  What it pins: which
 tensors are saved, the head permutation of q/k/v/merge and its inverse on the gradients, the concat / residual routing,
 the per-view BatchNorm groups of the pairwise path, the pair loops and the accumulation over pairs.  The kernels
 themselves are checked against the same stand-ins on the GPU (tests/test_train_backward_gpu.py)."""

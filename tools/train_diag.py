@@ -1,4 +1,4 @@
-"""Stage-by-stage error of the training step on the GPU: the kernels against the float64 stand-ins (tests/emul_ops.py,
+"""Stage-by-stage error of the training step on the GPU: the kernels against the float64 stand-ins (oracle/train_ops.py,
 run on the CPU of the same box) on one of the reference golden cases -- forward activations per layer, then every
 gradient of the backward per layer.  Usage: python tools/train_diag.py [case]   (default mv3_64)"""
 import json

@@ -1,5 +1,5 @@
 """CPU experiment behind the gradient tolerances of tests/test_train_backward_gpu.py: the training step on the float64
-stand-ins (tests/emul_ops.py), once exact and four times with the FORWARD GEMM outputs perturbed by 1e-6 of their maximum
+stand-ins (oracle/train_ops.py), once exact and four times with the FORWARD GEMM outputs perturbed by 1e-6 of their maximum
 (the size of the GPU forward's rounding, 2e-6 max-norm): a pre-ReLU activation within that distance of zero changes
 sign, its ReLU mask flips, and the gradient w.r.t. the MLP hidden layer (g_hid) moves by 1e-2 .. 1e-1 of its maximum at
 that element -- orders of magnitude above rounding -- which reaches the keypoint-encoder gradient as 3e-3 .. 7e-3.
