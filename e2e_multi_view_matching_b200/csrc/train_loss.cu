@@ -1,4 +1,4 @@
-// Training-side consumers of the matcher output (first slice of f-2): the weighted negative
+// Training-side consumers of the matcher output: the weighted negative
 // log-likelihood of the ground-truth assignment on the log-coupling matrix, compute_match_loss (helpers.py:228-241),
 // forward and backward.  log_p [bs, ft, ft] (ft = keypoints + 1 dustbin), gt_indices [bs, 2, ft] int64 (index of the
 // partner in the other view, -1 = last = dustbin, Python negative indexing), gt_weights [bs, 2, ft]:

@@ -1,4 +1,4 @@
-"""First slice of the training path: compute_match_loss kernels (forward + backward) and the
+"""Training consumers: compute_match_loss kernels (forward + backward) and the
 exact unrolled-iteration gradient of log_optimal_transport, against autograd through the CPU restatement of the
 reference's functions (helpers.py:228-241, superglue.py:143-172) in double precision."""
 import os
