@@ -354,7 +354,7 @@ int mvm_superpoint_dense(const mvm_superpoint_weights* w, const float* image, in
 int mvm_superpoint_sample(const float* dense_desc, const float* keypoints, int n, int h, int w, float* descriptors,
                           void* stream);
 
-/* ---- training-side consumers (first slice of SURVEY.md §8 f-2) ----------------------------------------------- */
+/* ---- training path: losses, ground-truth matches, train-mode BatchNorm, backward kernels ---- */
 
 /* compute_match_loss (helpers.py:228-241): weighted NLL of the ground-truth assignment on the log-couplings.
  * log_p [bs, ft, ft] (ft = keypoints + 1), gt_indices [bs, 2, ft] int64 (-1 = dustbin = last index), gt_weights
